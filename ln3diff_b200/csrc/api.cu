@@ -1,0 +1,107 @@
+// extern "C" surface of libln3b200 + shared host utilities (error text, tensor-map encoding).
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "ln3_internal.h"
+
+namespace ln3 {
+
+static thread_local char g_err[512] = "";
+static std::atomic<unsigned long long> g_launches{0};
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+void count_launch(int n) { g_launches.fetch_add(static_cast<unsigned long long>(n)); }
+
+int device_sm_count() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 1;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 1;
+  }
+  return sms;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || p == nullptr) {
+      set_error(LN3_ECUDA, "cuTensorMapEncodeTiled entry point unavailable: %s",
+                cudaGetErrorString(e));
+      return nullptr;
+    }
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+int make_tmap_2d_bf16(CUtensorMap* out, const void* ptr, long long rows, long long cols,
+                      long long ld, int box_rows, int box_cols) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return LN3_ECUDA;
+  if (box_cols != 64) return set_error(LN3_EINVAL, "tmap: box_cols must be 64 (128B swizzle)");
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(LN3_ECUDA, "cuTensorMapEncodeTiled(2d rows=%lld cols=%lld ld=%lld) -> %d", rows,
+                     cols, ld, static_cast<int>(r));
+  return LN3_OK;
+}
+
+int make_tmap_3d_bf16(CUtensorMap* out, const void* ptr, long long d0, long long d1, long long d2,
+                      long long s1, long long s2, int box0, int box1) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return LN3_ECUDA;
+  if (box0 != 64) return set_error(LN3_EINVAL, "tmap: box0 must be 64 (128B swizzle)");
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(d0), static_cast<cuuint64_t>(d1),
+                        static_cast<cuuint64_t>(d2)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(s1) * 2, static_cast<cuuint64_t>(s2) * 2};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(box0), static_cast<cuuint32_t>(box1), 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(LN3_ECUDA, "cuTensorMapEncodeTiled(3d %lldx%lldx%lld) -> %d", d2, d1, d0,
+                     static_cast<int>(r));
+  return LN3_OK;
+}
+
+}  // namespace ln3
+
+using namespace ln3;
+
+extern "C" {
+
+int ln3_abi_version(void) { return LN3_ABI_VERSION; }
+const char* ln3_last_error(void) { return g_err; }
+unsigned long long ln3_launch_count(void) { return g_launches.load(); }
+
+int ln3_gemm_bf16(const ln3_gemm_args* args, void* stream) {
+  if (!args) return set_error(LN3_EINVAL, "gemm: null args");
+  return gemm_bf16(args, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

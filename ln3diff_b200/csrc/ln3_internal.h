@@ -1,0 +1,26 @@
+// Internal declarations shared by the translation units of libln3b200.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "../../include/ln3b200.h"
+
+namespace ln3 {
+
+// Records a thread-local error message and returns `code` (so `return set_error(...)` works).
+int set_error(int code, const char* fmt, ...);
+void count_launch(int n = 1);
+int device_sm_count();
+
+// 2-D bf16 tensor map: tensor [rows, cols] with row pitch `ld` elements, box [box_rows, box_cols],
+// 128-byte swizzle (box_cols must be 64), zero fill out of bounds.
+int make_tmap_2d_bf16(CUtensorMap* out, const void* ptr, long long rows, long long cols,
+                      long long ld, int box_rows, int box_cols);
+// 3-D bf16 tensor map: tensor [d2, d1, d0] (d0 contiguous) with element strides (s2, s1, 1),
+// box [1, box1, box0], 128-byte swizzle.
+int make_tmap_3d_bf16(CUtensorMap* out, const void* ptr, long long d0, long long d1, long long d2,
+                      long long s1, long long s2, int box0, int box1);
+
+int gemm_bf16(const ln3_gemm_args* a, cudaStream_t stream);
+
+}  // namespace ln3
