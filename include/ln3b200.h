@@ -68,6 +68,126 @@ typedef struct ln3_gemm_args {
 
 int ln3_gemm_bf16(const ln3_gemm_args* args, void* stream);
 
+/* ------------------------------------------------------------------ attention (tcgen05)
+ * out[b, i, h*64:(h+1)*64] = softmax(q_h k_h^T * scale) v_h, no mask: replaces
+ * xformers.ops.memory_efficient_attention at vit/vision_transformer.py:114-118 (packed qkv of
+ * MemEffAttention), ldm/modules/attention.py:279-307 (cross-attention, incl. its three
+ * permute+contiguous copies) and the DiT2 decoder attention (dit/dit_decoder.py).
+ * q/k/v/out are bf16; head h of row i of batch b lives at ptr + b*bs + i*ld + h*64, so a packed
+ * (B, N, 3, H, 64) qkv buffer is addressed as q = base, k = base + H*64, v = base + 2*H*64 with
+ * ld = 3*H*64.  Lq and Lkv are arbitrary (tails are zero-filled by TMA and masked).
+ * head_dim must be 64 (every registry entry on the path except DiT-XL).
+ */
+typedef struct ln3_fmha_args {
+  const void* q;
+  const void* k;
+  const void* v;
+  void* out;
+  int B, H, Lq, Lkv, head_dim;
+  long long q_ld, q_bs, k_ld, k_bs, v_ld, v_bs, o_ld, o_bs; /* elements */
+  float scale;
+} ln3_fmha_args;
+
+int ln3_fmha_fwd(const ln3_fmha_args* args, void* stream);
+
+/* ------------------------------------------------------------------ norm + modulate (adaLN)
+ * out_bf16[r, :] = norm(x[r, :]) * (1 + scale[g(r), :] (+ scale_tab)) + shift[g(r), :] (+ shift_tab)
+ * with g(r) = r / mod_rows.  Replaces `modulate(self.norm1(x), shift, scale)` /
+ * `t2i_modulate(...)` (dit/dit_models_xformers.py:47-53, 285-294, 518-530) and `modulate2` with
+ * per-token operands (dit/dit_decoder.py:15-17; mod_rows = 1), producing the bf16 GEMM operand.
+ *   norm = LN3_NORM_LAYER: LayerNorm without affine, biased variance, eps (1e-6 on the path)
+ *          LN3_NORM_RMS  : x * rsqrt(mean(x^2) + eps) * weight        (dit/norm.py:27-40)
+ *          LN3_NORM_NONE : identity (plain fp32 -> bf16 cast, optional activation LN3_ACT_*)
+ * shift/scale NULL -> no modulation.  D must be a multiple of 128 and <= 2048.
+ */
+enum { LN3_NORM_NONE = 0, LN3_NORM_LAYER = 1, LN3_NORM_RMS = 2 };
+
+typedef struct ln3_norm_modulate_args {
+  const float* x;     /* [rows, ldx] */
+  void* out;          /* bf16 [rows, ldo] */
+  const float* shift; /* [groups, mod_ld] or NULL */
+  const float* scale;
+  const float* shift_tab; /* [D] or NULL: PixArt scale_shift_table rows */
+  const float* scale_tab;
+  const float* weight;    /* RMS weight [D] or NULL */
+  int rows, D;
+  long long ldx, ldo, mod_ld;
+  int mod_rows;
+  int norm;
+  int act;            /* applied last (only with LN3_NORM_NONE) */
+  float eps;
+} ln3_norm_modulate_args;
+
+int ln3_norm_modulate(const ln3_norm_modulate_args* args, void* stream);
+
+/* ------------------------------------------------------------------ timestep embedding
+ * out_bf16[b, 0:128] = cos(t_b f_i), out[b, 128:256] = sin(t_b f_i), f_i = exp(-ln(1e4) i/128):
+ * TimestepEmbedder.timestep_embedding (dit/dit_models_xformers.py:97-121), dim 256.
+ */
+int ln3_timestep_embedding(const float* t, int B, void* out_bf16, void* stream);
+
+/* ------------------------------------------------------------------ patch embed (roll-out)
+ * tokens[b, n*L + l, :] = Conv2d(k=s=2)(x[b, c*3+n, :, :])[l] + bias + pos_embed[n*L + l, :]
+ * i.e. rearrange 'b (c n) h w -> (b n) c h w' + timm PatchEmbed + pos_embed
+ * (dit/dit_trilatent.py:93-99).  x fp32 (B, 3*Cin, S, S) optionally pre-scaled per sample by
+ * in_scale[b] (the denoiser's c_in, sgm/modules/diffusionmodules/denoiser.py:34-42);
+ * weight fp32 (D, Cin, 2, 2); tokens fp32 (B, 3*(S/2)^2, D).
+ */
+typedef struct ln3_patch_embed_args {
+  const float* x;
+  const float* in_scale; /* [B] or NULL */
+  const float* weight;
+  const float* bias;
+  const float* pos_embed; /* [3*L, D] or NULL */
+  float* tokens;
+  int B, Cin, S, D;
+} ln3_patch_embed_args;
+
+int ln3_patch_embed(const ln3_patch_embed_args* args, void* stream);
+
+/* ------------------------------------------------------------------ final layer + unpatchify
+ * FinalLayer / T2IFinalLayer (dit/dit_models_xformers.py:61-84, 655-678): LayerNorm(no affine,
+ * eps 1e-6) -> modulate(shift, scale (+ tables)) -> Linear(D -> 4*Cout) -> unpatchify ->
+ * '(b n) c h w -> b (c n) h w' (dit/dit_trilatent.py:130-140), fp32 contiguous output
+ * (B, 3*Cout, S, S).  shift/scale are [B, mod_ld] rows.
+ */
+typedef struct ln3_final_layer_args {
+  const float* x; /* tokens [B, 3*L, D] */
+  const float* shift;
+  const float* scale;
+  const float* shift_tab;
+  const float* scale_tab;
+  const float* weight; /* [4*Cout, D] fp32 */
+  const float* bias;   /* [4*Cout] */
+  float* out;
+  int B, S, D, Cout;
+  long long mod_ld;
+} ln3_final_layer_args;
+
+int ln3_final_layer(const ln3_final_layer_args* args, void* stream);
+
+/* ------------------------------------------------------------------ fused sampler update
+ * x_out[b] = a[b] * x[b] + w0[b] * m0[b] + w1[b] * m1[b] + s[b] * noise[b]   (per-sample scalars)
+ * One launch per step covering (SURVEY.md section 8a row S*):
+ *   Euler-EDM + EpsScaling + VanillaCFG  sgm/modules/diffusionmodules/sampling.py:93-107,
+ *       denoiser.py:25-42, guiders.py:24-31, sampling_utils.py:34-35  (m0 = uncond, m1 = cond)
+ *   DDPM p_sample (eps/x0/v, fixed variance)  guided_diffusion/gaussian_diffusion.py:273-546
+ *   flow-matching Euler + CFG              transport/integrators.py:101-120, dit/dit_i23d.py:155-168
+ * coef is [B, 4] = (a, w0, w1, s); m1 / noise may be NULL when their weight is unused.
+ */
+typedef struct ln3_sampler_update_args {
+  const float* x;
+  const float* m0;
+  const float* m1;
+  const float* noise;
+  const float* coef;
+  float* x_out;
+  int B;
+  long long n_per_sample;
+} ln3_sampler_update_args;
+
+int ln3_sampler_affine_update(const ln3_sampler_update_args* args, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

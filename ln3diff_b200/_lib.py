@@ -30,6 +30,55 @@ class GemmArgs(C.Structure):
     ]
 
 
+class FmhaArgs(C.Structure):
+    _fields_ = [
+        ("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p), ("out", C.c_void_p),
+        ("B", C.c_int), ("H", C.c_int), ("Lq", C.c_int), ("Lkv", C.c_int), ("head_dim", C.c_int),
+        ("q_ld", C.c_longlong), ("q_bs", C.c_longlong), ("k_ld", C.c_longlong),
+        ("k_bs", C.c_longlong), ("v_ld", C.c_longlong), ("v_bs", C.c_longlong),
+        ("o_ld", C.c_longlong), ("o_bs", C.c_longlong),
+        ("scale", C.c_float),
+    ]
+
+
+class NormModulateArgs(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("out", C.c_void_p), ("shift", C.c_void_p), ("scale", C.c_void_p),
+        ("shift_tab", C.c_void_p), ("scale_tab", C.c_void_p), ("weight", C.c_void_p),
+        ("rows", C.c_int), ("D", C.c_int),
+        ("ldx", C.c_longlong), ("ldo", C.c_longlong), ("mod_ld", C.c_longlong),
+        ("mod_rows", C.c_int), ("norm", C.c_int), ("act", C.c_int), ("eps", C.c_float),
+    ]
+
+
+class PatchEmbedArgs(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("in_scale", C.c_void_p), ("weight", C.c_void_p), ("bias", C.c_void_p),
+        ("pos_embed", C.c_void_p), ("tokens", C.c_void_p),
+        ("B", C.c_int), ("Cin", C.c_int), ("S", C.c_int), ("D", C.c_int),
+    ]
+
+
+class FinalLayerArgs(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("shift", C.c_void_p), ("scale", C.c_void_p), ("shift_tab", C.c_void_p),
+        ("scale_tab", C.c_void_p), ("weight", C.c_void_p), ("bias", C.c_void_p), ("out", C.c_void_p),
+        ("B", C.c_int), ("S", C.c_int), ("D", C.c_int), ("Cout", C.c_int),
+        ("mod_ld", C.c_longlong),
+    ]
+
+
+class SamplerUpdateArgs(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("m0", C.c_void_p), ("m1", C.c_void_p), ("noise", C.c_void_p),
+        ("coef", C.c_void_p), ("x_out", C.c_void_p),
+        ("B", C.c_int), ("n_per_sample", C.c_longlong),
+    ]
+
+
+NORM_NONE, NORM_LAYER, NORM_RMS = 0, 1, 2
+
+
 def lib() -> C.CDLL:
     """Load libln3b200.so (once).  Raises if it has not been built -- no silent fallback."""
     global _lib

@@ -104,4 +104,29 @@ int ln3_gemm_bf16(const ln3_gemm_args* args, void* stream) {
   return gemm_bf16(args, static_cast<cudaStream_t>(stream));
 }
 
+int ln3_fmha_fwd(const ln3_fmha_args* args, void* stream) {
+  if (!args) return set_error(LN3_EINVAL, "fmha: null args");
+  return fmha_fwd(args, static_cast<cudaStream_t>(stream));
+}
+int ln3_norm_modulate(const ln3_norm_modulate_args* args, void* stream) {
+  if (!args) return set_error(LN3_EINVAL, "norm_modulate: null args");
+  return norm_modulate(args, static_cast<cudaStream_t>(stream));
+}
+int ln3_timestep_embedding(const float* t, int B, void* out_bf16, void* stream) {
+  if (!t || !out_bf16) return set_error(LN3_EINVAL, "timestep_embedding: null pointer");
+  return timestep_embedding(t, B, out_bf16, static_cast<cudaStream_t>(stream));
+}
+int ln3_patch_embed(const ln3_patch_embed_args* args, void* stream) {
+  if (!args) return set_error(LN3_EINVAL, "patch_embed: null args");
+  return patch_embed(args, static_cast<cudaStream_t>(stream));
+}
+int ln3_final_layer(const ln3_final_layer_args* args, void* stream) {
+  if (!args) return set_error(LN3_EINVAL, "final_layer: null args");
+  return final_layer(args, static_cast<cudaStream_t>(stream));
+}
+int ln3_sampler_affine_update(const ln3_sampler_update_args* args, void* stream) {
+  if (!args) return set_error(LN3_EINVAL, "sampler_update: null args");
+  return sampler_affine_update(args, static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

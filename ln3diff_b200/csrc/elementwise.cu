@@ -1,0 +1,331 @@
+// HBM-bound glue kernels of the DiT / sampler path (fp32 SIMT, vectorised, coalesced):
+//   norm_modulate      LayerNorm/RMSNorm + adaLN modulate -> bf16 GEMM operand
+//   timestep_embedding sinusoidal features of the timestep
+//   patch_embed        roll-out rearrange + 2x2 patch conv + pos_embed -> fp32 token stream
+//   final_layer        LN + modulate + Linear(D -> 4*Cout) + unpatchify -> fp32 latent layout
+//   sampler_update     x' = a x + w0 m0 + w1 m1 + s noise (all sampler engines, one launch/step)
+// Reference call sites are cited per kernel in include/ln3b200.h.
+#include "common.cuh"
+#include "ln3_internal.h"
+
+namespace ln3 {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == LN3_ACT_SILU) return silu(v);
+  if (act == LN3_ACT_GELU_ERF) return gelu_erf(v);
+  if (act == LN3_ACT_GELU_TANH) return gelu_tanh(v);
+  return v;
+}
+
+// ------------------------------------------------------------------ norm + modulate
+// One warp per row; the row lives in registers (NV float4 per lane, D = 128 * NV).
+template <int NV>
+__global__ void __launch_bounds__(256)
+norm_modulate_kernel(const ln3_norm_modulate_args a) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= a.rows) return;
+  const int lane = threadIdx.x & 31;
+  const float* x = a.x + static_cast<long long>(row) * a.ldx;
+  float4 v[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = *reinterpret_cast<const float4*>(x + (i * 32 + lane) * 4);
+
+  float mean = 0.f, rstd = 1.f;
+  if (a.norm == LN3_NORM_LAYER) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    mean = warp_sum(s) / static_cast<float>(a.D);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
+      q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+    }
+    rstd = rsqrtf(warp_sum(q) / static_cast<float>(a.D) + a.eps);
+  } else if (a.norm == LN3_NORM_RMS) {
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+      q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+    rstd = rsqrtf(warp_sum(q) / static_cast<float>(a.D) + a.eps);
+  }
+  const float* sh = nullptr;
+  const float* sc = nullptr;
+  if (a.shift != nullptr) {
+    const long long g = row / a.mod_rows;
+    sh = a.shift + g * a.mod_ld;
+    sc = a.scale + g * a.mod_ld;
+  }
+  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(a.out) + static_cast<long long>(row) * a.ldo;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    float4 y = make_float4((v[i].x - mean) * rstd, (v[i].y - mean) * rstd, (v[i].z - mean) * rstd,
+                           (v[i].w - mean) * rstd);
+    if (a.weight != nullptr) {
+      const float4 w = __ldg(reinterpret_cast<const float4*>(a.weight + c));
+      y.x *= w.x; y.y *= w.y; y.z *= w.z; y.w *= w.w;
+    }
+    if (sh != nullptr) {
+      float4 s1 = __ldg(reinterpret_cast<const float4*>(sc + c));
+      float4 s0 = __ldg(reinterpret_cast<const float4*>(sh + c));
+      if (a.scale_tab != nullptr) {
+        const float4 t1 = __ldg(reinterpret_cast<const float4*>(a.scale_tab + c));
+        const float4 t0 = __ldg(reinterpret_cast<const float4*>(a.shift_tab + c));
+        s1.x += t1.x; s1.y += t1.y; s1.z += t1.z; s1.w += t1.w;
+        s0.x += t0.x; s0.y += t0.y; s0.z += t0.z; s0.w += t0.w;
+      }
+      y.x = fmaf(y.x, 1.f + s1.x, s0.x);
+      y.y = fmaf(y.y, 1.f + s1.y, s0.y);
+      y.z = fmaf(y.z, 1.f + s1.z, s0.z);
+      y.w = fmaf(y.w, 1.f + s1.w, s0.w);
+    }
+    if (a.act != LN3_ACT_NONE) {
+      y.x = apply_act(y.x, a.act); y.y = apply_act(y.y, a.act);
+      y.z = apply_act(y.z, a.act); y.w = apply_act(y.w, a.act);
+    }
+    uint2 pk;
+    pk.x = pack_bf16x2(y.x, y.y);
+    pk.y = pack_bf16x2(y.z, y.w);
+    *reinterpret_cast<uint2*>(o + c) = pk;
+  }
+}
+
+int norm_modulate(const ln3_norm_modulate_args* a, cudaStream_t stream) {
+  if (a->rows <= 0) return LN3_OK;
+  if (a->D % 128 != 0 || a->D > 2048 || a->D <= 0)
+    return set_error(LN3_EINVAL, "norm_modulate: D=%d must be a multiple of 128, <= 2048", a->D);
+  if ((a->shift == nullptr) != (a->scale == nullptr))
+    return set_error(LN3_EINVAL, "norm_modulate: shift and scale must be given together");
+  if ((a->shift_tab == nullptr) != (a->scale_tab == nullptr))
+    return set_error(LN3_EINVAL, "norm_modulate: shift_tab and scale_tab must be given together");
+  if (a->shift != nullptr && a->mod_rows <= 0)
+    return set_error(LN3_EINVAL, "norm_modulate: mod_rows must be > 0");
+  if (a->ldx % 4 || a->ldo % 4 || (a->shift && a->mod_ld % 4))
+    return set_error(LN3_EINVAL, "norm_modulate: leading dimensions must be multiples of 4");
+  const int warps = 8;
+  dim3 grid((a->rows + warps - 1) / warps), block(warps * 32);
+  switch (a->D / 128) {
+#define LN3_NM_CASE(n) \
+  case n: norm_modulate_kernel<n><<<grid, block, 0, stream>>>(*a); break;
+    LN3_NM_CASE(1) LN3_NM_CASE(2) LN3_NM_CASE(3) LN3_NM_CASE(4) LN3_NM_CASE(5) LN3_NM_CASE(6)
+    LN3_NM_CASE(7) LN3_NM_CASE(8) LN3_NM_CASE(9) LN3_NM_CASE(10) LN3_NM_CASE(11) LN3_NM_CASE(12)
+    LN3_NM_CASE(13) LN3_NM_CASE(14) LN3_NM_CASE(15) LN3_NM_CASE(16)
+#undef LN3_NM_CASE
+    default: return set_error(LN3_EINVAL, "norm_modulate: unsupported D");
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(LN3_ECUDA, "norm_modulate launch: %s", cudaGetErrorString(e));
+  count_launch();
+  return LN3_OK;
+}
+
+// ------------------------------------------------------------------ timestep embedding
+__global__ void timestep_embedding_kernel(const float* __restrict__ t, int B,
+                                          __nv_bfloat16* __restrict__ out) {
+  const int b = blockIdx.x;
+  const int i = threadIdx.x;  // 0..127
+  if (b >= B) return;
+  // freqs = exp(-ln(10000) * i / 128) in fp32, as torch.exp(fp32 tensor) computes it
+  const float f = expf(-9.210340371976184f * static_cast<float>(i) / 128.0f);
+  const float arg = t[b] * f;
+  out[b * 256 + i] = __float2bfloat16(cosf(arg));
+  out[b * 256 + 128 + i] = __float2bfloat16(sinf(arg));
+}
+
+int timestep_embedding(const float* t, int B, void* out_bf16, cudaStream_t stream) {
+  if (B <= 0) return LN3_OK;
+  timestep_embedding_kernel<<<B, 128, 0, stream>>>(t, B, reinterpret_cast<__nv_bfloat16*>(out_bf16));
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(LN3_ECUDA, "timestep_embedding launch: %s", cudaGetErrorString(e));
+  count_launch();
+  return LN3_OK;
+}
+
+// ------------------------------------------------------------------ patch embed
+// Block = one token (b, n, l); threads stride over D.  K = Cin*4 (<= 64) inputs staged in smem.
+__global__ void __launch_bounds__(256)
+patch_embed_kernel(const ln3_patch_embed_args a) {
+  __shared__ float xin[64];
+  const int P = a.S / 2, L = P * P;
+  const int tok = blockIdx.x;  // b * 3L + n * L + l
+  const int b = tok / (3 * L);
+  const int nl = tok - b * 3 * L;
+  const int n = nl / L, l = nl - n * L;
+  const int pi = l / P, pj = l - pi * P;
+  const int K = a.Cin * 4;
+  if (threadIdx.x < K) {
+    const int c = threadIdx.x >> 2, p = (threadIdx.x >> 1) & 1, q = threadIdx.x & 1;
+    const float s = a.in_scale ? a.in_scale[b] : 1.f;
+    xin[threadIdx.x] =
+        s * a.x[((static_cast<long long>(b) * (3 * a.Cin) + c * 3 + n) * a.S + 2 * pi + p) * a.S +
+                2 * pj + q];
+  }
+  __syncthreads();
+  float* o = a.tokens + static_cast<long long>(tok) * a.D;
+  const float* pe = a.pos_embed ? a.pos_embed + static_cast<long long>(nl) * a.D : nullptr;
+  for (int d = threadIdx.x; d < a.D; d += blockDim.x) {
+    float acc = a.bias ? a.bias[d] : 0.f;
+    const float* w = a.weight + static_cast<long long>(d) * K;
+    for (int k = 0; k < K; ++k) acc = fmaf(w[k], xin[k], acc);
+    if (pe) acc += pe[d];
+    o[d] = acc;
+  }
+}
+
+int patch_embed(const ln3_patch_embed_args* a, cudaStream_t stream) {
+  if (a->B <= 0) return LN3_OK;
+  if (a->S % 2 || a->Cin <= 0 || a->Cin > 16 || a->D <= 0)
+    return set_error(LN3_EINVAL, "patch_embed: need even S, 1 <= Cin <= 16");
+  const int L = (a->S / 2) * (a->S / 2);
+  patch_embed_kernel<<<a->B * 3 * L, 256, 0, stream>>>(*a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(LN3_ECUDA, "patch_embed launch: %s", cudaGetErrorString(e));
+  count_launch();
+  return LN3_OK;
+}
+
+// ------------------------------------------------------------------ final layer
+// One warp per token: LN + modulate in registers, then 4*Cout dot products (warp reductions),
+// scattered into the unpatchified '(b, c*3+n, 2i+p, 2j+q)' layout.
+template <int NV>
+__global__ void __launch_bounds__(128)
+final_layer_kernel(const ln3_final_layer_args a) {
+  const int P = a.S / 2, L = P * P;
+  const int tok = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (tok >= a.B * 3 * L) return;
+  const int lane = threadIdx.x & 31;
+  const int b = tok / (3 * L);
+  const int nl = tok - b * 3 * L;
+  const int n = nl / L, l = nl - n * L;
+  const int pi = l / P, pj = l - pi * P;
+  const float* x = a.x + static_cast<long long>(tok) * a.D;
+  float4 v[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = *reinterpret_cast<const float4*>(x + (i * 32 + lane) * 4);
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  const float mean = warp_sum(s) / static_cast<float>(a.D);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
+    q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+  }
+  const float rstd = rsqrtf(warp_sum(q) / static_cast<float>(a.D) + 1e-6f);
+  const float* sh = a.shift + static_cast<long long>(b) * a.mod_ld;
+  const float* sc = a.scale + static_cast<long long>(b) * a.mod_ld;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    float4 s1 = __ldg(reinterpret_cast<const float4*>(sc + c));
+    float4 s0 = __ldg(reinterpret_cast<const float4*>(sh + c));
+    if (a.scale_tab != nullptr) {
+      const float4 t1 = __ldg(reinterpret_cast<const float4*>(a.scale_tab + c));
+      const float4 t0 = __ldg(reinterpret_cast<const float4*>(a.shift_tab + c));
+      s1.x += t1.x; s1.y += t1.y; s1.z += t1.z; s1.w += t1.w;
+      s0.x += t0.x; s0.y += t0.y; s0.z += t0.z; s0.w += t0.w;
+    }
+    v[i].x = fmaf((v[i].x - mean) * rstd, 1.f + s1.x, s0.x);
+    v[i].y = fmaf((v[i].y - mean) * rstd, 1.f + s1.y, s0.y);
+    v[i].z = fmaf((v[i].z - mean) * rstd, 1.f + s1.z, s0.z);
+    v[i].w = fmaf((v[i].w - mean) * rstd, 1.f + s1.w, s0.w);
+  }
+  const int nout = 4 * a.Cout;
+  for (int oidx = 0; oidx < nout; ++oidx) {
+    const float* w = a.weight + static_cast<long long>(oidx) * a.D;
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float4 ww = __ldg(reinterpret_cast<const float4*>(w + (i * 32 + lane) * 4));
+      acc = fmaf(v[i].x, ww.x, acc);
+      acc = fmaf(v[i].y, ww.y, acc);
+      acc = fmaf(v[i].z, ww.z, acc);
+      acc = fmaf(v[i].w, ww.w, acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      // unpatchify: feature index = (p * 2 + q) * Cout + c   ('nhwpqc->nchpwq')
+      const int c = oidx % a.Cout, pq = oidx / a.Cout, p = pq >> 1, qq = pq & 1;
+      a.out[((static_cast<long long>(b) * (3 * a.Cout) + c * 3 + n) * a.S + 2 * pi + p) * a.S +
+            2 * pj + qq] = acc + (a.bias ? a.bias[oidx] : 0.f);
+    }
+  }
+}
+
+int final_layer(const ln3_final_layer_args* a, cudaStream_t stream) {
+  if (a->B <= 0) return LN3_OK;
+  if (a->D % 128 != 0 || a->D > 2048) return set_error(LN3_EINVAL, "final_layer: bad D=%d", a->D);
+  if (a->shift == nullptr || a->scale == nullptr)
+    return set_error(LN3_EINVAL, "final_layer: shift/scale required");
+  const int L = (a->S / 2) * (a->S / 2);
+  const int toks = a->B * 3 * L;
+  dim3 grid((toks + 3) / 4), block(128);
+  switch (a->D / 128) {
+#define LN3_FL_CASE(n) \
+  case n: final_layer_kernel<n><<<grid, block, 0, stream>>>(*a); break;
+    LN3_FL_CASE(1) LN3_FL_CASE(2) LN3_FL_CASE(3) LN3_FL_CASE(4) LN3_FL_CASE(5) LN3_FL_CASE(6)
+    LN3_FL_CASE(7) LN3_FL_CASE(8) LN3_FL_CASE(9) LN3_FL_CASE(10) LN3_FL_CASE(11) LN3_FL_CASE(12)
+    LN3_FL_CASE(13) LN3_FL_CASE(14) LN3_FL_CASE(15) LN3_FL_CASE(16)
+#undef LN3_FL_CASE
+    default: return set_error(LN3_EINVAL, "final_layer: unsupported D");
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(LN3_ECUDA, "final_layer launch: %s", cudaGetErrorString(e));
+  count_launch();
+  return LN3_OK;
+}
+
+// ------------------------------------------------------------------ sampler update
+__global__ void __launch_bounds__(256)
+sampler_update_kernel(const ln3_sampler_update_args a) {
+  const int b = blockIdx.y;
+  const float4 cf = *reinterpret_cast<const float4*>(a.coef + b * 4);
+  const long long base = static_cast<long long>(b) * a.n_per_sample;
+  const long long n4 = a.n_per_sample >> 2;
+  for (long long i = blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long off = base + i * 4;
+    const float4 x = *reinterpret_cast<const float4*>(a.x + off);
+    const float4 m0 = *reinterpret_cast<const float4*>(a.m0 + off);
+    float4 r = make_float4(cf.x * x.x, cf.x * x.y, cf.x * x.z, cf.x * x.w);
+    r.x = fmaf(cf.y, m0.x, r.x); r.y = fmaf(cf.y, m0.y, r.y);
+    r.z = fmaf(cf.y, m0.z, r.z); r.w = fmaf(cf.y, m0.w, r.w);
+    if (a.m1 != nullptr) {
+      const float4 m1 = *reinterpret_cast<const float4*>(a.m1 + off);
+      r.x = fmaf(cf.z, m1.x, r.x); r.y = fmaf(cf.z, m1.y, r.y);
+      r.z = fmaf(cf.z, m1.z, r.z); r.w = fmaf(cf.z, m1.w, r.w);
+    }
+    if (a.noise != nullptr) {
+      const float4 nz = *reinterpret_cast<const float4*>(a.noise + off);
+      r.x = fmaf(cf.w, nz.x, r.x); r.y = fmaf(cf.w, nz.y, r.y);
+      r.z = fmaf(cf.w, nz.z, r.z); r.w = fmaf(cf.w, nz.w, r.w);
+    }
+    *reinterpret_cast<float4*>(a.x_out + off) = r;
+  }
+}
+
+int sampler_affine_update(const ln3_sampler_update_args* a, cudaStream_t stream) {
+  if (a->B <= 0 || a->n_per_sample <= 0) return LN3_OK;
+  if (a->n_per_sample % 4) return set_error(LN3_EINVAL, "sampler_update: n_per_sample % 4 != 0");
+  if (!a->x || !a->m0 || !a->coef || !a->x_out) return set_error(LN3_EINVAL, "sampler_update: null pointer");
+  const long long n4 = a->n_per_sample / 4;
+  int gx = static_cast<int>((n4 + 255) / 256);
+  if (gx > 1024) gx = 1024;
+  dim3 grid(gx, a->B);
+  sampler_update_kernel<<<grid, 256, 0, stream>>>(*a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(LN3_ECUDA, "sampler_update launch: %s", cudaGetErrorString(e));
+  count_launch();
+  return LN3_OK;
+}
+
+}  // namespace ln3

@@ -70,3 +70,173 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None, *,
     args.act, args.out_kind = act, out_kind
     _lib.check(_lib.lib().ln3_gemm_bf16(C.byref(args), _lib.current_stream()), "ln3_gemm_bf16")
     return out
+
+
+def fmha(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, *,
+         out: torch.Tensor | None = None, scale: float | None = None) -> torch.Tensor:
+    """softmax(q k^T * scale) v per head.  q (B,Lq,H*64), k/v (B,Lkv,H*64) bf16 views with unit
+    inner stride (slices of a packed qkv buffer are fine); returns (B,Lq,H*64) bf16."""
+    for name, t in (("q", q), ("k", k), ("v", v)):
+        _cuda(t, name, torch.bfloat16)
+        _req(t.dim() == 3 and t.stride(2) == 1, f"{name} must be (B,L,H*64) with unit inner stride")
+    B, Lq, C_ = q.shape
+    _req(C_ == heads * 64, "head_dim must be 64")
+    _req(k.shape == v.shape and k.shape[0] == B and k.shape[2] == C_, "k/v shape mismatch")
+    Lkv = k.shape[1]
+    if out is None:
+        out = torch.empty((B, Lq, C_), device=q.device, dtype=torch.bfloat16)
+    _cuda(out, "out", torch.bfloat16)
+    _req(out.shape == (B, Lq, C_) and out.stride(2) == 1, "out must be (B,Lq,H*64)")
+    a = _lib.FmhaArgs()
+    a.q, a.k, a.v, a.out = q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr()
+    a.B, a.H, a.Lq, a.Lkv, a.head_dim = B, heads, Lq, Lkv, 64
+    a.q_ld, a.q_bs = q.stride(1), q.stride(0)
+    a.k_ld, a.k_bs = k.stride(1), k.stride(0)
+    a.v_ld, a.v_bs = v.stride(1), v.stride(0)
+    a.o_ld, a.o_bs = out.stride(1), out.stride(0)
+    a.scale = float(scale if scale is not None else 64 ** -0.5)
+    _lib.check(_lib.lib().ln3_fmha_fwd(C.byref(a), _lib.current_stream()), "ln3_fmha_fwd")
+    return out
+
+
+def norm_modulate(x: torch.Tensor, *, norm: int, shift: torch.Tensor | None = None,
+                  scale: torch.Tensor | None = None, mod_rows: int = 1,
+                  shift_tab: torch.Tensor | None = None, scale_tab: torch.Tensor | None = None,
+                  weight: torch.Tensor | None = None, eps: float = 1e-6, act: int = ACT_NONE,
+                  out: torch.Tensor | None = None) -> torch.Tensor:
+    """bf16( norm(x) * (1 + scale[g]) + shift[g] ), x fp32 (rows, D); shift/scale 2-D fp32 views
+    (groups, D) with unit inner stride and equal row stride; row r uses group r // mod_rows."""
+    _cuda(x, "x", torch.float32)
+    _req(x.dim() == 2 and x.stride(1) == 1, "x must be (rows, D) with unit inner stride")
+    rows, D = x.shape
+    if out is None:
+        out = torch.empty((rows, D), device=x.device, dtype=torch.bfloat16)
+    _cuda(out, "out", torch.bfloat16)
+    _req(out.shape == (rows, D) and out.stride(1) == 1, "out must be (rows, D)")
+    a = _lib.NormModulateArgs()
+    a.x, a.out, a.rows, a.D = x.data_ptr(), out.data_ptr(), rows, D
+    a.ldx, a.ldo = x.stride(0), out.stride(0)
+    if shift is not None:
+        _cuda(shift, "shift", torch.float32)
+        _cuda(scale, "scale", torch.float32)
+        _req(shift.dim() == 2 and scale.dim() == 2 and shift.shape == scale.shape
+             and shift.shape[1] == D and shift.stride(1) == 1 and scale.stride(1) == 1
+             and shift.stride(0) == scale.stride(0), "shift/scale must be matching (groups, D) views")
+        _req(shift.shape[0] * mod_rows >= rows, "too few modulation rows")
+        a.shift, a.scale, a.mod_ld, a.mod_rows = shift.data_ptr(), scale.data_ptr(), shift.stride(0), mod_rows
+    if shift_tab is not None:
+        _cuda(shift_tab, "shift_tab", torch.float32)
+        _cuda(scale_tab, "scale_tab", torch.float32)
+        _req(shift_tab.shape == (D,) and scale_tab.shape == (D,) and shift_tab.is_contiguous()
+             and scale_tab.is_contiguous(), "tables must be contiguous (D,)")
+        a.shift_tab, a.scale_tab = shift_tab.data_ptr(), scale_tab.data_ptr()
+    if weight is not None:
+        _cuda(weight, "weight", torch.float32)
+        _req(weight.shape == (D,) and weight.is_contiguous(), "weight must be contiguous (D,)")
+        a.weight = weight.data_ptr()
+    a.norm, a.act, a.eps = norm, act, eps
+    _lib.check(_lib.lib().ln3_norm_modulate(C.byref(a), _lib.current_stream()), "ln3_norm_modulate")
+    return out
+
+
+def timestep_embedding(t: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """(B,) fp32 timesteps -> (B,256) bf16 [cos | sin] features."""
+    _cuda(t, "t", torch.float32)
+    _req(t.dim() == 1 and t.is_contiguous(), "t must be contiguous (B,)")
+    if out is None:
+        out = torch.empty((t.shape[0], 256), device=t.device, dtype=torch.bfloat16)
+    _cuda(out, "out", torch.bfloat16)
+    _req(out.shape == (t.shape[0], 256) and out.is_contiguous(), "out must be contiguous (B,256)")
+    _lib.check(_lib.lib().ln3_timestep_embedding(_lib.ptr(t), t.shape[0], _lib.ptr(out),
+                                                 _lib.current_stream()), "ln3_timestep_embedding")
+    return out
+
+
+def patch_embed(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None,
+                pos_embed: torch.Tensor | None, in_scale: torch.Tensor | None = None,
+                out: torch.Tensor | None = None) -> torch.Tensor:
+    """x fp32 (B,3*Cin,S,S) -> fp32 tokens (B, 3*(S/2)^2, D) (roll-out patch embed + pos_embed)."""
+    _cuda(x, "x", torch.float32)
+    _cuda(weight, "weight", torch.float32)
+    _req(x.dim() == 4 and x.is_contiguous() and weight.is_contiguous(), "x/weight must be contiguous")
+    B, C3, S, _ = x.shape
+    D, Cin = weight.shape[0], weight.shape[1]
+    _req(C3 == 3 * Cin and weight.shape[2:] == (2, 2), "patch_embed expects 3 planes and 2x2 patches")
+    T = 3 * (S // 2) ** 2
+    if out is None:
+        out = torch.empty((B, T, D), device=x.device, dtype=torch.float32)
+    _req(out.shape == (B, T, D) and out.is_contiguous() and out.dtype == torch.float32, "bad out")
+    a = _lib.PatchEmbedArgs()
+    a.x, a.weight, a.tokens = x.data_ptr(), weight.data_ptr(), out.data_ptr()
+    if bias is not None:
+        _cuda(bias, "bias", torch.float32)
+        a.bias = bias.data_ptr()
+    if pos_embed is not None:
+        _cuda(pos_embed, "pos_embed", torch.float32)
+        _req(pos_embed.numel() == T * D and pos_embed.is_contiguous(), "pos_embed must be (1,T,D)")
+        a.pos_embed = pos_embed.data_ptr()
+    if in_scale is not None:
+        _cuda(in_scale, "in_scale", torch.float32)
+        _req(in_scale.shape == (B,) and in_scale.is_contiguous(), "in_scale must be (B,)")
+        a.in_scale = in_scale.data_ptr()
+    a.B, a.Cin, a.S, a.D = B, Cin, S, D
+    _lib.check(_lib.lib().ln3_patch_embed(C.byref(a), _lib.current_stream()), "ln3_patch_embed")
+    return out
+
+
+def final_layer(x: torch.Tensor, shift: torch.Tensor, scale: torch.Tensor, weight: torch.Tensor,
+                bias: torch.Tensor | None, S: int, *, shift_tab: torch.Tensor | None = None,
+                scale_tab: torch.Tensor | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
+    """tokens fp32 (B,T,D) -> fp32 (B, 3*Cout, S, S): LN + modulate + Linear + unpatchify."""
+    _cuda(x, "x", torch.float32)
+    _req(x.dim() == 3 and x.is_contiguous(), "x must be contiguous (B,T,D)")
+    B, T, D = x.shape
+    _req(T == 3 * (S // 2) ** 2, "token count does not match S")
+    _cuda(weight, "weight", torch.float32)
+    _req(weight.dim() == 2 and weight.shape[1] == D and weight.is_contiguous(), "weight must be (4*Cout, D)")
+    Cout = weight.shape[0] // 4
+    for n_, t_ in (("shift", shift), ("scale", scale)):
+        _cuda(t_, n_, torch.float32)
+        _req(t_.dim() == 2 and t_.shape == (B, D) and t_.stride(1) == 1, f"{n_} must be a (B,D) view")
+    _req(shift.stride(0) == scale.stride(0), "shift/scale row strides differ")
+    if out is None:
+        out = torch.empty((B, 3 * Cout, S, S), device=x.device, dtype=torch.float32)
+    _req(out.shape == (B, 3 * Cout, S, S) and out.is_contiguous() and out.dtype == torch.float32, "bad out")
+    a = _lib.FinalLayerArgs()
+    a.x, a.shift, a.scale, a.weight, a.out = (x.data_ptr(), shift.data_ptr(), scale.data_ptr(),
+                                              weight.data_ptr(), out.data_ptr())
+    if bias is not None:
+        _cuda(bias, "bias", torch.float32)
+        a.bias = bias.data_ptr()
+    if shift_tab is not None:
+        a.shift_tab, a.scale_tab = shift_tab.data_ptr(), scale_tab.data_ptr()
+    a.B, a.S, a.D, a.Cout, a.mod_ld = B, S, D, Cout, shift.stride(0)
+    _lib.check(_lib.lib().ln3_final_layer(C.byref(a), _lib.current_stream()), "ln3_final_layer")
+    return out
+
+
+def sampler_affine_update(x: torch.Tensor, coef: torch.Tensor, m0: torch.Tensor,
+                          m1: torch.Tensor | None = None, noise: torch.Tensor | None = None,
+                          out: torch.Tensor | None = None) -> torch.Tensor:
+    """x_out[b] = a_b x[b] + w0_b m0[b] + w1_b m1[b] + s_b noise[b]; coef (B,4) fp32."""
+    _cuda(x, "x", torch.float32)
+    _cuda(coef, "coef", torch.float32)
+    B = x.shape[0]
+    _req(coef.shape == (B, 4) and coef.is_contiguous(), "coef must be contiguous (B,4)")
+    n = x[0].numel()
+    for nm, t_ in (("x", x), ("m0", m0), ("m1", m1), ("noise", noise)):
+        if t_ is None:
+            continue
+        _cuda(t_, nm, torch.float32)
+        _req(t_.is_contiguous() and t_.shape[0] == B and t_[0].numel() == n, f"{nm} must be contiguous, same shape as x")
+    if out is None:
+        out = torch.empty_like(x)
+    _req(out.is_contiguous() and out.shape == x.shape and out.dtype == torch.float32, "bad out")
+    a = _lib.SamplerUpdateArgs()
+    a.x, a.m0, a.coef, a.x_out = x.data_ptr(), m0.data_ptr(), coef.data_ptr(), out.data_ptr()
+    a.m1 = m1.data_ptr() if m1 is not None else None
+    a.noise = noise.data_ptr() if noise is not None else None
+    a.B, a.n_per_sample = B, n
+    _lib.check(_lib.lib().ln3_sampler_affine_update(C.byref(a), _lib.current_stream()),
+               "ln3_sampler_affine_update")
+    return out
