@@ -188,6 +188,67 @@ typedef struct ln3_sampler_update_args {
 
 int ln3_sampler_affine_update(const ln3_sampler_update_args* args, void* stream);
 
+/* ------------------------------------------------------------------ tri-plane volumetric renderer
+ * ln3_render_views: the whole of ImportanceRenderer.forward (nsr/volumetric_rendering/renderer.py:
+ * 133-307) for the Objaverse preset (nsr/script_util.py:761-797): 'auto' ray limits against the
+ * box (math_utils.py:124-190, renderer.py:145-155), 64 stratified + 64 importance samples per ray,
+ * tri-plane bilinear gather (renderer.py:55-104), in-box filter (:381-405), OSGDecoder
+ * (nsr/triplane.py:339-375, FullyConnectedLayer gains nsr/networks_stylegan2.py:141-145),
+ * MipRayMarcher2 (ray_marcher.py:26-68), sample_importance / sample_pdf (:479-552) and
+ * unify_samples (:422-435), fused into one persistent warp-per-ray kernel.
+ *
+ *   planes_cl    fp32 [n_obj, 3, H, W, 32] channels-last (ln3_planes_to_channels_last)
+ *   view_obj     int32 [V] object of each view, or NULL -> view v uses object v / views_per_obj
+ *   ray_o, ray_d fp32 [V, M, 3]           (ln3_generate_rays, or caller supplied)
+ *   noise_*      fp32 [V, M, 64] uniform [0,1): the tensors the reference draws with
+ *                torch.rand_like (renderer.py:464) and torch.rand (renderer.py:530)
+ *   w1,b1,w2,b2  raw OSGDecoder parameters (64,32), (64), (4,64), (4) -- gains applied inside
+ *   rgb          fp32 [V, 3, M]  ('feature_samples' permuted: image_raw when reshaped to H x W)
+ *   depth        fp32 [V, 1, M]   weights fp32 [V, 1, M]
+ * group_size consecutive views share the reference's per-call global reductions (min/max of the
+ * valid ray starts, depth clamp range): 1 when the reference renders one view per call
+ * (nsr/train_util_diffusion.py:292-302), N for a batched Triplane.forward.
+ * workspace: ln3_render_workspace_bytes(V, M, group_size) bytes of device memory.
+ * dbg_* (optional, tests only): per-sample in-box masks [V*M,128] (coarse ++ fine), searchsorted
+ * indices [V*M,64], sort permutation [V*M,128], fine depths [V*M,64].
+ */
+typedef struct ln3_render_args {
+  const float* planes_cl;
+  const int* view_obj;
+  const float* ray_o;
+  const float* ray_d;
+  const float* noise_coarse;
+  const float* noise_fine;
+  const float* w1;
+  const float* b1;
+  const float* w2;
+  const float* b2;
+  float* rgb;
+  float* depth;
+  float* weights;
+  void* workspace;
+  size_t workspace_bytes;
+  unsigned char* dbg_inbox;
+  int* dbg_inds;
+  int* dbg_order;
+  float* dbg_zfine;
+  int V, M, H, W, C, S, S_importance, hidden_dim, decoder_output_dim;
+  int group_size, views_per_obj, white_back;
+  double box_warp, bbox_min, bbox_max;
+} ln3_render_args;
+
+size_t ln3_render_workspace_bytes(int V, int M, int group_size);
+int ln3_render_views(const ln3_render_args* args, void* stream);
+
+/* RaySampler.forward (nsr/volumetric_rendering/ray_sampler.py:180-257): cams fp32 [V, 25]
+ * (16 cam2world row-major + 9 intrinsics) -> ray_o, ray_d fp32 [V, res*res, 3], ray m = y*res + x. */
+int ln3_generate_rays(const float* cams, int V, int res, float* ray_o, float* ray_d, void* stream);
+
+/* (n_obj, 3*32, H, W) fp32 tri-plane as the VAE decoder emits it (vit/vit_triplane.py:1964,
+ * channel = plane*32 + c) -> channels-last [n_obj, 3, H, W, 32] for the renderer's gathers. */
+int ln3_planes_to_channels_last(const float* planes, int n_obj, int C, int H, int W, float* out,
+                                void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -76,6 +76,23 @@ class SamplerUpdateArgs(C.Structure):
     ]
 
 
+class RenderArgs(C.Structure):
+    _fields_ = [
+        ("planes_cl", C.c_void_p), ("view_obj", C.c_void_p), ("ray_o", C.c_void_p),
+        ("ray_d", C.c_void_p), ("noise_coarse", C.c_void_p), ("noise_fine", C.c_void_p),
+        ("w1", C.c_void_p), ("b1", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_void_p),
+        ("rgb", C.c_void_p), ("depth", C.c_void_p), ("weights", C.c_void_p),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+        ("dbg_inbox", C.c_void_p), ("dbg_inds", C.c_void_p), ("dbg_order", C.c_void_p),
+        ("dbg_zfine", C.c_void_p),
+        ("V", C.c_int), ("M", C.c_int), ("H", C.c_int), ("W", C.c_int), ("C", C.c_int),
+        ("S", C.c_int), ("S_importance", C.c_int), ("hidden_dim", C.c_int),
+        ("decoder_output_dim", C.c_int),
+        ("group_size", C.c_int), ("views_per_obj", C.c_int), ("white_back", C.c_int),
+        ("box_warp", C.c_double), ("bbox_min", C.c_double), ("bbox_max", C.c_double),
+    ]
+
+
 NORM_NONE, NORM_LAYER, NORM_RMS = 0, 1, 2
 
 
@@ -91,6 +108,7 @@ def lib() -> C.CDLL:
         L.ln3_abi_version.restype = C.c_int
         L.ln3_last_error.restype = C.c_char_p
         L.ln3_launch_count.restype = C.c_ulonglong
+        L.ln3_render_workspace_bytes.restype = C.c_size_t
         _lib = L
     return _lib
 

@@ -129,4 +129,22 @@ int ln3_sampler_affine_update(const ln3_sampler_update_args* args, void* stream)
   return sampler_affine_update(args, static_cast<cudaStream_t>(stream));
 }
 
+size_t ln3_render_workspace_bytes(int V, int M, int group_size) {
+  if (V <= 0 || M <= 0 || group_size <= 0) return 0;
+  return render_workspace_bytes(V, M, group_size);
+}
+int ln3_render_views(const ln3_render_args* args, void* stream) {
+  if (!args) return set_error(LN3_EINVAL, "render: null args");
+  return render_views(args, static_cast<cudaStream_t>(stream));
+}
+int ln3_generate_rays(const float* cams, int V, int res, float* ray_o, float* ray_d, void* stream) {
+  if (!cams || !ray_o || !ray_d) return set_error(LN3_EINVAL, "generate_rays: null pointer");
+  return generate_rays(cams, V, res, ray_o, ray_d, static_cast<cudaStream_t>(stream));
+}
+int ln3_planes_to_channels_last(const float* planes, int n_obj, int C, int H, int W, float* out,
+                                void* stream) {
+  if (!planes || !out) return set_error(LN3_EINVAL, "planes_to_channels_last: null pointer");
+  return planes_to_channels_last(planes, n_obj, C, H, W, out, static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

@@ -240,3 +240,86 @@ def sampler_affine_update(x: torch.Tensor, coef: torch.Tensor, m0: torch.Tensor,
     _lib.check(_lib.lib().ln3_sampler_affine_update(C.byref(a), _lib.current_stream()),
                "ln3_sampler_affine_update")
     return out
+
+
+def generate_rays(cams: torch.Tensor, res: int):
+    """cams fp32 (V,25) -> ray_o, ray_d fp32 (V, res*res, 3) (RaySampler.forward)."""
+    _cuda(cams, "cams", torch.float32)
+    _req(cams.dim() == 2 and cams.shape[1] == 25 and cams.is_contiguous(), "cams must be contiguous (V,25)")
+    V = cams.shape[0]
+    o = torch.empty((V, res * res, 3), device=cams.device, dtype=torch.float32)
+    d = torch.empty_like(o)
+    _lib.check(_lib.lib().ln3_generate_rays(_lib.ptr(cams), V, res, _lib.ptr(o), _lib.ptr(d),
+                                            _lib.current_stream()), "ln3_generate_rays")
+    return o, d
+
+
+def planes_to_channels_last(planes: torch.Tensor) -> torch.Tensor:
+    """(N, 96, H, W) or (N, 3, 32, H, W) fp32 -> (N, 3, H, W, 32) fp32."""
+    _cuda(planes, "planes", torch.float32)
+    _req(planes.is_contiguous(), "planes must be contiguous")
+    if planes.dim() == 4:
+        N, C3, H, W = planes.shape
+        _req(C3 == 96, "planes must have 3*32 channels")
+    else:
+        N, three, C, H, W = planes.shape
+        _req(three == 3 and C == 32, "planes must be (N,3,32,H,W)")
+    out = torch.empty((N, 3, H, W, 32), device=planes.device, dtype=torch.float32)
+    _lib.check(_lib.lib().ln3_planes_to_channels_last(_lib.ptr(planes), N, 32, H, W, _lib.ptr(out),
+                                                      _lib.current_stream()),
+               "ln3_planes_to_channels_last")
+    return out
+
+
+def render_views(planes_cl: torch.Tensor, ray_o: torch.Tensor, ray_d: torch.Tensor,
+                 noise_coarse: torch.Tensor, noise_fine: torch.Tensor, osg: tuple, *,
+                 view_obj: torch.Tensor | None = None, views_per_obj: int = 0, group_size: int = 1,
+                 box_warp: float = 0.9, bbox_min: float = -0.45, bbox_max: float = 0.45,
+                 white_back: bool = True, debug: bool = False):
+    """Fused ImportanceRenderer.forward for V views.  Returns dict(rgb (V,3,M), depth (V,1,M),
+    weights (V,1,M)) (+ debug index tensors)."""
+    for nm, t_ in (("planes_cl", planes_cl), ("ray_o", ray_o), ("ray_d", ray_d),
+                   ("noise_coarse", noise_coarse), ("noise_fine", noise_fine)):
+        _cuda(t_, nm, torch.float32)
+        _req(t_.is_contiguous(), f"{nm} must be contiguous")
+    _req(planes_cl.dim() == 5 and planes_cl.shape[1] == 3 and planes_cl.shape[4] == 32,
+         "planes_cl must be (N,3,H,W,32)")
+    V, M, _ = ray_o.shape
+    _req(ray_d.shape == (V, M, 3), "ray_d shape")
+    _req(noise_coarse.numel() == V * M * 64 and noise_fine.numel() == V * M * 64,
+         "noise tensors must hold V*M*64 values")
+    w1, b1, w2, b2 = osg
+    for nm, t_, shp in (("w1", w1, (64, 32)), ("b1", b1, (64,)), ("w2", w2, (4, 64)), ("b2", b2, (4,))):
+        _cuda(t_, nm, torch.float32)
+        _req(tuple(t_.shape) == shp and t_.is_contiguous(), f"{nm} must be contiguous {shp}")
+    dev = ray_o.device
+    a = _lib.RenderArgs()
+    if view_obj is not None:
+        _req(view_obj.is_cuda and view_obj.dtype == torch.int32 and view_obj.shape == (V,), "view_obj int32 (V,)")
+        a.view_obj = view_obj.data_ptr()
+    else:
+        _req(views_per_obj > 0, "need view_obj or views_per_obj")
+    rgb = torch.empty((V, 3, M), device=dev, dtype=torch.float32)
+    depth = torch.empty((V, 1, M), device=dev, dtype=torch.float32)
+    wts = torch.empty((V, 1, M), device=dev, dtype=torch.float32)
+    nbytes = _lib.lib().ln3_render_workspace_bytes(V, M, group_size)
+    ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+    a.planes_cl, a.ray_o, a.ray_d = planes_cl.data_ptr(), ray_o.data_ptr(), ray_d.data_ptr()
+    a.noise_coarse, a.noise_fine = noise_coarse.data_ptr(), noise_fine.data_ptr()
+    a.w1, a.b1, a.w2, a.b2 = w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr()
+    a.rgb, a.depth, a.weights = rgb.data_ptr(), depth.data_ptr(), wts.data_ptr()
+    a.workspace, a.workspace_bytes = ws.data_ptr(), nbytes
+    out = dict(rgb=rgb, depth=depth, weights=wts)
+    if debug:
+        out["inbox"] = torch.empty((V * M, 128), device=dev, dtype=torch.uint8)
+        out["inds"] = torch.empty((V * M, 64), device=dev, dtype=torch.int32)
+        out["order"] = torch.empty((V * M, 128), device=dev, dtype=torch.int32)
+        out["z_fine"] = torch.empty((V * M, 64), device=dev, dtype=torch.float32)
+        a.dbg_inbox, a.dbg_inds = out["inbox"].data_ptr(), out["inds"].data_ptr()
+        a.dbg_order, a.dbg_zfine = out["order"].data_ptr(), out["z_fine"].data_ptr()
+    a.V, a.M, a.H, a.W, a.C = V, M, planes_cl.shape[2], planes_cl.shape[3], 32
+    a.S, a.S_importance, a.hidden_dim, a.decoder_output_dim = 64, 64, 64, 3
+    a.group_size, a.views_per_obj, a.white_back = group_size, views_per_obj, int(white_back)
+    a.box_warp, a.bbox_min, a.bbox_max = box_warp, bbox_min, bbox_max
+    _lib.check(_lib.lib().ln3_render_views(C.byref(a), _lib.current_stream()), "ln3_render_views")
+    return out

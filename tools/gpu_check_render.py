@@ -1,0 +1,141 @@
+"""GPU diagnostic: fused renderer vs the CPU oracle (oracle/render.py) + timing."""
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+from ln3diff_b200 import ops
+from oracle import render as R
+
+dev = "cuda"
+res_out = {"cases": {}}
+
+
+def rel(a, b):
+    return ((a.float() - b.float()).norm() / b.float().norm()).item()
+
+
+def make_scene(seed, n_obj=1):
+    g = torch.Generator().manual_seed(seed)
+    planes = 5 * torch.randn(n_obj, 3, 32, 128, 128, generator=g)
+    w1 = torch.randn(64, 32, generator=g)
+    b1 = torch.randn(64, generator=g) * 0.1
+    w2 = torch.randn(4, 64, generator=g)
+    b2 = torch.randn(4, generator=g) * 0.1
+    b2[0] += 2.0
+    return planes, (w1, b1, w2, b2)
+
+
+def test_cameras(V):
+    """Orbit cameras like assets/objv_eval_pose.pt: radius ~1.7, looking at the origin, fx=fy=1.3889."""
+    cams = []
+    for v in range(V):
+        az = 2 * 3.14159265 * v / max(V, 1) + 0.3
+        el = 0.35 + 0.2 * ((v % 3) - 1)
+        r = 1.7
+        import math
+        eye = torch.tensor([r * math.cos(el) * math.cos(az), r * math.cos(el) * math.sin(az), r * math.sin(el)])
+        fwd = -eye / eye.norm()
+        up = torch.tensor([0.0, 0.0, 1.0])
+        right = torch.linalg.cross(fwd, up)
+        right = right / right.norm()
+        down = torch.linalg.cross(fwd, right)
+        c2w = torch.eye(4)
+        c2w[:3, 0], c2w[:3, 1], c2w[:3, 2], c2w[:3, 3] = right, down, fwd, eye
+        K = torch.tensor([1.3889, 0, 0.5, 0, 1.3889, 0.5, 0, 0, 1.0])
+        cams.append(torch.cat([c2w.reshape(-1), K]))
+    return torch.stack(cams).float()
+
+
+def check(res, V, seed):
+    planes, osg = make_scene(seed)
+    cams = test_cameras(V)
+    M = res * res
+    g = torch.Generator().manual_seed(100 + seed)
+    nc = torch.rand(V, M, 64, generator=g)
+    nf = torch.rand(V, M, 64, generator=g)
+    # oracle per view (reference renders one view per call)
+    t0 = time.time()
+    refs = [R.render_view(planes[0], osg, cams[v], res, R.OBJAVERSE_OPTS, nc[v], nf[v]) for v in range(V)]
+    t_or = time.time() - t0
+    o_ref, d_ref = R.generate_rays(cams[:, :16].reshape(V, 4, 4), cams[:, 16:].reshape(V, 3, 3), res)
+    o, d = ops.generate_rays(cams.to(dev), res)
+    tag = f"res{res}_V{V}"
+    res_out["cases"]["rays_" + tag] = {"max_abs_d": (d.cpu() - d_ref).abs().max().item(),
+                                       "max_abs_o": (o.cpu() - o_ref).abs().max().item(),
+                                       "ok": bool((d.cpu() - d_ref).abs().max().item() < 1e-6)}
+    pcl = ops.planes_to_channels_last(planes.to(dev).contiguous())
+    ref_cl = planes.permute(0, 1, 3, 4, 2).contiguous()
+    res_out["cases"]["planes_cl_" + tag] = {"ok": bool(torch.equal(pcl.cpu(), ref_cl))}
+    # use the oracle's rays so renderer inputs are identical
+    out = ops.render_views(pcl, o_ref.to(dev).contiguous(), d_ref.to(dev).contiguous(), nc.to(dev), nf.to(dev),
+                           tuple(t.to(dev) for t in osg), views_per_obj=V, group_size=1, debug=True)
+    torch.cuda.synchronize()
+    img = out["rgb"].cpu().reshape(V, 3, res, res)
+    dep = out["depth"].cpu().reshape(V, 1, res, res)
+    wts = out["weights"].cpu().reshape(V, 1, res, res)
+    ref_img = torch.stack([r["image_raw"] for r in refs])
+    ref_dep = torch.stack([r["image_depth"] for r in refs])
+    ref_w = torch.stack([r["weights_samples"] for r in refs])
+    c = {"rgb_rel": rel(img, ref_img), "depth_rel": rel(dep, ref_dep), "w_rel": rel(wts, ref_w),
+         "rgb_maxabs": (img - ref_img).abs().max().item(), "oracle_s_per_view": t_or / V,
+         "w_mean": ref_w.mean().item()}
+    c["ok"] = bool(c["rgb_rel"] < 1e-3 and c["depth_rel"] < 1e-3 and c["w_rel"] < 1e-3)
+    # index bookkeeping vs oracle debug tensors (view 0)
+    dbg = R.render_rays(planes[0], osg, o_ref[0], d_ref[0], R.OBJAVERSE_OPTS, nc[0], nf[0], return_debug=True)
+    inb = out["inbox"].cpu()[:M].bool()
+    c["inbox_coarse_mismatch"] = int((inb[:, :64] != dbg["inbox_coarse"]).sum())
+    c["inbox_fine_mismatch"] = int((inb[:, 64:] != dbg["inbox_fine"]).sum())
+    c["inds_mismatch"] = int((out["inds"].cpu()[:M].long() != dbg["inds"]).sum())
+    c["order_mismatch"] = int((out["order"].cpu()[:M].long() != dbg["order"]).sum())
+    c["zfine_maxabs"] = (out["z_fine"].cpu()[:M] - dbg["z_fine"]).abs().max().item()
+    res_out["cases"]["render_" + tag] = c
+    print(tag, c, flush=True)
+
+
+def bench(res, V, n_obj):
+    planes, osg = make_scene(5, n_obj)
+    cams = test_cameras(V).repeat(n_obj, 1).to(dev)
+    VV = V * n_obj
+    M = res * res
+    nc = torch.rand(VV, M, 64, device=dev)
+    nf = torch.rand(VV, M, 64, device=dev)
+    pcl = ops.planes_to_channels_last(planes.to(dev).contiguous())
+    o, d = ops.generate_rays(cams, res)
+    osg_d = tuple(t.to(dev) for t in osg)
+    for _ in range(2):
+        ops.render_views(pcl, o, d, nc, nf, osg_d, views_per_obj=V)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    e0.record()
+    n = 3
+    for _ in range(n):
+        ops.render_views(pcl, o, d, nc, nf, osg_d, views_per_obj=V)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    r = {"res": res, "views": VV, "ms": ms, "views_per_s": VV / ms * 1e3, "ms_per_view": ms / VV,
+         "gflops_per_s": 0.70e-3 * M * VV / ms * 1e3}
+    print("bench", r, flush=True)
+    res_out.setdefault("bench", []).append(r)
+
+
+try:
+    check(32, 2, 1)
+    check(64, 3, 2)
+    check(128, 1, 3)
+    bench(128, 16, 4)
+    bench(256, 8, 2)
+    res_out["ok"] = all(c.get("ok", False) for c in res_out["cases"].values())
+except Exception as e:  # noqa
+    import traceback
+    traceback.print_exc()
+    res_out["error"] = repr(e)
+    res_out["ok"] = False
+os.makedirs("gpurun_out", exist_ok=True)
+with open("gpurun_out/render_check.json", "w") as f:
+    json.dump(res_out, f, indent=1)
+print("OK" if res_out.get("ok") else "FAILED")
