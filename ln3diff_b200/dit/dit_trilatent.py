@@ -23,6 +23,8 @@ from .dit_models_xformers import (CaptionEmbedder, DiTBlock, FinalLayer, T2IFina
 class DiT_TriLatent(nn.Module):
     """reference dit/dit_trilatent.py:22-143 (+ base dit_models_xformers.py:681-819)."""
 
+    _ln3_fused_in_scale = True  # forward(..., in_scale=) folds the denoiser's c_in into patch embed
+
     def __init__(self, input_size=32, patch_size=2, in_channels=4, hidden_size=1152, depth=28,
                  num_heads=16, mlp_ratio=4, class_dropout_prob=0.1, num_classes=1000,
                  learn_sigma=True, mixing_logit_init=-3, mixed_prediction=True, context_dim=False,
