@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""bench.py -- denoised-latents/sec (+ rendered-views/sec) of the LN3Diff generation hot path.
+
+Workload (BASELINE.json configs[1]): DiT-L/2 T23D tri-latent, 250-step Euler-EDM + VanillaCFG(6.5)
+(the shipped sampler, sgm/configs/txt2img-clipl-compat.yaml:47-60), batch = 8 prompts per GPU
+(16 DiT samples per forward), bf16 tensor-core GEMMs / fp32 residual + sampler state.
+One "step" = one full pass of the hot path over one batch: 250 denoising steps for 8 latents.
+Independent prompts shard across GPUs with no data-path collective (weak scaling); the finished
+latents are all-gathered once per step (tiny).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+`--impl reference` times the reference algorithm's CPU path (the oracle port -- /root/reference
+is a Python tree that cannot travel to the GPU box) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ARCH = "DiT-L/2"
+PROMPTS_PER_GPU = 8
+DENOISE_STEPS = 250
+CFG_SCALE = 6.5
+FLOPS_PER_FORWARD_PER_SAMPLE = 0.613e12  # SURVEY.md section 8d (T23D DiT-L/2, MAC = 2 FLOP)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--denoise-steps", type=int, default=DENOISE_STEPS, help=argparse.SUPPRESS)
+    return ap.parse_args()
+
+
+def workload_config(n_gpus):
+    return {"workload": "configs[1]: DiT-L/2 T23D tri-latent (12x32x32), EulerEDM 250 steps + VanillaCFG 6.5, "
+                        "8 prompts/GPU (16 samples/forward)",
+            "arch": ARCH, "denoise_steps": DENOISE_STEPS, "cfg_scale": CFG_SCALE,
+            "prompts_per_gpu": PROMPTS_PER_GPU, "global_batch": PROMPTS_PER_GPU * n_gpus,
+            "parallelism": f"prompt-sharded x{n_gpus} (replicated weights, no data-path collective)",
+            "l2": "inputs larger than L2: 1.1 GB of bf16 weights stream through every forward"}
+
+
+# ------------------------------------------------------------------ CPU reference arm / baseline
+def cpu_reference_sample(n_steps_sample=1, prompts=1, threads=None):
+    """Time `n_steps_sample` Euler-EDM+CFG steps of DiT-L/2 for `prompts` prompts with the oracle
+    port on the host cores; returns (latents_per_sec extrapolated to 250 steps, seconds, cores)."""
+    import torch
+    from oracle import dit as odit
+    from oracle import samplers as osmp
+    from ln3diff_b200.utils import build_t23d
+    cores = threads or os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    m = build_t23d(ARCH)
+    sd = {k: v.float() for k, v in m.state_dict().items()}
+    del m
+    g = torch.Generator().manual_seed(41)
+    x = torch.randn(prompts, 12, 32, 32, generator=g)
+    c = {"crossattn": torch.randn(prompts, 77, 768, generator=g)}
+    uc = {"crossattn": torch.zeros(prompts, 77, 768)}
+    calls = []
+
+    def net(xin, idx, cond):
+        t0 = time.perf_counter()
+        out = odit.dit_t23d_forward(sd, ARCH, xin, idx, cond["crossattn"])
+        calls.append(time.perf_counter() - t0)
+        return out
+
+    # run the first `n_steps_sample` steps of the real 250-step schedule
+    table = osmp.legacy_ddpm_sigmas(1000, append_zero=False, flip=True)
+    sigmas = osmp.legacy_ddpm_sigmas(DENOISE_STEPS)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        xx = x * torch.sqrt(1.0 + sigmas[0] ** 2.0)
+        for i in range(n_steps_sample):
+            s = torch.ones(prompts) * sigmas[i]
+            nxt = torch.ones(prompts) * sigmas[i + 1]
+            xin, sin = torch.cat([xx] * 2), torch.cat([s] * 2)
+            sq = table[osmp.sigma_to_idx(sin, table)]
+            sq4 = sq[:, None, None, None]
+            den = net(xin / (sq4 ** 2 + 1.0) ** 0.5, osmp.sigma_to_idx(sq, table),
+                      {"crossattn": torch.cat((uc["crossattn"], c["crossattn"]), 0)}) * (-sq4) + xin
+            x_u, x_c = den.chunk(2)
+            d = (xx - (x_u + CFG_SCALE * (x_c - x_u))) / s[:, None, None, None]
+            xx = xx + (nxt - s)[:, None, None, None] * d
+    dt = time.perf_counter() - t0
+    per_step = dt / n_steps_sample
+    return prompts / (per_step * DENOISE_STEPS), dt, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vals = []
+    t_all = time.perf_counter()
+    for i in range(args.warmup + args.steps):
+        v, dt, cores = cpu_reference_sample(n_steps_sample=1, prompts=1)
+        if i >= args.warmup:
+            vals.append((v, dt))
+    value = sum(v for v, _ in vals) / len(vals)
+    ms = 1e3 * sum(dt for _, dt in vals) / len(vals)
+    sample = ("1 of 250 Euler-EDM+CFG steps for 1 prompt (2 DiT-L/2 fp32 forwards) per bench step, "
+              "latents/s extrapolated linearly in steps x prompts")
+    line = {"impl": "reference", "metric": "denoised-latents/sec", "value": value, "unit": "latents/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(args.gpus),
+            "cpu_baseline": {"value": value, "unit": "latents/s", "cores": cores, "kind": "port",
+                             "sample": sample},
+            "e2e": {"value": value, "unit": "latents/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "wall_s": time.perf_counter() - t_all}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------ clocks sampler
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons, pw = [], [], set(), []
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from ln3diff_b200 import _lib, ops, pipeline
+    from ln3diff_b200.utils import build_t23d
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py --impl ours needs a CUDA GPU (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n_gpus = world
+    B = PROMPTS_PER_GPU
+    nsteps = args.denoise_steps
+
+    model = build_t23d(ARCH, seed=0, device=dev)
+    model.prepare()
+    # identical-seed inputs as the reference engine draws them (CPU generator, then moved):
+    # one global randn for all prompts, sliced per rank
+    g = torch.Generator().manual_seed(41)
+    randn_all = torch.randn(B * n_gpus, 12, 32, 32, generator=g)
+    ctx_all = torch.randn(B * n_gpus, 77, 768, generator=g)
+    sl = slice(rank * B, (rank + 1) * B)
+    randn_h = randn_all[sl].contiguous().pin_memory()
+    ctx_h = ctx_all[sl].contiguous().pin_memory()
+    out_h = torch.empty(B, 12, 32, 32).pin_memory()
+    randn_d, ctx_d = randn_h.to(dev), ctx_h.to(dev)
+    uc_d = torch.zeros_like(ctx_d)
+    tables = pipeline.edm_cfg_tables(nsteps, CFG_SCALE, B, dev)
+    gathered = torch.empty(n_gpus * B, 12, 32, 32, device=dev) if world > 1 else None
+
+    def one_step_device():
+        lat = pipeline.sample_t23d(model, randn_d, {"crossattn": ctx_d}, {"crossattn": uc_d}, nsteps,
+                                   CFG_SCALE, tables)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, lat)
+        return lat
+
+    def one_step_e2e():
+        x = randn_h.to(dev, non_blocking=True)
+        c = ctx_h.to(dev, non_blocking=True)
+        lat = pipeline.sample_t23d(model, x, {"crossattn": c}, {"crossattn": torch.zeros_like(c)}, nsteps,
+                                   CFG_SCALE, tables)
+        out_h.copy_(lat, non_blocking=True)
+        return lat
+
+    def timed(fn, k, w):
+        for _ in range(w):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = _lib.launch_count()
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item(), _lib.launch_count() - l0
+
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    ms_total, launches = timed(one_step_device, args.steps, args.warmup)
+    clk = clocks.stop() if rank == 0 else None
+    ms_step = ms_total / args.steps
+    value = B * n_gpus / (ms_step / 1e3)
+
+    ms_e2e_total, _ = timed(one_step_e2e, args.steps, 1)
+    e2e_value = B * n_gpus / (ms_e2e_total / args.steps / 1e3)
+
+    line = None
+    if rank == 0:
+        # ---- roofline of the dominant kernel (tcgen05 GEMM): instrumented pass over one forward,
+        # CUDA events around every GEMM launch on the launching stream.
+        peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                peaks = json.load(f)
+        except Exception:
+            pass
+        peak_tf = peaks.get("bf16_tflops_sustained")
+        peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
+        if not peak_tf:
+            peak_tf, peak_src = 1400.0, "fallback (B200_PROFILING.md sustained ~1.4 PFLOP/s)"
+        ev, flops = [], []
+        real_gemm = ops.gemm
+
+        def gemm_probe(a, w, *a_, **kw):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = real_gemm(a, w, *a_, **kw)
+            e1.record()
+            ev.append((e0, e1))
+            flops.append(2.0 * a.shape[0] * a.shape[1] * w.shape[0])
+            return r
+
+        x2 = torch.randn(2 * B, 12, 32, 32, device=dev)
+        ctx2 = torch.cat([uc_d, ctx_d], 0)
+        model(x2, tables["t_idx"][0], ctx2, in_scale=tables["c_in"][0])
+        torch.cuda.synchronize()
+        ops.gemm = gemm_probe
+        import ln3diff_b200.dit.dit_trilatent as _dt
+        try:
+            _dt.ops.gemm = gemm_probe
+            model(x2, tables["t_idx"][1], ctx2, in_scale=tables["c_in"][1])
+            torch.cuda.synchronize()
+        finally:
+            ops.gemm = real_gemm
+            _dt.ops.gemm = real_gemm
+        big = [(f, e0.elapsed_time(e1)) for f, (e0, e1) in zip(flops, ev) if f > 1e10]
+        gemm_ms = sum(t for _, t in big)
+        gemm_fl = sum(f for f, _ in big)
+        achieved = gemm_fl / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+        roofline = {"kernel": "ln3::gemm_bf16_kernel<256> (tcgen05 128x256x64, fused epilogues)",
+                    "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+                    "frac": achieved / peak_tf, "peak_source": peak_src, "traffic": None,
+                    "launches_measured": len(big), "avg_launch_us": 1e3 * gemm_ms / max(len(big), 1),
+                    "flops_per_launch_avg": gemm_fl / max(len(big), 1),
+                    "note": "events add launch gaps; gemm share of the forward in profiles/"}
+        model_tf = FLOPS_PER_FORWARD_PER_SAMPLE * 2 * B * nsteps / (ms_step / 1e3) / 1e12
+
+        # ---- second headline quantity: rendered views/sec of the fused ray-march kernel
+        views = None
+        try:
+            gg = torch.Generator().manual_seed(4)
+            n_obj, V, res = 4, 16, 128
+            planes = (5 * torch.randn(n_obj, 3, 32, 128, 128, generator=gg)).to(dev)
+            osg = [torch.randn(64, 32, generator=gg), torch.randn(64, generator=gg) * 0.1,
+                   torch.randn(4, 64, generator=gg), torch.randn(4, generator=gg) * 0.1]
+            osg[3][0] += 2.0
+            osg = tuple(t.to(dev) for t in osg)
+            from ln3diff_b200.utils import orbit_cameras
+            cams = orbit_cameras(V).repeat(n_obj, 1).to(dev)
+            M = res * res
+            nc = torch.rand(n_obj * V, M, 64, device=dev)
+            nf = torch.rand(n_obj * V, M, 64, device=dev)
+            pcl = ops.planes_to_channels_last(planes)
+            o, d = ops.generate_rays(cams, res)
+            for _ in range(2):
+                ops.render_views(pcl, o, d, nc, nf, osg, views_per_obj=V)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                ops.render_views(pcl, o, d, nc, nf, osg, views_per_obj=V)
+            e1.record()
+            torch.cuda.synchronize()
+            rms = e0.elapsed_time(e1) / 3
+            views = {"value": n_obj * V / (rms / 1e3), "unit": "views/s", "res": res, "views": n_obj * V,
+                     "samples_per_ray": "64+64", "ms": rms,
+                     "fp32_tflops": 0.70e6 * M * n_obj * V / (rms / 1e3) / 1e12,
+                     "data": "synthetic planes 5*randn, explicit noise (SURVEY.md 8d config 3 render-only)"}
+        except Exception as e:  # noqa
+            views = {"error": repr(e)}
+
+        cpu = None
+        if n_gpus == 1:
+            v, dt, cores = cpu_reference_sample(n_steps_sample=1, prompts=1)
+            cpu = {"value": v, "unit": "latents/s", "cores": cores, "kind": "port",
+                   "sample": f"1 of 250 Euler-EDM+CFG steps for 1 prompt (2 DiT-L/2 fp32 forwards, {dt:.1f} s); "
+                             "latents/s extrapolated linearly in steps x prompts"}
+        line = {"metric": "denoised-latents/sec", "value": value, "unit": "latents/s", "n_gpus": n_gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": workload_config(n_gpus),
+                "e2e": {"value": e2e_value, "unit": "latents/s",
+                        "h2d_bytes_per_step": randn_h.numel() * 4 + ctx_h.numel() * 4,
+                        "d2h_bytes_per_step": out_h.numel() * 4},
+                "gpu_launches": int(launches), "clocks": clk, "roofline": roofline,
+                "model_tflops": model_tf, "rendered_views": views, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

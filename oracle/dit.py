@@ -159,3 +159,24 @@ def derandomize_zero_init(sd: dict, std: float = 0.02, seed: int = 1234) -> dict
             v = torch.randn(v.shape, generator=g, dtype=torch.float32) * std
         out[k] = v
     return out
+
+
+def synth_state_dict(shapes: dict, seed: int = 7, keep: dict | None = None) -> dict:
+    """Deterministic weights independent of module construction order: every tensor is drawn from
+    a CPU generator in sorted-key order (weights N(0, 1/fan_in), biases / vectors N(0, 0.02^2));
+    `keep` entries (e.g. the analytic pos_embed) are passed through."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for k in sorted(shapes.keys()):
+        if keep and k in keep:
+            sd[k] = keep[k].clone()
+            continue
+        shp = tuple(shapes[k])
+        if len(shp) >= 2:
+            fan_in = 1
+            for s in shp[1:]:
+                fan_in *= s
+            sd[k] = torch.randn(shp, generator=g) * (1.0 / fan_in ** 0.5)
+        else:
+            sd[k] = torch.randn(shp, generator=g) * 0.02
+    return sd

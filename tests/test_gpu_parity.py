@@ -1,0 +1,314 @@
+"""GPU (-m gpu): the CUDA path, called through the C ABI (ctypes), against the CPU oracle on the same
+seeded inputs and against the committed golden fixtures.  Tolerances: bf16 tensor-core operands ->
+rel-L2 <= 1e-2 per op / 2e-2 per DiT forward; fp32 kernels <= 1e-5; rendered pixels <= 1e-3
+(north_star); integer bookkeeping bit-exact where the float inputs are identical."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
+    return ((a - b).norm() / b.norm()).item()
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "-m gpu tests need a GPU"
+    from ln3diff_b200 import _lib
+    _lib.lib()  # fail loudly if the CUDA extension is missing
+    return torch.device("cuda", 0)
+
+
+# ------------------------------------------------------------------ GEMM
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 512, 1024), (1232, 1024, 768), (16, 6144, 1024),
+                                   (77, 256, 128), (3000, 3072, 1024)])
+def test_gemm_bf16(dev, M, N, K):
+    from ln3diff_b200 import ops
+    g = torch.Generator().manual_seed(M + N + K)
+    a = (torch.randn(M, K, generator=g) * 0.5).bfloat16()
+    w = (torch.randn(N, K, generator=g) * 0.05).bfloat16()
+    b = torch.randn(N, generator=g)
+    ref = a.float() @ w.float().t() + b
+    out = ops.gemm(a.to(dev), w.to(dev), b.to(dev))
+    assert _rel(out, ref) < 4e-3                       # bf16 output rounding only
+    out32 = ops.gemm(a.to(dev), w.to(dev), b.to(dev), out_kind=ops.OUT_F32)
+    assert _rel(out32, ref) < 1e-5                     # fp32 accumulate in TMEM
+
+
+def test_gemm_epilogues(dev):
+    from ln3diff_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    M, N, K = 1536, 1024, 512
+    a = (torch.randn(M, K, generator=g) * 0.5).bfloat16()
+    w = (torch.randn(N, K, generator=g) * 0.05).bfloat16()
+    b = torch.randn(N, generator=g)
+    lin = a.float() @ w.float().t() + b
+    for act, fn in ((ops.ACT_GELU_ERF, F.gelu), (ops.ACT_GELU_TANH, lambda v: F.gelu(v, approximate="tanh")),
+                    (ops.ACT_SILU, F.silu)):
+        out = ops.gemm(a.to(dev), w.to(dev), b.to(dev), act=act, out_kind=ops.OUT_F32)
+        assert _rel(out, fn(lin)) < 1e-5
+    x0 = torch.randn(M, N, generator=g)
+    gate = torch.randn(2, N, generator=g)
+    x = x0.clone().to(dev)
+    xb = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
+    ops.gemm(a.to(dev), w.to(dev), b.to(dev), out_kind=ops.OUT_RESID_F32, out=x, gate=gate.to(dev),
+             gate_rows=768, out2=xb)
+    ref = x0 + gate.repeat_interleave(768, 0) * lin
+    assert _rel(x, ref) < 1e-5 and _rel(xb, ref) < 4e-3
+
+
+def test_gemm_rejects_bad_shapes(dev):
+    from ln3diff_b200 import ops
+    a = torch.zeros(128, 96, dtype=torch.bfloat16, device=dev)
+    w = torch.zeros(128, 96, dtype=torch.bfloat16, device=dev)
+    with pytest.raises(RuntimeError, match="multiple of 64"):
+        ops.gemm(a, w)
+
+
+# ------------------------------------------------------------------ attention
+@pytest.mark.parametrize("B,H,Lq,Lkv", [(2, 12, 768, 768), (2, 16, 768, 77), (1, 4, 200, 333),
+                                        (2, 16, 768, 1024), (3, 16, 256, 256), (1, 2, 1, 1)])
+def test_fmha(dev, B, H, Lq, Lkv):
+    from ln3diff_b200 import ops
+    g = torch.Generator().manual_seed(Lq * 7 + Lkv)
+    D = H * 64
+    qkv = torch.randn(B, max(Lq, Lkv), 3 * D, generator=g).bfloat16()
+    q, k, v = qkv[:, :Lq, :D], qkv[:, :Lkv, D:2 * D], qkv[:, :Lkv, 2 * D:]
+    dq = qkv.to(dev)
+    out = ops.fmha(dq[:, :Lq, :D], dq[:, :Lkv, D:2 * D], dq[:, :Lkv, 2 * D:], H)
+    qf, kf, vf = (t.float().reshape(B, -1, H, 64).transpose(1, 2) for t in (q, k, v))
+    ref = F.scaled_dot_product_attention(qf, kf, vf).transpose(1, 2).reshape(B, Lq, D)
+    assert _rel(out, ref) < 6e-3
+
+
+# ------------------------------------------------------------------ elementwise
+def test_norm_modulate_timestep_patch_final(dev):
+    from ln3diff_b200 import ops
+    from ln3diff_b200._lib import NORM_LAYER, NORM_NONE, NORM_RMS
+    from oracle import dit as odit
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(300, 1024, generator=g) * 2 + 0.5
+    sh = torch.randn(3, 6 * 1024, generator=g)
+    out = ops.norm_modulate(x.to(dev), norm=NORM_LAYER, shift=sh.to(dev)[:, 0:1024], scale=sh.to(dev)[:, 1024:2048],
+                            mod_rows=100)
+    ref = odit.layer_norm(x) * (1 + sh[:, 1024:2048].repeat_interleave(100, 0)) + sh[:, :1024].repeat_interleave(100, 0)
+    assert _rel(out, ref) < 4e-3
+    w = torch.randn(768, generator=g)
+    x7 = torch.randn(77, 768, generator=g)
+    assert _rel(ops.norm_modulate(x7.to(dev), norm=NORM_RMS, weight=w.to(dev), eps=1e-5), odit.rms_norm(x7, w)) < 4e-3
+    assert _rel(ops.norm_modulate(x7.to(dev), norm=NORM_NONE, act=ops.ACT_SILU), F.silu(x7)) < 4e-3
+    t = torch.tensor([0.0, 1.0, 17.0, 999.0, 0.37])
+    assert _rel(ops.timestep_embedding(t.to(dev)), odit.timestep_embedding(t)) < 4e-3
+    sd = {"x_embedder.proj.weight": torch.randn(768, 4, 2, 2, generator=g), "x_embedder.proj.bias": torch.randn(768, generator=g)}
+    xin, pos = torch.randn(2, 12, 32, 32, generator=g), torch.randn(1, 768, 768, generator=g)
+    out = ops.patch_embed(xin.to(dev), sd["x_embedder.proj.weight"].to(dev), sd["x_embedder.proj.bias"].to(dev), pos.to(dev))
+    assert _rel(out, odit.patch_embed_rollout(sd, xin) + pos) < 1e-6
+    tok = torch.randn(2, 768, 768, generator=g)
+    shift, scale = torch.randn(2, 768, generator=g), torch.randn(2, 768, generator=g)
+    wf, bfin = torch.randn(16, 768, generator=g) * 0.05, torch.randn(16, generator=g)
+    ref = odit.unpatchify_rollout(F.linear(odit.layer_norm(tok) * (1 + scale[:, None]) + shift[:, None], wf, bfin), 4)
+    out = ops.final_layer(tok.to(dev), shift.to(dev), scale.to(dev), wf.to(dev), bfin.to(dev), 32)
+    assert _rel(out, ref) < 1e-5
+
+
+def test_sampler_update_kernel(dev):
+    from ln3diff_b200 import ops
+    g = torch.Generator().manual_seed(2)
+    x, m0, m1, nz = (torch.randn(3, 12, 32, 32, generator=g) for _ in range(4))
+    cf = torch.randn(3, 4, generator=g)
+    c = cf[:, :, None, None, None]
+    ref = c[:, 0] * x + c[:, 1] * m0 + c[:, 2] * m1 + c[:, 3] * nz
+    out = ops.sampler_affine_update(x.to(dev), cf.to(dev), m0.to(dev), m1.to(dev), nz.to(dev))
+    assert _rel(out, ref) < 1e-6
+    out = ops.sampler_affine_update(x.to(dev), cf.to(dev), m0.to(dev))
+    assert _rel(out, c[:, 0] * x + c[:, 1] * m0) < 1e-6
+
+
+# ------------------------------------------------------------------ DiT forward + samplers
+def test_dit_forward_matches_reference_golden(dev, golden):
+    """CUDA DiT-B/2 forward vs the REFERENCE's own output (tests/golden/dit_t23d.npz)."""
+    from ln3diff_b200.dit.dit_models_xformers import TextCondDiTBlock
+    from ln3diff_b200.dit.dit_trilatent import DiT_models
+    from oracle import dit as odit
+    from oracle import fixtures as fx
+    m = DiT_models["DiT-B/2"](input_size=32, num_classes=0, learn_sigma=False, in_channels=4,
+                              context_dim=768, roll_out=True, vit_blk=TextCondDiTBlock)
+    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    m.load_state_dict(odit.synth_state_dict(shapes, seed=7, keep={"pos_embed": m.state_dict()["pos_embed"]}))
+    m = m.to(dev)
+    x, t, ctx = fx.dit_inputs()
+    out = m(x.to(dev), t.to(dev), {"crossattn": ctx.to(dev)})
+    assert out.dtype == torch.float32 and out.is_contiguous() and out.shape == (2, 12, 32, 32)
+    assert _rel(out, golden("dit_t23d.npz")["out"]) < 2e-2
+
+
+def test_edm_cfg_pipeline_vs_oracle(dev):
+    """DiT-B/2, 4 Euler-EDM+CFG steps: fused pipeline and the mirrored sampler classes vs the oracle."""
+    from ln3diff_b200 import pipeline
+    from ln3diff_b200.sgm.modules.diffusionmodules.denoiser import DiscreteDenoiser
+    from ln3diff_b200.sgm.modules.diffusionmodules.sampling import EulerEDMSampler
+    from ln3diff_b200.utils import build_t23d
+    from oracle import dit as odit
+    from oracle import samplers as osmp
+    m = build_t23d("DiT-B/2")
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    g = torch.Generator().manual_seed(41)
+    x0 = torch.randn(2, 12, 32, 32, generator=g)
+    c = {"crossattn": torch.randn(2, 77, 768, generator=g)}
+    uc = {"crossattn": torch.zeros(2, 77, 768)}
+    ref = osmp.euler_edm_cfg_sample(lambda xi, ti, cc: odit.dit_t23d_forward(sd, "DiT-B/2", xi, ti, cc["crossattn"]),
+                                    x0.clone(), c, uc, 4, 6.5)
+    m = m.to(dev)
+    cd, ucd = {"crossattn": c["crossattn"].to(dev)}, {"crossattn": uc["crossattn"].to(dev)}
+    out = pipeline.sample_t23d(m, x0.to(dev), cd, ucd, 4, 6.5)
+    assert _rel(out, ref) < 2e-2
+    disc = {"target": "sgm.modules.diffusionmodules.discretizer.LegacyDDPMDiscretization"}
+    s = EulerEDMSampler(discretization_config=disc, num_steps=4, device=str(dev), guider_config={
+        "target": "sgm.modules.diffusionmodules.guiders.VanillaCFG", "params": {"scale": 6.5}})
+    d = DiscreteDenoiser(scaling_config={"target": "sgm.modules.diffusionmodules.denoiser_scaling.EpsScaling"},
+                         num_idx=1000, discretization_config=disc).to(dev)
+    out2 = s(lambda i, sg, cc: d(m, i, sg, cc), x0.clone().to(dev), cd, ucd)
+    assert _rel(out2, ref) < 2e-2
+    assert _rel(out2, out) < 1e-2
+
+
+def test_ddpm_p_sample_loop_config1(dev):
+    """BASELINE configs[0]: DiT-B/2, SpacedDiffusion('10') p_sample_loop, batch 1, vs the oracle."""
+    from ln3diff_b200.guided_diffusion import gaussian_diffusion as gd
+    from ln3diff_b200.guided_diffusion.respace import SpacedDiffusion, space_timesteps
+    from ln3diff_b200.utils import build_t23d
+    from oracle import dit as odit
+    from oracle import samplers as osmp
+    m = build_t23d("DiT-B/2")
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    g = torch.Generator().manual_seed(1)
+    noise = torch.randn(1, 12, 32, 32, generator=g)
+    ctx = torch.randn(1, 77, 768, generator=torch.Generator().manual_seed(2))
+    step_noise = [torch.randn(1, 12, 32, 32, generator=g) for _ in range(10)]
+    tab = osmp.DDPMTables(osmp.linear_betas(1000), osmp.space_timesteps(1000, "10"))
+    ref = osmp.ddpm_p_sample_loop(lambda xx, tt, cc: odit.dit_t23d_forward(sd, "DiT-B/2", xx, tt, cc),
+                                  (1, 12, 32, 32), tab, noise, step_noise, cond=ctx)
+    m = m.to(dev)
+    diff = SpacedDiffusion(use_timesteps=space_timesteps(1000, "10"), betas=gd.get_named_beta_schedule("linear", 1000),
+                           model_mean_type=gd.ModelMeanType.EPSILON, model_var_type=gd.ModelVarType.FIXED_LARGE,
+                           loss_type=gd.LossType.MSE)
+
+    class Engine:  # what TrainLoop.apply_model_inference does: call the denoiser with the context
+        def apply_model_inference(self, x, t, c, **kw):
+            return m(x, t, c)
+
+    it = iter(step_noise)
+    orig = torch.randn_like
+    torch.randn_like = lambda v: next(it).to(v.device)
+    try:
+        out = diff.p_sample_loop(Engine(), (1, 12, 32, 32), cond=ctx.to(dev), noise=noise.to(dev),
+                                 clip_denoised=False, device=dev)
+    finally:
+        torch.randn_like = orig
+    assert _rel(out, ref) < 2e-2
+
+
+# ------------------------------------------------------------------ renderer
+def _render_cuda(dev, planes, osg, o, d, nc, nf, **kw):
+    from ln3diff_b200 import ops
+    pcl = ops.planes_to_channels_last(planes[None].contiguous().to(dev))
+    return ops.render_views(pcl, o.contiguous().to(dev), d.contiguous().to(dev), nc.contiguous().to(dev),
+                            nf.contiguous().to(dev), tuple(t.to(dev) for t in osg), views_per_obj=o.shape[0], **kw)
+
+
+def test_render_matches_reference_golden(dev, golden):
+    """Fused CUDA renderer vs the REFERENCE's ImportanceRenderer outputs (tests/golden/render.npz)."""
+    from oracle import fixtures as fx
+    g = golden("render.npz")
+    res = 24
+    planes, osg, nc, nf = fx.render_inputs(res)
+    o = torch.stack([torch.from_numpy(g[f"ray_o_{v}"]) for v in range(2)])
+    d = torch.stack([torch.from_numpy(g[f"ray_d_{v}"]) for v in range(2)])
+    r = _render_cuda(dev, planes, osg, o, d, nc, nf)
+    for v in range(2):
+        assert _rel(r["rgb"][v].t(), g[f"rgb_{v}"]) < 1e-3          # north_star tolerance on pixels
+        assert _rel(r["rgb"][v].t(), g[f"rgb_{v}"]) < 2e-5          # what the fp32 kernel actually achieves
+        assert _rel(r["depth"][v].t(), g[f"depth_{v}"]) < 2e-5
+        assert _rel(r["weights"][v].t(), g[f"weights_{v}"]) < 2e-5
+
+
+def test_render_bookkeeping_and_rays_vs_oracle(dev, golden):
+    from ln3diff_b200 import ops
+    from oracle import fixtures as fx
+    from oracle import render as orender
+    cams = torch.from_numpy(golden("cameras.npz")["objv_eval_pose"])[:3]
+    res = 32
+    o_ref, d_ref = orender.generate_rays(cams[:, :16].reshape(-1, 4, 4), cams[:, 16:].reshape(-1, 3, 3), res)
+    o, d = ops.generate_rays(cams.to(dev).contiguous(), res)
+    assert torch.equal(o.cpu(), o_ref)                              # origins + ray order m = y*W + x: exact
+    assert (d.cpu() - d_ref).abs().max() < 3e-7
+    planes, osg, nc, nf = fx.render_inputs(res, n_views=3)
+    r = _render_cuda(dev, planes, osg, o_ref, d_ref, nc, nf, debug=True)
+    M = res * res
+    n_bad_idx = n_bad_ord = 0
+    for v in range(3):
+        dbg = orender.render_rays(planes, osg, o_ref[v], d_ref[v], orender.OBJAVERSE_OPTS, nc[v], nf[v], return_debug=True)
+        inb = r["inbox"].cpu()[v * M:(v + 1) * M].bool()
+        assert torch.equal(inb[:, :64], dbg["inbox_coarse"])        # integer bookkeeping: bit-exact
+        zf = r["z_fine"].cpu()[v * M:(v + 1) * M]
+        assert (zf - dbg["z_fine"]).abs().max() < 5e-6
+        # in-box of the fine samples / searchsorted / sort permutation depend on float cdf / depth
+        # values that differ in the last ulp (scan order): allow ties only
+        assert (inb[:, 64:] != dbg["inbox_fine"]).sum() <= 2
+        n_bad_idx += int((r["inds"].cpu()[v * M:(v + 1) * M].long() != dbg["inds"]).sum())
+        n_bad_ord += int((r["order"].cpu()[v * M:(v + 1) * M].long() != dbg["order"]).sum())
+    assert n_bad_idx <= 3 * M * 64 * 2e-5 + 2
+    assert n_bad_ord <= 3 * M * 128 * 2e-5 + 2
+
+
+def test_render_edge_cases(dev):
+    from oracle import fixtures as fx
+    from oracle import render as orender
+    res = 8
+    planes, osg, nc, nf = fx.render_inputs(res, n_views=2)
+    miss_o = torch.tensor([[3.0, 3.0, 3.0]]).repeat(res * res, 1)
+    miss_d = F.normalize(torch.tensor([[1.0, 0.2, 0.1]]), dim=1).repeat(res * res, 1)
+    in_o = torch.zeros(res * res, 3)
+    in_d = F.normalize(torch.randn(res * res, 3, generator=torch.Generator().manual_seed(3)), dim=1)
+    o, d = torch.stack([miss_o, in_o]), torch.stack([miss_d, in_d])
+    r = _render_cuda(dev, planes, osg, o, d, nc, nf)                # group_size 1: per-view reductions
+    for v in range(2):
+        ref = orender.render_rays(planes, osg, o[v], d[v], orender.OBJAVERSE_OPTS, nc[v], nf[v])
+        assert torch.isfinite(r["rgb"][v]).all()
+        assert (r["rgb"][v].t().cpu() - ref["rgb"]).abs().max() < 1e-4
+        assert (r["depth"][v].t().cpu() - ref["depth"]).abs().max() < 1e-4
+        assert (r["weights"][v].t().cpu() - ref["weights"]).abs().max() < 1e-4
+
+
+def test_render_full_size_properties(dev):
+    """BASELINE config 3 size (128x128, 16 views): size-independent properties -- outputs in range,
+    weights in [0,1], white background where nothing is hit, determinism, and view-batch
+    independence (rendering views together == one at a time)."""
+    from ln3diff_b200 import ops
+    from ln3diff_b200.utils import orbit_cameras
+    g = torch.Generator().manual_seed(4)
+    V, res = 16, 128
+    planes = (5 * torch.randn(1, 3, 32, 128, 128, generator=g)).to(dev)
+    osg = [torch.randn(64, 32, generator=g), torch.randn(64, generator=g) * 0.1,
+           torch.randn(4, 64, generator=g), torch.randn(4, generator=g) * 0.1]
+    osg[3][0] += 2.0
+    osg = tuple(t.to(dev) for t in osg)
+    M = res * res
+    nc, nf = torch.rand(V, M, 64, generator=g).to(dev), torch.rand(V, M, 64, generator=g).to(dev)
+    pcl = ops.planes_to_channels_last(planes)
+    o, d = ops.generate_rays(orbit_cameras(V).to(dev), res)
+    r = ops.render_views(pcl, o, d, nc, nf, osg, views_per_obj=V)
+    assert torch.isfinite(r["rgb"]).all() and torch.isfinite(r["depth"]).all()
+    assert r["rgb"].min() >= -1.003 and r["rgb"].max() <= 1.003
+    assert r["weights"].min() >= 0 and r["weights"].max() <= 1 + 1e-5
+    empty = r["weights"][:, 0] < 1e-7
+    assert empty.any() and (r["rgb"].permute(0, 2, 1)[empty] - 1).abs().max() < 1e-5
+    r2 = ops.render_views(pcl, o, d, nc, nf, osg, views_per_obj=V)
+    assert torch.equal(r["rgb"], r2["rgb"])                          # deterministic
+    one = ops.render_views(pcl, o[5:6].contiguous(), d[5:6].contiguous(), nc[5:6].contiguous(),
+                           nf[5:6].contiguous(), osg, views_per_obj=1)
+    assert torch.equal(one["rgb"][0], r["rgb"][5]) and torch.equal(one["depth"][0], r["depth"][5])
