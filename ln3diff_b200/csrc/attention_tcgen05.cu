@@ -7,25 +7,31 @@
 //   dit/dit_decoder.py                (in-plane / global attention of the DiT2 VAE decoder).
 // Semantics: out = softmax(q k^T * scale) v, no mask (xformers FMHA with attn_bias=None).
 //
-// One CTA = 128 query rows of one (batch, head); 128 threads, thread r owns query row r (TMEM lane r),
-// so the online softmax needs no cross-thread reduction.
-//   S = Q K^T   : tcgen05.mma 128x128x16 x4, Q/K tiles K-major in 128B-swizzled smem (TMA)
-//   P = exp2(..): TMEM -> registers -> bf16 -> smem (same swizzle, written by the owning thread)
-//   O_j = P V   : tcgen05.mma 128x64x16 x8, V tile MN-major straight from the TMA layout
-//   O   = O * alpha + O_j in registers.
-// K/V tiles are double buffered; QK^T of block j+1 is issued right behind PV of block j so the
-// tensor pipe works while the CUDA cores rescale O; two CTAs per SM interleave softmax and MMA.
+// Warp-specialised, one CTA = 256 query rows (two 128-row tiles) of one (batch, head):
+//   warps 0-3 / 4-7 : softmax warpgroup of tile 0 / 1; thread r owns query row r (= TMEM lane r), so
+//                     the row max / sum need no cross-thread reduction.  S (128 fp32) is read once
+//                     from TMEM into registers, P = exp2(S*scale - m) goes to 128B-swizzled smem as bf16.
+//   warp 8          : TMA producer (Q once, K/V tiles double buffered)
+//   warp 9          : tcgen05.mma issuer:  S_t = Q_t K^T (128x128x16 x4),  O_t += P_t V (128x64x16 x8,
+//                     V MN-major straight from the TMA layout).  While warpgroup 0 runs its softmax the
+//                     tensor core computes S_1 / P_1 V and vice versa.
+// O accumulates in TMEM across KV blocks.  The running max is only refreshed when it grew by more
+// than 2^8 (then the owning thread rescales its O row in TMEM); otherwise P is computed against the
+// stale max, which is exact after the final 1/l normalisation.
 #include "common.cuh"
 #include "ln3_internal.h"
 
 namespace ln3 {
 
-static constexpr int kQT = 128;   // query rows per CTA
+static constexpr int kQT = 128;   // query rows per tile (2 tiles per CTA)
 static constexpr int kKT = 128;   // kv rows per block
 static constexpr int kHD = 64;    // head dim
 static constexpr int kTileBytes = 128 * kHD * 2;  // 16 KB
-static constexpr int kFmhaSmem = 1024 + kTileBytes * (1 + 2 + 2 + 2) + 128;
-static constexpr int kFmhaTmemCols = 256;  // S: [0,128)  O_j: [128,192)
+// Q0 Q1 | K[2] | V[2] | P0 (2 atoms) P1 (2 atoms)
+static constexpr int kFmhaSmem = 1024 + kTileBytes * (2 + 2 + 2 + 4) + 256;
+static constexpr int kFmhaTmemCols = 512;  // S0 [0,128) S1 [128,256) O0 [256,320) O1 [320,384)
+static constexpr int kFmhaThreads = 320;
+static constexpr float kRescaleThreshold = 8.0f;  // log2 units
 
 struct FmhaParams {
   int Lq, Lkv;
@@ -34,39 +40,48 @@ struct FmhaParams {
   long long out_ld, out_bs;  // row / batch stride (elements); head h at column h*64
 };
 
-__global__ void __launch_bounds__(128, 2)
+__global__ void __launch_bounds__(kFmhaThreads, 1)
 fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const FmhaParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + kTileBytes;      // [2]
-  uint8_t* sV = sK + 2 * kTileBytes;  // [2]
-  uint8_t* sP = sV + 2 * kTileBytes;  // two 64-column atoms
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kTileBytes);
-  uint64_t* q_full = bars;
-  uint64_t* k_full = bars + 1;  // [2]
-  uint64_t* v_full = bars + 3;  // [2]
-  uint64_t* s_done = bars + 5;
-  uint64_t* o_done = bars + 6;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
+  uint8_t* sQ = smem;                  // [2]
+  uint8_t* sK = sQ + 2 * kTileBytes;   // [2]
+  uint8_t* sV = sK + 2 * kTileBytes;   // [2]
+  uint8_t* sP = sV + 2 * kTileBytes;   // [2 tiles][2 atoms]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 4 * kTileBytes);
+  uint64_t* q_full = bars;        // 1
+  uint64_t* kv_full = bars + 1;   // [2]
+  uint64_t* kv_empty = bars + 3;  // [2]
+  uint64_t* s_full = bars + 5;    // [2 tiles]
+  uint64_t* p_full = bars + 7;    // [2 tiles], 128 arrivals
+  uint64_t* o_full = bars + 9;    // [2 tiles]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
-  const int q0 = blockIdx.x * kQT;
+  const int q0 = blockIdx.x * 2 * kQT;
   const int head = blockIdx.y;
   const int batch = blockIdx.z;
   const int nkv = (p.Lkv + kKT - 1) / kKT;
+  const int ntiles = (q0 + kQT < p.Lq) ? 2 : 1;  // second tile entirely out of range -> skipped
 
   if (tid == 0) {
     tma_prefetch_desc(&tmap_q);
     tma_prefetch_desc(&tmap_k);
     tma_prefetch_desc(&tmap_v);
-    for (int i = 0; i < 7; ++i) mbar_init(&bars[i], 1);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 128);
+      mbar_init(&o_full[i], 1);
+    }
     fence_barrier_init();
   }
-  if (warp == 0) {
+  if (warp == 9) {
     tmem_alloc(tmem_slot, kFmhaTmemCols);
     tmem_relinquish();
   }
@@ -74,153 +89,163 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tS = tmem_base;
-  const uint32_t tO = tmem_base + 128;
-  const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
 
-  constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
-  constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);  // B (= V) is MN-major
-
-  auto load_kv = [&](int j) {
-    const int b = j & 1;
-    mbar_arrive_expect_tx(&k_full[b], kTileBytes);
-    tma_load_3d(sK + b * kTileBytes, &tmap_k, &k_full[b], head * kHD, j * kKT, batch);
-    mbar_arrive_expect_tx(&v_full[b], kTileBytes);
-    tma_load_3d(sV + b * kTileBytes, &tmap_v, &v_full[b], head * kHD, j * kKT, batch);
-  };
-  auto issue_qk = [&](int j) {
-    const int b = j & 1;
-    mbar_wait(&k_full[b], (j >> 1) & 1);
-    tc_fence_after();
-    const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK + b * kTileBytes);
-#pragma unroll
-    for (int k = 0; k < kHD / 16; ++k)
-      umma_f16_ss(tS, make_smem_desc_sw128(qa + k * 32, 0, 1024),
-                  make_smem_desc_sw128(ka + k * 32, 0, 1024), idesc_s, k != 0);
-    umma_commit(s_done);
-  };
-
-  if (tid == 0) {
-    mbar_arrive_expect_tx(q_full, kTileBytes);
-    tma_load_3d(sQ, &tmap_q, q_full, head * kHD, q0, batch);
-    load_kv(0);
-    if (nkv > 1) load_kv(1);
-    mbar_wait(q_full, 0);
-    issue_qk(0);
-  }
-
-  float m_run = -INFINITY, l_run = 0.f;
-  float o[kHD];
-#pragma unroll
-  for (int i = 0; i < kHD; ++i) o[i] = 0.f;
-
-  const int row = tid;  // == TMEM lane
-  const uint32_t p_row = smem_u32(sP) + row * 128;
-  const int swz = row & 7;
-
-  for (int j = 0; j < nkv; ++j) {
-    const int kv_valid = min(kKT, p.Lkv - j * kKT);
-    mbar_wait(s_done, j & 1);
-    tc_fence_after();
-
-    // pass 1: row max (log2 domain)
-    float mx = -INFINITY;
-#pragma unroll 1
-    for (int c = 0; c < kKT; c += 32) {
-      uint32_t v[32];
-      tmem_ld_32x32(tS + lane_off + c, v);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const float s = (c + i < kv_valid) ? __uint_as_float(v[i]) : -INFINITY;
-        mx = fmaxf(mx, s);
+  if (warp == 8) {
+    // ------------------------------------------------------------ TMA producer
+    if ((tid & 31) == 0) {
+      mbar_arrive_expect_tx(q_full, ntiles * kTileBytes);
+      for (int t = 0; t < ntiles; ++t)
+        tma_load_3d(sQ + t * kTileBytes, &tmap_q, q_full, head * kHD, q0 + t * kQT, batch);
+      for (int j = 0; j < nkv; ++j) {
+        const int b = j & 1;
+        mbar_wait(&kv_empty[b], ((j >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&kv_full[b], 2 * kTileBytes);
+        tma_load_3d(sK + b * kTileBytes, &tmap_k, &kv_full[b], head * kHD, j * kKT, batch);
+        tma_load_3d(sV + b * kTileBytes, &tmap_v, &kv_full[b], head * kHD, j * kKT, batch);
       }
     }
-    const float m_new = fmaxf(m_run, mx * p.scale_log2);
-    const float alpha = exp2f(m_run - m_new);  // 0 on the first block (m_run = -inf)
-    // pass 2: p = exp2(s*scale - m_new) -> bf16 -> swizzled smem, row sum
-    float rs = 0.f;
-#pragma unroll 1
-    for (int c = 0; c < kKT; c += 32) {
-      uint32_t v[32];
-      tmem_ld_32x32(tS + lane_off + c, v);
-      tmem_ld_wait();
-      float pv[32];
+  } else if (warp == 9) {
+    // ------------------------------------------------------------ MMA issuer
+    if ((tid & 31) == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);  // B (= V) is MN-major
+      auto issue_qk = [&](int t, int j) {
+        const uint32_t qa = smem_u32(sQ + t * kTileBytes), ka = smem_u32(sK + (j & 1) * kTileBytes);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const float e = exp2f(fmaf(__uint_as_float(v[i]), p.scale_log2, -m_new));
-        pv[i] = (c + i < kv_valid) ? e : 0.f;
+        for (int k = 0; k < kHD / 16; ++k)
+          umma_f16_ss(tmem_base + t * 128, make_smem_desc_sw128(qa + k * 32, 0, 1024),
+                      make_smem_desc_sw128(ka + k * 32, 0, 1024), idesc_s, k != 0);
+        umma_commit(&s_full[t]);
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(&kv_full[0], 0);
+      tc_fence_after();
+      for (int t = 0; t < ntiles; ++t) issue_qk(t, 0);
+      for (int j = 0; j < nkv; ++j) {
+        for (int t = 0; t < ntiles; ++t) {
+          mbar_wait(&p_full[t], j & 1);  // P_t(j) in smem, S_t consumed, O_t rescaled if needed
+          tc_fence_after();
+          const uint32_t pa = smem_u32(sP + t * 2 * kTileBytes);
+          const uint32_t va = smem_u32(sV + (j & 1) * kTileBytes);
+#pragma unroll
+          for (int k = 0; k < kKT / 16; ++k)
+            umma_f16_ss(tmem_base + 256 + t * 64,
+                        make_smem_desc_sw128(pa + (k >> 2) * kTileBytes + (k & 3) * 32, 0, 1024),
+                        make_smem_desc_sw128(va + k * 16 * 128, 1024, 1024), idesc_o, (j | k) != 0);
+          umma_commit(&o_full[t]);
+          if (j + 1 < nkv) {
+            if (t == 0) {
+              mbar_wait(&kv_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
+              tc_fence_after();
+            }
+            issue_qk(t, j + 1);
+          }
+        }
+        umma_commit(&kv_empty[j & 1]);  // every MMA that read K[j] / V[j] has been issued
       }
-      const uint32_t atom = p_row + (c >> 6) * kTileBytes;
-      const int chunk0 = (c & 63) >> 3;
+    }
+  } else if (warp < 4 * ntiles) {
+    // ------------------------------------------------------------ softmax warpgroups
+    const int t = warp >> 2;
+    const int row = tid & 127;  // TMEM lane
+    const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const uint32_t tS = tmem_base + t * 128 + lane_off;
+    const uint32_t tO = tmem_base + 256 + t * 64 + lane_off;
+    const uint32_t p_row = smem_u32(sP + t * 2 * kTileBytes) + row * 128;
+    const int swz = row & 7;
+    float m_ref = -INFINITY, l_run = 0.f;
+
+    for (int j = 0; j < nkv; ++j) {
+      const int kv_valid = p.Lkv - j * kKT;  // >= 1
+      mbar_wait(&s_full[t], j & 1);
+      tc_fence_after();
+      uint32_t s[128];
+      tmem_ld_32x32(tS + 0, s);
+      tmem_ld_32x32(tS + 32, s + 32);
+      tmem_ld_32x32(tS + 64, s + 64);
+      tmem_ld_32x32(tS + 96, s + 96);
+      tmem_ld_wait();
+      if (kv_valid < kKT) {
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const uint32_t x = pack_bf16x2(pv[g * 8 + 0], pv[g * 8 + 1]);
-        const uint32_t y = pack_bf16x2(pv[g * 8 + 2], pv[g * 8 + 3]);
-        const uint32_t z = pack_bf16x2(pv[g * 8 + 4], pv[g * 8 + 5]);
-        const uint32_t w = pack_bf16x2(pv[g * 8 + 6], pv[g * 8 + 7]);
-        // row sum of the values the tensor core will actually see (bf16-rounded)
-        __nv_bfloat162 bx = *reinterpret_cast<const __nv_bfloat162*>(&x);
-        __nv_bfloat162 by = *reinterpret_cast<const __nv_bfloat162*>(&y);
-        __nv_bfloat162 bz = *reinterpret_cast<const __nv_bfloat162*>(&z);
-        __nv_bfloat162 bw = *reinterpret_cast<const __nv_bfloat162*>(&w);
-        rs += (__low2float(bx) + __high2float(bx)) + (__low2float(by) + __high2float(by)) +
-              (__low2float(bz) + __high2float(bz)) + (__low2float(bw) + __high2float(bw));
-        const uint32_t addr = atom + (((chunk0 + g) ^ swz) << 4);
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z),
-                     "r"(w)
+        for (int i = 0; i < 128; ++i)
+          if (i >= kv_valid) s[i] = 0xff800000u;  // -inf
+      }
+      float mx = fmax3(__uint_as_float(s[0]), __uint_as_float(s[1]), __uint_as_float(s[2]));
+#pragma unroll
+      for (int i = 3; i < 127; i += 2) mx = fmax3(mx, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
+      mx = fmaxf(mx, __uint_as_float(s[127]));
+      const float m_cand = mx * p.scale_log2;
+      float alpha = 1.f;
+      bool need = false;
+      if (j == 0) {
+        m_ref = m_cand;
+      } else if (m_cand > m_ref + kRescaleThreshold) {
+        need = true;
+        alpha = fast_exp2(m_ref - m_cand);
+        m_ref = m_cand;
+        l_run *= alpha;
+      }
+      float rs = 0.f;
+#pragma unroll
+      for (int c = 0; c < 128; c += 8) {
+        float e[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) e[i] = fast_exp2(fmaf(__uint_as_float(s[c + i]), p.scale_log2, -m_ref));
+        rs += ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));
+        const uint32_t addr = p_row + (c >> 6) * kTileBytes + ((((c & 63) >> 3) ^ swz) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pack_bf16x2(e[0], e[1])),
+                     "r"(pack_bf16x2(e[2], e[3])), "r"(pack_bf16x2(e[4], e[5])),
+                     "r"(pack_bf16x2(e[6], e[7]))
                      : "memory");
       }
-    }
-    l_run = l_run * alpha + rs;
-    m_run = m_new;
-
-    fence_proxy_async_smem();  // P (generic-proxy stores) -> visible to the tensor core
-    tc_fence_before();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      const int b = j & 1;
-      mbar_wait(&v_full[b], (j >> 1) & 1);
-      const uint32_t pa = smem_u32(sP), va = smem_u32(sV + b * kTileBytes);
+      l_run += rs;
+      if (j > 0 && __any_sync(0xffffffffu, need)) {
+        // O_t(j-1) must be complete before it is rescaled in place
+        mbar_wait(&o_full[t], (j - 1) & 1);
+        tc_fence_after();
 #pragma unroll
-      for (int k = 0; k < kKT / 16; ++k)
-        umma_f16_ss(tO, make_smem_desc_sw128(pa + (k >> 2) * kTileBytes + (k & 3) * 32, 0, 1024),
-                    make_smem_desc_sw128(va + k * 16 * 128, 1024, 1024), idesc_o, k != 0);
-      umma_commit(o_done);
-      if (j + 1 < nkv) issue_qk(j + 1);  // S is free: every thread finished pass 2 before the sync
+        for (int c = 0; c < kHD; c += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(tO + c, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+          tmem_st_32x32(tO + c, v);
+        }
+        tmem_st_wait();
+      }
+      fence_proxy_async_smem();  // P (generic-proxy stores) -> visible to the tensor core
+      tc_fence_before();
+      mbar_arrive(&p_full[t]);
     }
-    mbar_wait(o_done, j & 1);
+    mbar_wait(&o_full[t], (nkv - 1) & 1);
     tc_fence_after();
-    if (tid == 0 && j + 2 < nkv) load_kv(j + 2);  // K/V buffer (j&1) is free once PV(j) retired
+    const float inv = 1.f / l_run;
+    const int qrow = q0 + t * kQT + row;
+    __nv_bfloat16* dst = p.out + batch * p.out_bs + static_cast<long long>(qrow) * p.out_ld + head * kHD;
 #pragma unroll
     for (int c = 0; c < kHD; c += 32) {
       uint32_t v[32];
-      tmem_ld_32x32(tO + lane_off + c, v);
+      tmem_ld_32x32(tO + c, v);
       tmem_ld_wait();
+      if (qrow < p.Lq) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) o[c + i] = fmaf(o[c + i], alpha, __uint_as_float(v[i]));
+        for (int i = 0; i < 32; i += 8) {
+          uint4 q;
+          q.x = pack_bf16x2(__uint_as_float(v[i]) * inv, __uint_as_float(v[i + 1]) * inv);
+          q.y = pack_bf16x2(__uint_as_float(v[i + 2]) * inv, __uint_as_float(v[i + 3]) * inv);
+          q.z = pack_bf16x2(__uint_as_float(v[i + 4]) * inv, __uint_as_float(v[i + 5]) * inv);
+          q.w = pack_bf16x2(__uint_as_float(v[i + 6]) * inv, __uint_as_float(v[i + 7]) * inv);
+          *reinterpret_cast<uint4*>(dst + c + i) = q;
+        }
+      }
     }
   }
 
-  const float inv = 1.f / l_run;
-  if (q0 + row < p.Lq) {
-    __nv_bfloat16* dst = p.out + batch * p.out_bs + static_cast<long long>(q0 + row) * p.out_ld +
-                         head * kHD;
-#pragma unroll
-    for (int i = 0; i < kHD; i += 8) {
-      uint4 q;
-      q.x = pack_bf16x2(o[i] * inv, o[i + 1] * inv);
-      q.y = pack_bf16x2(o[i + 2] * inv, o[i + 3] * inv);
-      q.z = pack_bf16x2(o[i + 4] * inv, o[i + 5] * inv);
-      q.w = pack_bf16x2(o[i + 6] * inv, o[i + 7] * inv);
-      *reinterpret_cast<uint4*>(dst + i) = q;
-    }
-  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (warp == 0) tmem_dealloc(tmem_base, kFmhaTmemCols);
+  if (warp == 9) tmem_dealloc(tmem_base, kFmhaTmemCols);
 }
 
 int fmha_fwd(const ln3_fmha_args* a, cudaStream_t stream) {
@@ -253,8 +278,8 @@ int fmha_fwd(const ln3_fmha_args* a, cudaStream_t stream) {
   p.out = reinterpret_cast<__nv_bfloat16*>(a->out);
   p.out_ld = a->o_ld;
   p.out_bs = a->o_bs;
-  dim3 grid((a->Lq + kQT - 1) / kQT, a->H, a->B);
-  fmha_fwd_kernel<<<grid, 128, kFmhaSmem, stream>>>(tq, tk, tv, p);
+  dim3 grid((a->Lq + 2 * kQT - 1) / (2 * kQT), a->H, a->B);
+  fmha_fwd_kernel<<<grid, kFmhaThreads, kFmhaSmem, stream>>>(tq, tk, tv, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(LN3_ECUDA, "fmha launch: %s", cudaGetErrorString(e));
   count_launch();
