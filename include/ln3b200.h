@@ -249,6 +249,44 @@ int ln3_generate_rays(const float* cams, int V, int res, float* ray_o, float* ra
 int ln3_planes_to_channels_last(const float* planes, int n_obj, int C, int H, int W, float* out,
                                 void* stream);
 
+/* ------------------------------------------------------------------ VAE decoder: conv tail (NHWC fp32)
+ * The reference's superresolution['conv_sr'] = ldm Decoder (ldm/modules/diffusionmodules/model.py:
+ * 625-731) and PatchEmbedTriplane (vit/vit_triplane.py:58-108).  Activations are NHWC so the DiT2
+ * token stream feeds conv_in directly and conv_out writes the renderer's channels-last tri-plane.
+ *
+ * ln3_conv_nhwc: out = conv(ksize in {1,3}, stride 1, pad ksize/2)(f(up(x))) + bias (+ residual)
+ *   f = identity, or the fused GroupNorm-apply (+ swish): v*in_scale[n,c] + in_shift[n,c]
+ *       (model.py:46-52 nonlinearity / Normalize; scale/shift from ln3_groupnorm_stats)
+ *   up = identity or nearest 2x (Upsample, model.py:54-69): x is then [N, H/2, W/2, Cin]
+ *   w is the Conv2d weight repacked to [ksize*ksize, Cin, Cout].
+ * ln3_groupnorm_stats: torch.nn.GroupNorm(G, C, eps) statistics of x [N, HW, C] folded with the
+ *   affine parameters into per-(image, channel) scale / shift [N, C].
+ * ln3_attn_single_head: MemoryEfficientAttnBlock core (model.py:209-272): softmax(q k^T/sqrt(C)) v,
+ *   q/k/v/out fp32 [N, L, C], one head of width C (128 in conv_sr).
+ * ln3_patch_embed_triplane: Conv2d(3*Cz -> 3*E, k=s=2, groups=3) + the reference's
+ *   (B,3E,h,w)->(B,E,3,h,w)->(B,3hw,E) reshape; x fp32 [B, 3*Cz, S, S] is pre-multiplied by in_mul
+ *   (triplane_scaling_divider, nsr/train_util_diffusion.py:188); optional bf16 SiLU copy of the
+ *   tokens (the adaLN operand of every DiT2 block, dit/dit_decoder.py:29-31).
+ */
+typedef struct ln3_conv_args {
+  const float* x;
+  const float* w;
+  const float* bias;
+  const float* in_scale;
+  const float* in_shift;
+  const float* residual;
+  float* out;
+  int N, H, W, Cin, Cout, ksize, upsample, in_swish;
+} ln3_conv_args;
+
+int ln3_conv_nhwc(const ln3_conv_args* args, void* stream);
+int ln3_groupnorm_stats(const float* x, const float* gamma, const float* beta, int N, int HW, int C,
+                        int G, float eps, float* scale, float* shift, void* stream);
+int ln3_attn_single_head(const float* q, const float* k, const float* v, float* out, int N, int L,
+                         int C, void* stream);
+int ln3_patch_embed_triplane(const float* x, const float* w, const float* bias, int B, int Cz, int S,
+                             int E, float in_mul, float* tokens, void* silu_bf16, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -147,4 +147,25 @@ int ln3_planes_to_channels_last(const float* planes, int n_obj, int C, int H, in
   return planes_to_channels_last(planes, n_obj, C, H, W, out, static_cast<cudaStream_t>(stream));
 }
 
+int ln3_conv_nhwc(const ln3_conv_args* args, void* stream) {
+  if (!args) return set_error(LN3_EINVAL, "conv: null args");
+  return conv_nhwc(args, static_cast<cudaStream_t>(stream));
+}
+int ln3_groupnorm_stats(const float* x, const float* gamma, const float* beta, int N, int HW, int C,
+                        int G, float eps, float* scale, float* shift, void* stream) {
+  if (!x || !gamma || !beta || !scale || !shift) return set_error(LN3_EINVAL, "groupnorm: null pointer");
+  return groupnorm_stats(x, gamma, beta, N, HW, C, G, eps, scale, shift, static_cast<cudaStream_t>(stream));
+}
+int ln3_attn_single_head(const float* q, const float* k, const float* v, float* out, int N, int L,
+                         int C, void* stream) {
+  if (!q || !k || !v || !out) return set_error(LN3_EINVAL, "attn_single_head: null pointer");
+  return attn_single_head(q, k, v, out, N, L, C, static_cast<cudaStream_t>(stream));
+}
+int ln3_patch_embed_triplane(const float* x, const float* w, const float* bias, int B, int Cz, int S,
+                             int E, float in_mul, float* tokens, void* silu_bf16, void* stream) {
+  if (!x || !w || !tokens) return set_error(LN3_EINVAL, "patch_embed_triplane: null pointer");
+  return patch_embed_triplane(x, w, bias, B, Cz, S, E, in_mul, tokens, silu_bf16,
+                              static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

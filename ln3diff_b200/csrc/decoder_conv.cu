@@ -1,0 +1,283 @@
+// Convolutional tail of the tri-plane VAE decoder (fp32 SIMT, NHWC).
+//
+// Replaces the cuDNN / aten launches of the reference's `superresolution['conv_sr']` =
+// ldm Decoder(z_channels=1024, ch=32, ch_mult=[1,2,2,4], num_res_blocks=1, out_ch=32)
+// (ldm/modules/diffusionmodules/model.py:625-731: ResnetBlock :94-153, Upsample :54-69,
+// MemoryEfficientAttnBlock :209-272, GroupNorm(32, eps 1e-6) + swish :46-52) and of
+// PatchEmbedTriplane (vit/vit_triplane.py:58-108).
+//
+// Layout: activations are NHWC fp32.  The DiT2 decoder's token stream (3B, 16*16, 1024) already IS
+// NHWC, and the last conv writes (3B, 128, 128, 32) = exactly the channels-last tri-plane the ray
+// marcher gathers from, so the reference's '(b n) c h w' / 'b (n c) h w' permute copies disappear.
+//   conv_nhwc       3x3 (pad 1) or 1x1 conv + bias, optional fused GroupNorm-apply + swish on the
+//                   input (per (image, channel) scale/shift from groupnorm_stats), optional fused
+//                   nearest-2x upsample of the input, optional residual add
+//   groupnorm_stats per (image, group) mean / rstd -> per (image, channel) scale / shift
+//   attn_single_head  softmax(q k^T / sqrt(C)) v for the 256-token mid block (C = 128)
+//   patch_embed_triplane  grouped 2x2/s2 conv + the reference's channel interleave -> tokens
+// The decode is < 1 % of the pipeline's FLOPs (20 GFLOP / latent vs 307 TFLOP of sampling), so these
+// kernels favour exact fp32 parity with the reference over tensor-core throughput.
+#include "common.cuh"
+#include "ln3_internal.h"
+
+namespace ln3 {
+
+// ------------------------------------------------------------------ conv (NHWC, direct)
+// Block: 8x8 output pixels x COT output channels; 256 threads = 64 pixels x 4 channel groups, each
+// thread accumulates COT/4 channels.  Input channels are consumed in chunks of 16 staged in smem as
+// [cin][10x10 halo tile] (pixel fastest -> conflict-free reads), weights as [tap][cin][COT].
+static constexpr int kCT = 8;        // tile edge (pixels)
+static constexpr int kCinChunk = 16;
+
+template <int COT, int KS>
+__global__ void __launch_bounds__(256)
+conv_nhwc_kernel(const ln3_conv_args a) {
+  constexpr int HALO = (KS == 3) ? 1 : 0;
+  constexpr int TW = kCT + 2 * HALO;           // staged tile edge
+  constexpr int NACC = COT / 4;
+  __shared__ float s_in[kCinChunk][TW * TW + 1];
+  __shared__ __align__(16) float s_w[KS * KS][kCinChunk][COT];
+
+  const int n = blockIdx.z;
+  const int tiles_x = (a.W + kCT - 1) / kCT;
+  const int ty0 = (blockIdx.x / tiles_x) * kCT, tx0 = (blockIdx.x % tiles_x) * kCT;
+  const int co0 = blockIdx.y * COT;
+  const int pix = threadIdx.x & 63, q = threadIdx.x >> 6;
+  const int py = pix >> 3, px = pix & 7;
+  const int Hin = a.upsample ? a.H / 2 : a.H, Win = a.upsample ? a.W / 2 : a.W;
+
+  float acc[NACC];
+#pragma unroll
+  for (int i = 0; i < NACC; ++i) acc[i] = 0.f;
+
+  for (int c0 = 0; c0 < a.Cin; c0 += kCinChunk) {
+    // stage input tile (GroupNorm-apply + swish + nearest upsample fused into the load)
+    for (int i = threadIdx.x; i < TW * TW * kCinChunk; i += 256) {
+      const int ci = i % kCinChunk, t = i / kCinChunk;   // channel fastest in gmem (NHWC)
+      const int yy = ty0 + t / TW - HALO, xx = tx0 + t % TW - HALO;
+      float v = 0.f;
+      if (yy >= 0 && yy < a.H && xx >= 0 && xx < a.W && c0 + ci < a.Cin) {
+        const int ys = a.upsample ? (yy >> 1) : yy, xs = a.upsample ? (xx >> 1) : xx;
+        v = a.x[((static_cast<long long>(n) * Hin + ys) * Win + xs) * a.Cin + c0 + ci];
+        if (a.in_scale != nullptr) {
+          v = fmaf(v, a.in_scale[n * a.Cin + c0 + ci], a.in_shift[n * a.Cin + c0 + ci]);
+          if (a.in_swish) v = v / (1.f + __expf(-v));
+        }
+      }
+      s_in[ci][t] = v;
+    }
+    // stage weights [tap][cin][COT] from the repacked [KS*KS][Cin][Cout] tensor
+    for (int i = threadIdx.x; i < KS * KS * kCinChunk * COT; i += 256) {
+      const int co = i % COT, r = i / COT, ci = r % kCinChunk, tap = r / kCinChunk;
+      float w = 0.f;
+      if (c0 + ci < a.Cin && co0 + co < a.Cout)
+        w = a.w[(static_cast<long long>(tap) * a.Cin + c0 + ci) * a.Cout + co0 + co];
+      s_w[tap][ci][co] = w;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int tap = 0; tap < KS * KS; ++tap) {
+      const int t = (py + tap / KS) * TW + (px + tap % KS);
+#pragma unroll 4
+      for (int ci = 0; ci < kCinChunk; ++ci) {
+        const float xv = s_in[ci][t];
+        const float4* wp = reinterpret_cast<const float4*>(&s_w[tap][ci][q * NACC]);
+#pragma unroll
+        for (int i = 0; i < NACC / 4; ++i) {
+          const float4 w = wp[i];
+          acc[4 * i + 0] = fmaf(xv, w.x, acc[4 * i + 0]);
+          acc[4 * i + 1] = fmaf(xv, w.y, acc[4 * i + 1]);
+          acc[4 * i + 2] = fmaf(xv, w.z, acc[4 * i + 2]);
+          acc[4 * i + 3] = fmaf(xv, w.w, acc[4 * i + 3]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  const int oy = ty0 + py, ox = tx0 + px;
+  if (oy < a.H && ox < a.W) {
+    const long long o = ((static_cast<long long>(n) * a.H + oy) * a.W + ox) * a.Cout + co0 + q * NACC;
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) {
+      const int co = co0 + q * NACC + i;
+      if (co < a.Cout) {
+        float v = acc[i] + (a.bias ? a.bias[co] : 0.f);
+        if (a.residual) v += a.residual[o + i];
+        a.out[o + i] = v;
+      }
+    }
+  }
+}
+
+int conv_nhwc(const ln3_conv_args* a, cudaStream_t stream) {
+  if (a->N <= 0) return LN3_OK;
+  if (a->ksize != 1 && a->ksize != 3) return set_error(LN3_EUNSUPPORTED, "conv: ksize must be 1 or 3");
+  if (a->upsample && ((a->H | a->W) & 1)) return set_error(LN3_EINVAL, "conv: upsample needs even H, W");
+  if ((a->in_scale == nullptr) != (a->in_shift == nullptr))
+    return set_error(LN3_EINVAL, "conv: in_scale / in_shift must be given together");
+  if (!a->x || !a->w || !a->out) return set_error(LN3_EINVAL, "conv: null pointer");
+  const int tiles = ((a->H + kCT - 1) / kCT) * ((a->W + kCT - 1) / kCT);
+  const int cot = (a->Cout >= 64) ? 64 : 32;
+  dim3 grid(tiles, (a->Cout + cot - 1) / cot, a->N);
+  if (a->ksize == 3) {
+    if (cot == 64) conv_nhwc_kernel<64, 3><<<grid, 256, 0, stream>>>(*a);
+    else conv_nhwc_kernel<32, 3><<<grid, 256, 0, stream>>>(*a);
+  } else {
+    if (cot == 64) conv_nhwc_kernel<64, 1><<<grid, 256, 0, stream>>>(*a);
+    else conv_nhwc_kernel<32, 1><<<grid, 256, 0, stream>>>(*a);
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(LN3_ECUDA, "conv launch: %s", cudaGetErrorString(e));
+  count_launch();
+  return LN3_OK;
+}
+
+// ------------------------------------------------------------------ GroupNorm statistics
+// One block per (image, group): mean / biased variance over H*W*(C/G) elements (two-pass, fp32 with
+// a shifted second pass for accuracy) -> per-channel scale = gamma*rstd, shift = beta - mean*scale.
+__global__ void __launch_bounds__(256)
+groupnorm_stats_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                       const float* __restrict__ beta, int HW, int C, int G, float eps,
+                       float* __restrict__ scale, float* __restrict__ shift) {
+  __shared__ float red[32];
+  __shared__ float s_mean, s_rstd;
+  const int n = blockIdx.y, g = blockIdx.x;
+  const int cpg = C / G;
+  const float* xb = x + static_cast<long long>(n) * HW * C + g * cpg;
+  const long long cnt = static_cast<long long>(HW) * cpg;
+  auto block_sum = [&](float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float t = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.f;
+    if (threadIdx.x < 32) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    }
+    __syncthreads();
+    return t;  // valid in thread 0
+  };
+  float s = 0.f;
+  for (long long i = threadIdx.x; i < cnt; i += blockDim.x) s += xb[(i / cpg) * C + (i % cpg)];
+  s = block_sum(s);
+  if (threadIdx.x == 0) s_mean = s / static_cast<float>(cnt);
+  __syncthreads();
+  const float mean = s_mean;
+  float q = 0.f;
+  for (long long i = threadIdx.x; i < cnt; i += blockDim.x) {
+    const float d = xb[(i / cpg) * C + (i % cpg)] - mean;
+    q = fmaf(d, d, q);
+  }
+  q = block_sum(q);
+  if (threadIdx.x == 0) s_rstd = rsqrtf(q / static_cast<float>(cnt) + eps);
+  __syncthreads();
+  if (threadIdx.x < cpg) {
+    const int c = g * cpg + threadIdx.x;
+    const float sc = gamma[c] * s_rstd;
+    scale[n * C + c] = sc;
+    shift[n * C + c] = beta[c] - mean * sc;
+  }
+}
+
+int groupnorm_stats(const float* x, const float* gamma, const float* beta, int N, int HW, int C, int G,
+                    float eps, float* scale, float* shift, cudaStream_t stream) {
+  if (N <= 0) return LN3_OK;
+  if (C % G != 0 || C / G > 256) return set_error(LN3_EINVAL, "groupnorm: bad C / G");
+  groupnorm_stats_kernel<<<dim3(G, N), 256, 0, stream>>>(x, gamma, beta, HW, C, G, eps, scale, shift);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(LN3_ECUDA, "groupnorm launch: %s", cudaGetErrorString(e));
+  count_launch();
+  return LN3_OK;
+}
+
+// ------------------------------------------------------------------ single-head attention (mid block)
+// q, k, v, out: (N, L, C) fp32 NHWC tokens; one warp per query row, K / V rows streamed from L2.
+__global__ void __launch_bounds__(256)
+attn_single_head_kernel(const float* __restrict__ q, const float* __restrict__ k,
+                        const float* __restrict__ v, float* __restrict__ out, int L, int C, float scale) {
+  const int n = blockIdx.y;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= L) return;
+  const int lane = threadIdx.x & 31;
+  const int per = C / 32;  // <= 8
+  const float* qb = q + (static_cast<long long>(n) * L + row) * C;
+  const float* kb = k + static_cast<long long>(n) * L * C;
+  const float* vb = v + static_cast<long long>(n) * L * C;
+  float qr[8], o[8];
+  for (int i = 0; i < per; ++i) { qr[i] = qb[lane + 32 * i] * scale; o[i] = 0.f; }
+  float m = -INFINITY, l = 0.f;
+  for (int j = 0; j < L; ++j) {
+    float s = 0.f;
+    for (int i = 0; i < per; ++i) s = fmaf(qr[i], kb[static_cast<long long>(j) * C + lane + 32 * i], s);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    const float mn = fmaxf(m, s);
+    const float alpha = __expf(m - mn), p = __expf(s - mn);
+    l = l * alpha + p;
+    for (int i = 0; i < per; ++i) o[i] = fmaf(o[i], alpha, p * vb[static_cast<long long>(j) * C + lane + 32 * i]);
+    m = mn;
+  }
+  float* ob = out + (static_cast<long long>(n) * L + row) * C;
+  for (int i = 0; i < per; ++i) ob[lane + 32 * i] = o[i] / l;
+}
+
+int attn_single_head(const float* q, const float* k, const float* v, float* out, int N, int L, int C,
+                     cudaStream_t stream) {
+  if (N <= 0) return LN3_OK;
+  if (C % 32 != 0 || C > 256) return set_error(LN3_EUNSUPPORTED, "attn_single_head: C must be a multiple of 32, <= 256");
+  attn_single_head_kernel<<<dim3((L + 7) / 8, N), 256, 0, stream>>>(q, k, v, out, L, C,
+                                                                      1.0f / sqrtf(static_cast<float>(C)));
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(LN3_ECUDA, "attn_single_head launch: %s", cudaGetErrorString(e));
+  count_launch();
+  return LN3_OK;
+}
+
+// ------------------------------------------------------------------ PatchEmbedTriplane
+// Conv2d(3*Cz -> 3*E, k = s = 2, groups = 3) followed by reshape (B, 3E, h, w) -> (B, E, 3, h, w) ->
+// tokens (B, 3*h*w, E): tokens[b, n*hw + l, e] = conv_out[b, e*3 + n, l]   (vit_triplane.py:100-106),
+// where output channel o = e*3 + n belongs to conv group o / E and reads input channels
+// [ (o/E)*Cz, (o/E+1)*Cz ).  Optional SiLU'd bf16 copy (the DiT2 adaLN operand).
+__global__ void __launch_bounds__(256)
+patch_embed_triplane_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                            const float* __restrict__ bias, int B, int Cz, int S, int E,
+                            float in_mul, float* __restrict__ tokens, __nv_bfloat16* __restrict__ silu_bf16) {
+  __shared__ float xin[3][16][4];  // [group][cz][2x2]
+  const int P = S / 2, L = P * P;
+  const int tok = blockIdx.x;  // b * 3L + n * L + l
+  const int b = tok / (3 * L);
+  const int nl = tok - b * 3 * L;
+  const int n = nl / L, l = nl - n * L;
+  const int pi = l / P, pj = l - pi * P;
+  if (threadIdx.x < 3 * Cz * 4) {
+    const int g = threadIdx.x / (Cz * 4), r = threadIdx.x % (Cz * 4), c = r >> 2, p = (r >> 1) & 1, qq = r & 1;
+    xin[g][c][r & 3] = in_mul * x[((static_cast<long long>(b) * (3 * Cz) + g * Cz + c) * S + 2 * pi + p) * S + 2 * pj + qq];
+  }
+  __syncthreads();
+  const int K = Cz * 4;
+  for (int e = threadIdx.x; e < E; e += blockDim.x) {
+    const int o = e * 3 + n;
+    const int g = o / E;
+    float acc = bias ? bias[o] : 0.f;
+    const float* wr = w + static_cast<long long>(o) * K;
+    for (int kk = 0; kk < K; ++kk) acc = fmaf(wr[kk], xin[g][kk >> 2][kk & 3], acc);
+    tokens[static_cast<long long>(tok) * E + e] = acc;
+    if (silu_bf16) silu_bf16[static_cast<long long>(tok) * E + e] = __float2bfloat16(silu(acc));
+  }
+}
+
+int patch_embed_triplane(const float* x, const float* w, const float* bias, int B, int Cz, int S, int E,
+                         float in_mul, float* tokens, void* silu_bf16, cudaStream_t stream) {
+  if (B <= 0) return LN3_OK;
+  if (Cz <= 0 || Cz > 16 || (S & 1)) return set_error(LN3_EINVAL, "patch_embed_triplane: need 1 <= Cz <= 16, even S");
+  const int L = (S / 2) * (S / 2);
+  patch_embed_triplane_kernel<<<B * 3 * L, 256, 0, stream>>>(x, w, bias, B, Cz, S, E, in_mul, tokens,
+                                                             reinterpret_cast<__nv_bfloat16*>(silu_bf16));
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(LN3_ECUDA, "patch_embed_triplane launch: %s", cudaGetErrorString(e));
+  count_launch();
+  return LN3_OK;
+}
+
+}  // namespace ln3

@@ -34,4 +34,12 @@ int generate_rays(const float* cams, int V, int res, float* ray_o, float* ray_d,
 int planes_to_channels_last(const float* planes, int n_obj, int C, int H, int W, float* out,
                             cudaStream_t stream);
 
+int conv_nhwc(const ln3_conv_args* a, cudaStream_t stream);
+int groupnorm_stats(const float* x, const float* gamma, const float* beta, int N, int HW, int C, int G,
+                    float eps, float* scale, float* shift, cudaStream_t stream);
+int attn_single_head(const float* q, const float* k, const float* v, float* out, int N, int L, int C,
+                     cudaStream_t stream);
+int patch_embed_triplane(const float* x, const float* w, const float* bias, int B, int Cz, int S, int E,
+                         float in_mul, float* tokens, void* silu_bf16, cudaStream_t stream);
+
 }  // namespace ln3
