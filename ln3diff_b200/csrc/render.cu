@@ -140,6 +140,14 @@ struct BlockSmem {
 __device__ __forceinline__ float softplus_t(float x) {  // torch.nn.Softplus(beta=1, threshold=20)
   return x > 20.f ? x : log1pf(expf(x));
 }
+// softplus(x) = max(x, 0) + ln(1 + e^-|x|) with MUFU ex2 / lg2 (abs error ~1e-7: 1 + e^-|x| is in
+// [1, 2] where lg2.approx is accurate to 2^-22); used for the 64 hidden units of every sample.
+__device__ __forceinline__ float softplus_fast(float x) {
+  const float e = fast_exp2(-fabsf(x) * 1.4426950408889634f);
+  float l;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(1.f + e));
+  return fmaf(l, 0.6931471805599453f, fmaxf(x, 0.f));
+}
 
 __device__ __forceinline__ float warp_incl_prod(float v, int lane) {
 #pragma unroll
@@ -205,21 +213,34 @@ __device__ __forceinline__ void eval_batch(const RenderParams& p, const BlockSme
     plane_taps(sz, sx, p.H, p.W, 2 * HWC, &ws.tap_off[lane][8], &ws.tap_w[lane][8]);  // (z, x)
   }
   __syncwarp();
-  // phase B: lane = channel; one coalesced 128-byte line per tap
+  // phase B: 8 lanes x float4 cover one 128-byte texel; the 4 lane groups work on 4 samples at once,
+  // so one LDG.128 warp instruction fetches one tap for 4 samples (4 coalesced lines).
+  {
+    const int grp = lane >> 3, c4 = (lane & 7) * 4;
+    const float* pl_base = planes_obj + c4;
 #pragma unroll 2
-  for (int s = 0; s < 32; ++s) {
-    float f[3];
+    for (int s0 = 0; s0 < 32; s0 += 4) {
+      const int sidx = s0 + grp;
+      float4 f[3];
 #pragma unroll
-    for (int pl = 0; pl < 3; ++pl) {
-      const int4 o = *reinterpret_cast<const int4*>(&ws.tap_off[s][pl * 4]);
-      const float4 w = *reinterpret_cast<const float4*>(&ws.tap_w[s][pl * 4]);
-      const float v0 = __ldg(planes_obj + o.x + lane);
-      const float v1 = __ldg(planes_obj + o.y + lane);
-      const float v2 = __ldg(planes_obj + o.z + lane);
-      const float v3 = __ldg(planes_obj + o.w + lane);
-      f[pl] = ((v0 * w.x + v1 * w.y) + v2 * w.z) + v3 * w.w;
+      for (int pl = 0; pl < 3; ++pl) {
+        const int4 o = *reinterpret_cast<const int4*>(&ws.tap_off[sidx][pl * 4]);
+        const float4 w = *reinterpret_cast<const float4*>(&ws.tap_w[sidx][pl * 4]);
+        const float4 v0 = __ldg(reinterpret_cast<const float4*>(pl_base + o.x));
+        const float4 v1 = __ldg(reinterpret_cast<const float4*>(pl_base + o.y));
+        const float4 v2 = __ldg(reinterpret_cast<const float4*>(pl_base + o.z));
+        const float4 v3 = __ldg(reinterpret_cast<const float4*>(pl_base + o.w));
+        f[pl].x = ((v0.x * w.x + v1.x * w.y) + v2.x * w.z) + v3.x * w.w;
+        f[pl].y = ((v0.y * w.x + v1.y * w.y) + v2.y * w.z) + v3.y * w.w;
+        f[pl].z = ((v0.z * w.x + v1.z * w.y) + v2.z * w.z) + v3.z * w.w;
+        f[pl].w = ((v0.w * w.x + v1.w * w.y) + v2.w * w.z) + v3.w * w.w;
+      }
+      // sampled_features.mean(1)
+      ws.feat[sidx][c4 + 0] = ((f[0].x + f[1].x) + f[2].x) / 3.f;
+      ws.feat[sidx][c4 + 1] = ((f[0].y + f[1].y) + f[2].y) / 3.f;
+      ws.feat[sidx][c4 + 2] = ((f[0].z + f[1].z) + f[2].z) / 3.f;
+      ws.feat[sidx][c4 + 3] = ((f[0].w + f[1].w) + f[2].w) / 3.f;
     }
-    ws.feat[s][lane] = ((f[0] + f[1]) + f[2]) / 3.f;  // sampled_features.mean(1)
   }
   __syncwarp();
   // phase C: lane = sample; 32 -> 64 (softplus) -> 4
@@ -238,7 +259,7 @@ __device__ __forceinline__ void eval_batch(const RenderParams& p, const BlockSme
       acc = fmaf(x[c + 2], w.z, acc);
       acc = fmaf(x[c + 3], w.w, acc);
     }
-    const float h = softplus_t(acc);
+    const float h = softplus_fast(acc);
     y0 = fmaf(h, bs.w2[0][j], y0);
     y1 = fmaf(h, bs.w2[1][j], y1);
     y2 = fmaf(h, bs.w2[2][j], y2);

@@ -194,22 +194,24 @@ class DiT_TriLatent(nn.Module):
             raise RuntimeError("ln3diff_b200 DiT runs on CUDA only (no CPU fallback)")
         if self._prep is None:
             self.prepare()
+        kv = self._context_kv(context)
+        t = timesteps.to(device=x.device, dtype=torch.float32).contiguous()
+        return self._forward_impl(x.float().contiguous(), t, kv, in_scale)
+
+    def _forward_impl(self, x, t, kv, in_scale):
+        """The fixed launch sequence of one forward (capturable in a CUDA graph: no host syncs, all
+        intermediates in the per-batch workspace)."""
         P = self._prep
         B = x.shape[0]
         D, H, T = self.embed_dim, self.num_heads, self.pos_embed.shape[1]
         M = B * T
         ws = self._workspace(B)
-        kv = self._context_kv(context)
-        Lc = kv.shape[1]
-
-        t = timesteps.to(device=x.device, dtype=torch.float32).contiguous()
         ops.timestep_embedding(t, out=ws["tfeat"])
         ops.gemm(ws["tfeat"], P["t0_w"], P["t0_b"], act=ops.ACT_SILU, out=ws["th"])
         ops.gemm(ws["th"], P["t2_w"], P["t2_b"], act=ops.ACT_SILU, out=ws["st"])  # silu(t_emb)
         mod = ops.gemm(ws["st"], P["ada_w"], P["ada_b"], out_kind=ops.OUT_F32, out=ws["mod"])
 
-        xs = ops.patch_embed(x.float().contiguous(), P["pe_w"], P["pe_b"], P["pos"],
-                             in_scale=in_scale, out=ws["x"])
+        xs = ops.patch_embed(x, P["pe_w"], P["pe_b"], P["pos"], in_scale=in_scale, out=ws["x"])
         x2 = xs.view(M, D)
         qkv3 = ws["qkv"].view(B, T, 3 * D)
         att3 = ws["att"].view(B, T, D)
@@ -231,9 +233,41 @@ class DiT_TriLatent(nn.Module):
             ops.gemm(ws["h"], W["fc2_w"], W["fc2_b"], out_kind=ops.OUT_RESID_F32, out=x2,
                      gate=sl(5), gate_rows=T)
         f0 = self.depth * 6 * D
-        out = ops.final_layer(xs, mod[:, f0:f0 + D], mod[:, f0 + D:f0 + 2 * D], P["fin_w"],
-                              P["fin_b"], self.input_size)
-        return out
+        return ops.final_layer(xs, mod[:, f0:f0 + D], mod[:, f0 + D:f0 + 2 * D], P["fin_w"],
+                               P["fin_b"], self.input_size)
+
+    @torch.no_grad()
+    def capture_graph(self, B, context):
+        """CUDA-graph one forward for a fixed batch B and a fixed (step-invariant) context: the ~250
+        launches of a forward replay as one graph launch, removing the host launch gaps between the
+        short kernels.  Returns an object with static inputs .x (B,3C,S,S), .t (B,), .in_scale (B,),
+        static output .out and .replay()."""
+        if self._prep is None:
+            self.prepare()
+        if isinstance(context, dict):
+            context = context["crossattn"]
+        dev = context.device
+        kv = self._context_kv(context)
+
+        class _G:
+            pass
+
+        g = _G()
+        g.kv = kv  # keep the cached K/V alive: the graph holds raw pointers into it
+        g.x = torch.zeros(B, 3 * self.in_channels, self.input_size, self.input_size, device=dev)
+        g.t = torch.zeros(B, device=dev)
+        g.in_scale = torch.ones(B, device=dev)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(2):  # warm-up outside capture (function attributes, workspaces)
+                self._forward_impl(g.x, g.t, kv, g.in_scale)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        g.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g.graph):
+            g.out = self._forward_impl(g.x, g.t, kv, g.in_scale)
+        g.replay = g.graph.replay
+        return g
 
     @torch.no_grad()
     def forward_with_cfg(self, x, t, context, cfg_scale):

@@ -323,3 +323,85 @@ def render_views(planes_cl: torch.Tensor, ray_o: torch.Tensor, ray_d: torch.Tens
     a.box_warp, a.bbox_min, a.bbox_max = box_warp, bbox_min, bbox_max
     _lib.check(_lib.lib().ln3_render_views(C.byref(a), _lib.current_stream()), "ln3_render_views")
     return out
+
+
+def conv_nhwc(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor | None, *, ksize: int,
+              upsample: bool = False, gn: tuple | None = None, swish: bool = False,
+              residual: torch.Tensor | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
+    """NHWC fp32 conv (stride 1, pad ksize//2).  x (N,Hin,Win,Cin); w_packed (ksize*ksize, Cin, Cout);
+    gn = (scale, shift) (N,Cin) fuses GroupNorm-apply (+ swish) into the input load; upsample = fused
+    nearest 2x of the input; residual (N,H,W,Cout) is added to the result."""
+    _cuda(x, "x", torch.float32)
+    _cuda(w_packed, "w_packed", torch.float32)
+    _req(x.dim() == 4 and x.is_contiguous() and w_packed.dim() == 3 and w_packed.is_contiguous(), "bad conv operands")
+    N, Hin, Win, Cin = x.shape
+    _req(w_packed.shape[0] == ksize * ksize and w_packed.shape[1] == Cin, "weight/ksize mismatch")
+    Cout = w_packed.shape[2]
+    H, W = (2 * Hin, 2 * Win) if upsample else (Hin, Win)
+    if out is None:
+        out = torch.empty((N, H, W, Cout), device=x.device, dtype=torch.float32)
+    _req(out.shape == (N, H, W, Cout) and out.is_contiguous() and out.dtype == torch.float32, "bad out")
+    a = _lib.ConvArgs()
+    a.x, a.w, a.out = x.data_ptr(), w_packed.data_ptr(), out.data_ptr()
+    if bias is not None:
+        _cuda(bias, "bias", torch.float32)
+        a.bias = bias.data_ptr()
+    if gn is not None:
+        sc, sh = gn
+        _req(sc.shape == (N, Cin) and sh.shape == (N, Cin) and sc.is_contiguous() and sh.is_contiguous(), "bad gn")
+        a.in_scale, a.in_shift = sc.data_ptr(), sh.data_ptr()
+    if residual is not None:
+        _cuda(residual, "residual", torch.float32)
+        _req(residual.shape == out.shape and residual.is_contiguous(), "bad residual")
+        a.residual = residual.data_ptr()
+    a.N, a.H, a.W, a.Cin, a.Cout = N, H, W, Cin, Cout
+    a.ksize, a.upsample, a.in_swish = ksize, int(upsample), int(swish)
+    _lib.check(_lib.lib().ln3_conv_nhwc(C.byref(a), _lib.current_stream()), "ln3_conv_nhwc")
+    return out
+
+
+def groupnorm_stats(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, groups: int = 32,
+                    eps: float = 1e-6):
+    """x (N,H,W,C) fp32 NHWC -> per-(image, channel) (scale, shift) of GroupNorm(groups, C, eps)."""
+    _cuda(x, "x", torch.float32)
+    _req(x.dim() == 4 and x.is_contiguous(), "x must be contiguous NHWC")
+    N, H, W, Cc = x.shape
+    sc = torch.empty((N, Cc), device=x.device, dtype=torch.float32)
+    sh = torch.empty_like(sc)
+    _lib.check(_lib.lib().ln3_groupnorm_stats(_lib.ptr(x), _lib.ptr(gamma), _lib.ptr(beta), N, H * W, Cc, groups,
+                                              C.c_float(eps), _lib.ptr(sc), _lib.ptr(sh), _lib.current_stream()),
+               "ln3_groupnorm_stats")
+    return sc, sh
+
+
+def attn_single_head(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor) -> torch.Tensor:
+    """q/k/v (N, L, C) fp32 -> softmax(q k^T / sqrt(C)) v (the ldm mid-block attention core)."""
+    for t_ in (q, k, v):
+        _cuda(t_, "qkv", torch.float32)
+        _req(t_.is_contiguous() and t_.shape == q.shape, "q/k/v must be contiguous and equal-shaped")
+    N = q.shape[0]
+    Cc = q.shape[-1]
+    L = q.numel() // (N * Cc)
+    out = torch.empty_like(q)
+    _lib.check(_lib.lib().ln3_attn_single_head(_lib.ptr(q), _lib.ptr(k), _lib.ptr(v), _lib.ptr(out), N, L, Cc,
+                                               _lib.current_stream()), "ln3_attn_single_head")
+    return out
+
+
+def patch_embed_triplane(latent: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None,
+                         in_mul: float = 1.0, want_silu_bf16: bool = True):
+    """latent fp32 (B, 3*Cz, S, S) -> tokens fp32 (B, 3*(S/2)^2, E) [+ bf16 SiLU(tokens)]."""
+    _cuda(latent, "latent", torch.float32)
+    _cuda(weight, "weight", torch.float32)
+    _req(latent.is_contiguous() and weight.is_contiguous(), "latent/weight must be contiguous")
+    B, C3, S, _ = latent.shape
+    E3, Cz = weight.shape[0], weight.shape[1]
+    _req(C3 == 3 * Cz and E3 % 3 == 0 and weight.shape[2:] == (2, 2), "PatchEmbedTriplane shapes")
+    E = E3 // 3
+    T = 3 * (S // 2) ** 2
+    tok = torch.empty((B, T, E), device=latent.device, dtype=torch.float32)
+    sb = torch.empty((B, T, E), device=latent.device, dtype=torch.bfloat16) if want_silu_bf16 else None
+    _lib.check(_lib.lib().ln3_patch_embed_triplane(_lib.ptr(latent), _lib.ptr(weight), _lib.ptr(bias), B, Cz, S, E,
+                                                   C.c_float(in_mul), _lib.ptr(tok), _lib.ptr(sb),
+                                                   _lib.current_stream()), "ln3_patch_embed_triplane")
+    return tok, sb

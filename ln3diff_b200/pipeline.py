@@ -44,7 +44,7 @@ def edm_cfg_tables(num_steps: int, scale: float, B: int, device, dtype=torch.flo
 
 @torch.no_grad()
 def sample_t23d(model, randn: torch.Tensor, c: dict, uc: dict, num_steps: int = 250,
-                scale: float = 6.5, tables: dict | None = None) -> torch.Tensor:
+                scale: float = 6.5, tables: dict | None = None, use_graph: bool = True) -> torch.Tensor:
     """randn (B, 12, 32, 32) fp32 on the GPU (the reference draws it on the CPU generator and moves
     it, sgm_DiffusionEngine.py:395); c / uc = {'crossattn': (B, 77, ctx_dim)}.  Returns the
     denoised latents (B, 12, 32, 32) fp32."""
@@ -55,8 +55,20 @@ def sample_t23d(model, randn: torch.Tensor, c: dict, uc: dict, num_steps: int = 
         tables = edm_cfg_tables(num_steps, scale, B, randn.device)
     ctx = torch.cat((uc["crossattn"], c["crossattn"]), 0).contiguous()   # VanillaCFG order: (uc, c)
     x = (randn.float() * tables["init_scale"]).contiguous()
-    x2 = torch.empty((2 * B,) + tuple(x.shape[1:]), device=x.device, dtype=torch.float32)
     xa, xb = x, torch.empty_like(x)
+    if use_graph and num_steps >= 4:
+        # one CUDA graph = one DiT forward of the 2B CFG batch; replayed every step
+        g = model.capture_graph(2 * B, ctx)
+        for i in range(num_steps):
+            g.x[:B].copy_(xa)
+            g.x[B:].copy_(xa)
+            g.t.copy_(tables["t_idx"][i])
+            g.in_scale.copy_(tables["c_in"][i])
+            g.replay()
+            ops.sampler_affine_update(xa, tables["coef"][i], g.out[:B], g.out[B:], out=xb)
+            xa, xb = xb, xa
+        return xa.clone()
+    x2 = torch.empty((2 * B,) + tuple(x.shape[1:]), device=x.device, dtype=torch.float32)
     for i in range(num_steps):
         x2[:B].copy_(xa)
         x2[B:].copy_(xa)

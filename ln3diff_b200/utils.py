@@ -54,3 +54,32 @@ def orbit_cameras(V: int, radius: float = 1.7, focal: float = 1.3889) -> torch.T
         K = torch.tensor([focal, 0, 0.5, 0, focal, 0.5, 0, 0, 1.0])
         cams.append(torch.cat([c2w.reshape(-1), K]))
     return torch.stack(cams).float()
+
+
+OBJAVERSE_RENDERING_KWARGS = dict(  # nsr/script_util.py:433-465,761-797 (resolved preset)
+    image_resolution=256, disparity_space_sampling=False, clamp_mode="softplus", c_gen_conditioning_zero=True,
+    c_scale=1, superresolution_noise_mode="none", density_reg=0.25, density_reg_p_dist=0.004, reg_type="l1",
+    decoder_lr_mul=1, decoder_activation="sigmoid", sr_antialias=True, return_triplane_features=False,
+    return_sampling_details_flag=True, depth_resolution=64, depth_resolution_importance=64, ray_start="auto",
+    ray_end="auto", box_warp=0.9, white_back=True, radius_range=[1.5, 2], sampler_bbox_min=-0.45,
+    sampler_bbox_max=0.45, filter_out_of_bbox=True, PatchRaySampler=True, patch_rendering_resolution=45,
+    z_near=1.05, z_far=2.45)
+
+
+def build_ae_decoder(arch: str = "DiT2-L/2", image_size: int = 128, seed: int = 0, device: str | None = None):
+    """The AE decoder as create_3DAE_model assembles it for the Objaverse release
+    (nsr/script_util.py:1355-1429): Triplane renderer + DiT2 backbone + SD conv upsampler."""
+    from .dit.dit_decoder import DiT2_models
+    from .nsr.triplane import Triplane
+    from .vit.vit_triplane import (
+        RodinSR_256_fusionv6_ConvQuant_liteSR_dinoInit3DAttn_SD_B_3L_C_withrollout_withSD_D_ditDecoder as AEDec)
+    torch.manual_seed(seed)
+    D = {"DiT2-L/2": 1024, "DiT2-L/2-half": 1024, "DiT2-B/2": 768, "DiT2-S/2": 384}[arch]
+    vd = DiT2_models[arch](input_size=16, num_classes=0, learn_sigma=False, in_channels=D, mixed_prediction=False,
+                           context_dim=None, roll_out=True, plane_n=3, return_all_layers=False)
+    tri = Triplane(c_dim=25, img_resolution=image_size, img_channels=3, out_chans=96, triplane_size=224,
+                   rendering_kwargs=dict(OBJAVERSE_RENDERING_KWARGS), decoder_in_chans=32, decoder_output_dim=3)
+    m = AEDec(vd, tri, False, vae_p=2, ldm_z_channels=4, ldm_embed_dim=4)
+    derandomize_zero_init(m)
+    m.eval()
+    return m.to(device) if device else m

@@ -53,3 +53,21 @@ def render_inputs(res: int, n_views: int = len(RENDER_CAM_ROWS), plane_res: int 
     nc = torch.rand(n_views, M, 64, generator=g)
     nf = torch.rand(n_views, M, 64, generator=g)
     return planes, (w1, b1, w2, b2), nc, nf
+
+
+DECODER_ARCH, DECODER_DIM = "DiT2-S/2", 384
+SCALING_DIVIDER = 0.96806  # --triplane_scaling_divider of the release scripts
+
+
+def decoder_state_dict(shapes: dict) -> dict:
+    """Key-seeded synthetic AE-decoder weights; GroupNorm / norm scales are centred at 1."""
+    from .dit import synth_state_dict
+    sd = synth_state_dict(shapes, seed=9)
+    for k in sd:
+        if "norm" in k and k.endswith("weight") and sd[k].dim() == 1:
+            sd[k] = 1 + sd[k]
+    return sd
+
+
+def decoder_latent():
+    return torch.randn(1, 12, 32, 32, generator=torch.Generator().manual_seed(3))

@@ -146,6 +146,38 @@ def main():
         outs[f"weights_{vi}"] = r["weights_samples"][0].numpy()
         print("render view", vi, float(r["weights_samples"].mean()))
     np.savez_compressed(os.path.join(OUT, "render.npz"), **outs)
+    # ---------------------------------------------------------------- VAE decoder
+    import ldm.modules.diffusionmodules.model as lm
+    lm.XFORMERS_IS_AVAILBLE = True
+    lm.xformers = sys.modules["xformers"]
+    from dit.dit_decoder import DiT2_models
+    from einops import rearrange
+    from ldm.modules.diffusionmodules.model import Decoder
+    from vit.vit_triplane import PatchEmbedTriplane
+    arch, D = fx.DECODER_ARCH, fx.DECODER_DIM
+    with contextlib.redirect_stdout(io.StringIO()):
+        up = PatchEmbedTriplane(32, 2, 12, D, bias=True)
+        vd = DiT2_models[arch](input_size=16, num_classes=0, learn_sigma=False, in_channels=D,
+                               mixed_prediction=False, context_dim=None, roll_out=True, plane_n=3,
+                               return_all_layers=False)
+        vd.pos_embed = torch.nn.Parameter(torch.zeros(1, 768, D))   # vit_triplane.py:210
+        srd = Decoder(resolution=128, in_channels=3, ch=32, ch_mult=[1, 2, 2, 4], num_res_blocks=1, dropout=0.0,
+                      attn_resolutions=[], out_ch=32, z_channels=D)
+    assert type(srd.mid.attn_1).__name__ == "MemoryEfficientAttnBlock"
+    parts = (("superresolution.ldm_upsample.", up), ("vit_decoder.", vd), ("superresolution.conv_sr.", srd))
+    shapes = {pre + k: tuple(v.shape) for pre, m in parts for k, v in m.state_dict().items()}
+    sdd = fx.decoder_state_dict(shapes)
+    for pre, m in parts:
+        m.load_state_dict({k[len(pre):]: v for k, v in sdd.items() if k.startswith(pre)})
+    lat = fx.decoder_latent()
+    with torch.no_grad():
+        tok = vd(up(lat * fx.SCALING_DIVIDER))
+        z = rearrange(tok.reshape(1, 3, 16, 16, D), "b n h w c->(b n) c h w")
+        y = rearrange(srd(z), "(b n) c h w->b (n c) h w", n=3)
+    np.savez_compressed(os.path.join(OUT, "decoder.npz"), crop=y[:, :, 40:56, 40:56].numpy(),
+                        chan_mean=y.mean(dim=(0, 2, 3)).numpy(), chan_absmean=y.abs().mean(dim=(0, 2, 3)).numpy(),
+                        tokens_crop=tok[:, ::37, ::29].numpy())
+    print("decoder", tuple(y.shape), float(y.abs().max()))
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -87,3 +87,19 @@ def test_render_edge_cases():
     d2 = torch.nn.functional.normalize(torch.randn(res * res, 3, generator=g), dim=1)
     r2 = orender.render_rays(planes, osg, o2, d2, orender.OBJAVERSE_OPTS, nc[0], nf[0], return_debug=True)
     assert bool(r2["valid"].all()) and torch.isfinite(r2["rgb"]).all()
+
+
+def test_vae_decoder_matches_reference(golden):
+    from oracle import decoder as odec
+    from ln3diff_b200.utils import build_ae_decoder
+    g = golden("decoder.npz")
+    m = build_ae_decoder(fx.DECODER_ARCH)
+    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()
+              if k.startswith(("superresolution.ldm_upsample", "superresolution.conv_sr", "vit_decoder"))}
+    sd = fx.decoder_state_dict(shapes)
+    with torch.no_grad():
+        y = odec.vae_decode(sd, fx.DECODER_ARCH, fx.decoder_latent(), fx.SCALING_DIVIDER)
+    assert y.shape == (1, 96, 128, 128)
+    assert _rel(y[:, :, 40:56, 40:56], g["crop"]) < 1e-5
+    assert _rel(y.mean(dim=(0, 2, 3)), g["chan_mean"]) < 1e-4
+    assert _rel(y.abs().mean(dim=(0, 2, 3)), g["chan_absmean"]) < 1e-5
