@@ -34,6 +34,9 @@ int ln3_abi_version(void);
 const char* ln3_last_error(void);
 /* Number of kernels this library has launched in this process (for bench.py gpu_launches). */
 unsigned long long ln3_launch_count(void);
+/* A CUDA graph captured from these entry points re-executes its kernels without passing through
+ * the library: callers add the graph's kernel-node count per replay to keep the tally honest. */
+void ln3_add_launch_count(unsigned long long n);
 
 /* ------------------------------------------------------------------ GEMM (tcgen05 + TMA)
  * out = epilogue(A[M,K] . W[N,K]^T): replaces every nn.Linear on the path

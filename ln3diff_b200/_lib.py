@@ -117,6 +117,7 @@ def lib() -> C.CDLL:
         L.ln3_abi_version.restype = C.c_int
         L.ln3_last_error.restype = C.c_char_p
         L.ln3_launch_count.restype = C.c_ulonglong
+        L.ln3_add_launch_count.restype = None
         L.ln3_render_workspace_bytes.restype = C.c_size_t
         _lib = L
     return _lib
@@ -130,6 +131,10 @@ def check(rc: int, what: str = "ln3") -> None:
 
 def launch_count() -> int:
     return int(lib().ln3_launch_count())
+
+
+def add_launch_count(n: int) -> None:
+    lib().ln3_add_launch_count(C.c_ulonglong(n))
 
 
 def current_stream() -> C.c_void_p:

@@ -98,6 +98,7 @@ extern "C" {
 int ln3_abi_version(void) { return LN3_ABI_VERSION; }
 const char* ln3_last_error(void) { return g_err; }
 unsigned long long ln3_launch_count(void) { return g_launches.load(); }
+void ln3_add_launch_count(unsigned long long n) { g_launches.fetch_add(n); }
 
 int ln3_gemm_bf16(const ln3_gemm_args* args, void* stream) {
   if (!args) return set_error(LN3_EINVAL, "gemm: null args");

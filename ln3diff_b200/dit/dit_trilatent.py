@@ -13,7 +13,7 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
-from .. import ops
+from .. import _lib, ops
 from .._lib import NORM_LAYER, NORM_NONE
 from .dit_models_xformers import (CaptionEmbedder, DiTBlock, FinalLayer, T2IFinalLayer,
                                   TextCondDiTBlock, TimestepEmbedder, _PatchEmbed,
@@ -264,9 +264,15 @@ class DiT_TriLatent(nn.Module):
                 self._forward_impl(g.x, g.t, kv, g.in_scale)
         torch.cuda.current_stream(dev).wait_stream(side)
         g.graph = torch.cuda.CUDAGraph()
+        n0 = _lib.launch_count()
         with torch.cuda.graph(g.graph):
             g.out = self._forward_impl(g.x, g.t, kv, g.in_scale)
-        g.replay = g.graph.replay
+        g.n_kernels = _lib.launch_count() - n0
+
+        def replay():
+            g.graph.replay()
+            _lib.add_launch_count(g.n_kernels)
+        g.replay = replay
         return g
 
     @torch.no_grad()
