@@ -67,6 +67,15 @@ typedef struct ln3_gemm_args {
   int gate_rows;
   int act;
   int out_kind;
+  /* optional per-head RMSNorm of the first head_norm_nsec column sections (each head_norm_sec_cols
+   * wide, heads of 64 columns) before the bf16 store: y = x * rsqrt(mean_64(x^2) + eps) * w[sec][i].
+   * This is `q, k = self.q_norm(q), self.k_norm(k)` (qk_norm=True, RMSNorm(64, eps 1e-5):
+   * vit/vision_transformer.py:81-82,116; ldm/modules/attention.py:264-265,294) fused into the
+   * projection GEMM.  head_norm_w: fp32 [head_norm_nsec, 64] or NULL.  LN3_OUT_BF16 only. */
+  const float* head_norm_w;
+  int head_norm_nsec;
+  int head_norm_sec_cols;
+  float head_norm_eps;
 } ln3_gemm_args;
 
 int ln3_gemm_bf16(const ln3_gemm_args* args, void* stream);
@@ -89,6 +98,14 @@ typedef struct ln3_fmha_args {
   int B, H, Lq, Lkv, head_dim;
   long long q_ld, q_bs, k_ld, k_bs, v_ld, v_bs, o_ld, o_bs; /* elements */
   float scale;
+  /* optional second K/V source appended after the first along the sequence (Lkv must then be a
+   * multiple of 128): the step-invariant DINO tokens the I23D blocks concatenate to the latent
+   * tokens for self-attention (dit/dit_models_xformers.py:522-530) -- their K/V are cached per
+   * prompt and never copied.  k2/v2 NULL -> unused. */
+  const void* k2;
+  const void* v2;
+  int Lkv2;
+  long long k2_ld, k2_bs, v2_ld, v2_bs;
 } ln3_fmha_args;
 
 int ln3_fmha_fwd(const ln3_fmha_args* args, void* stream);

@@ -27,6 +27,8 @@ class GemmArgs(C.Structure):
         ("lda", C.c_longlong), ("ldw", C.c_longlong), ("ldo", C.c_longlong),
         ("ldo2", C.c_longlong), ("gate_ld", C.c_longlong),
         ("gate_rows", C.c_int), ("act", C.c_int), ("out_kind", C.c_int),
+        ("head_norm_w", C.c_void_p), ("head_norm_nsec", C.c_int), ("head_norm_sec_cols", C.c_int),
+        ("head_norm_eps", C.c_float),
     ]
 
 
@@ -38,6 +40,8 @@ class FmhaArgs(C.Structure):
         ("k_bs", C.c_longlong), ("v_ld", C.c_longlong), ("v_bs", C.c_longlong),
         ("o_ld", C.c_longlong), ("o_bs", C.c_longlong),
         ("scale", C.c_float),
+        ("k2", C.c_void_p), ("v2", C.c_void_p), ("Lkv2", C.c_int),
+        ("k2_ld", C.c_longlong), ("k2_bs", C.c_longlong), ("v2_ld", C.c_longlong), ("v2_bs", C.c_longlong),
     ]
 
 

@@ -35,6 +35,7 @@ static constexpr float kRescaleThreshold = 8.0f;  // log2 units
 
 struct FmhaParams {
   int Lq, Lkv;
+  int Lkv2;  // rows of the optional second K/V source (0 = none)
   float scale_log2;  // softmax scale * log2(e)
   __nv_bfloat16* out;
   long long out_ld, out_bs;  // row / batch stride (elements); head h at column h*64
@@ -42,7 +43,8 @@ struct FmhaParams {
 
 __global__ void __launch_bounds__(kFmhaThreads, 1)
 fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
-                const __grid_constant__ CUtensorMap tmap_v, const FmhaParams p) {
+                const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_k2,
+                const __grid_constant__ CUtensorMap tmap_v2, const FmhaParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -64,13 +66,18 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   const int q0 = blockIdx.x * 2 * kQT;
   const int head = blockIdx.y;
   const int batch = blockIdx.z;
-  const int nkv = (p.Lkv + kKT - 1) / kKT;
+  const int nkv1 = (p.Lkv + kKT - 1) / kKT;  // with a second source Lkv is a multiple of 128
+  const int nkv = nkv1 + (p.Lkv2 + kKT - 1) / kKT;
   const int ntiles = (q0 + kQT < p.Lq) ? 2 : 1;  // second tile entirely out of range -> skipped
 
   if (tid == 0) {
     tma_prefetch_desc(&tmap_q);
     tma_prefetch_desc(&tmap_k);
     tma_prefetch_desc(&tmap_v);
+    if (p.Lkv2 > 0) {
+      tma_prefetch_desc(&tmap_k2);
+      tma_prefetch_desc(&tmap_v2);
+    }
     mbar_init(q_full, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&kv_full[i], 1);
@@ -100,8 +107,13 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         const int b = j & 1;
         mbar_wait(&kv_empty[b], ((j >> 1) & 1) ^ 1);
         mbar_arrive_expect_tx(&kv_full[b], 2 * kTileBytes);
-        tma_load_3d(sK + b * kTileBytes, &tmap_k, &kv_full[b], head * kHD, j * kKT, batch);
-        tma_load_3d(sV + b * kTileBytes, &tmap_v, &kv_full[b], head * kHD, j * kKT, batch);
+        if (j < nkv1) {
+          tma_load_3d(sK + b * kTileBytes, &tmap_k, &kv_full[b], head * kHD, j * kKT, batch);
+          tma_load_3d(sV + b * kTileBytes, &tmap_v, &kv_full[b], head * kHD, j * kKT, batch);
+        } else {
+          tma_load_3d(sK + b * kTileBytes, &tmap_k2, &kv_full[b], head * kHD, (j - nkv1) * kKT, batch);
+          tma_load_3d(sV + b * kTileBytes, &tmap_v2, &kv_full[b], head * kHD, (j - nkv1) * kKT, batch);
+        }
       }
     }
   } else if (warp == 9) {
@@ -156,7 +168,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     float m_ref = -INFINITY, l_run = 0.f;
 
     for (int j = 0; j < nkv; ++j) {
-      const int kv_valid = p.Lkv - j * kKT;  // >= 1
+      const int kv_valid = (j < nkv1) ? p.Lkv - j * kKT : p.Lkv2 - (j - nkv1) * kKT;  // >= 1
       mbar_wait(&s_full[t], j & 1);
       tc_fence_after();
       uint32_t s[128];
@@ -265,21 +277,37 @@ int fmha_fwd(const ln3_fmha_args* a, cudaStream_t stream) {
       return set_error(LN3_ECUDA, "fmha: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  CUtensorMap tq, tk, tv;
+  if (a->k2 != nullptr || a->v2 != nullptr) {
+    if (!a->k2 || !a->v2 || a->Lkv2 <= 0) return set_error(LN3_EINVAL, "fmha: k2/v2/Lkv2 must be given together");
+    if (a->Lkv % kKT != 0) return set_error(LN3_EINVAL, "fmha: Lkv must be a multiple of 128 with a second K/V source");
+    if ((a->k2_ld | a->v2_ld | a->k2_bs | a->v2_bs) % 8 ||
+        ((reinterpret_cast<uintptr_t>(a->k2) | reinterpret_cast<uintptr_t>(a->v2)) & 15))
+      return set_error(LN3_EINVAL, "fmha: k2/v2 alignment");
+  }
+  CUtensorMap tq, tk, tv, tk2, tv2;
   int rc;
   const long long cols = static_cast<long long>(a->H) * kHD;
   if ((rc = make_tmap_3d_bf16(&tq, a->q, cols, a->Lq, a->B, a->q_ld, a->q_bs, kHD, kQT))) return rc;
   if ((rc = make_tmap_3d_bf16(&tk, a->k, cols, a->Lkv, a->B, a->k_ld, a->k_bs, kHD, kKT))) return rc;
   if ((rc = make_tmap_3d_bf16(&tv, a->v, cols, a->Lkv, a->B, a->v_ld, a->v_bs, kHD, kKT))) return rc;
+  const bool two = a->k2 != nullptr;
+  if (two) {
+    if ((rc = make_tmap_3d_bf16(&tk2, a->k2, cols, a->Lkv2, a->B, a->k2_ld, a->k2_bs, kHD, kKT))) return rc;
+    if ((rc = make_tmap_3d_bf16(&tv2, a->v2, cols, a->Lkv2, a->B, a->v2_ld, a->v2_bs, kHD, kKT))) return rc;
+  } else {
+    tk2 = tk;
+    tv2 = tv;
+  }
   FmhaParams p;
   p.Lq = a->Lq;
   p.Lkv = a->Lkv;
+  p.Lkv2 = two ? a->Lkv2 : 0;
   p.scale_log2 = a->scale * 1.4426950408889634f;
   p.out = reinterpret_cast<__nv_bfloat16*>(a->out);
   p.out_ld = a->o_ld;
   p.out_bs = a->o_bs;
   dim3 grid((a->Lq + 2 * kQT - 1) / (2 * kQT), a->H, a->B);
-  fmha_fwd_kernel<<<grid, kFmhaThreads, kFmhaSmem, stream>>>(tq, tk, tv, p);
+  fmha_fwd_kernel<<<grid, kFmhaThreads, kFmhaSmem, stream>>>(tq, tk, tv, tk2, tv2, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(LN3_ECUDA, "fmha launch: %s", cudaGetErrorString(e));
   count_launch();

@@ -214,6 +214,16 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n, int a_mn_ma
 __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }
+// erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7) with MUFU rcp / ex2: ~12 instructions instead of
+// erff's ~25; used where the result is rounded to bf16 anyway (FusedMLP epilogue).
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __fdividef(1.f, fmaf(0.3275911f, z, 1.f));
+  const float poly = t * (0.254829592f + t * (-0.284496736f + t * (1.421413741f + t * (-1.453152027f + t * 1.061405429f))));
+  const float e = poly * __expf(-z * z);           // 1 - erf(z)
+  const float erf_abs = 1.f - e;
+  return 0.5f * x * (1.f + copysignf(erf_abs, x));
+}
 __device__ __forceinline__ float gelu_tanh(float x) {
   const float k0 = 0.7978845608028654f, k1 = 0.044715f;
   return 0.5f * x * (1.0f + tanhf(k0 * (x + k1 * x * x * x)));

@@ -18,6 +18,7 @@ namespace ln3 {
 static constexpr int BM = 128;
 static constexpr int BK = 64;  // 64 bf16 = 128 bytes = one 128B-swizzle row
 static constexpr int kGemmThreads = 192;
+static constexpr int kStageLd = 36;  // floats per row of the epilogue transpose tile
 
 template <int BN>
 struct GemmCfg {
@@ -26,7 +27,8 @@ struct GemmCfg {
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = 2 * BN;  // two accumulator stages
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kEpiStageBytes = 4 * 32 * kStageLd * 4;  // 4 epilogue warps x 32x32 transpose tile
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + kEpiStageBytes;
 };
 
 struct GemmParams {
@@ -41,9 +43,12 @@ struct GemmParams {
   const float* gate;       // RESID: gate[(m / gate_rows) * gate_ld + n]; null -> 1
   int gate_rows;
   long long gate_ld;
+  const float* hn_w;       // per-head RMSNorm weights [nsec][64] (HN kernels only)
+  int hn_nsec, hn_sec_cols;
+  float hn_eps;
 };
 
-template <int BN>
+template <int BN, bool HN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
                  const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
@@ -59,6 +64,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
   uint64_t* tmem_full = bars + 2 * Cfg::kStages;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;            // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* stage_base = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes + 256);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -153,7 +159,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
   } else {
     // Epilogue warps 2..5 own TMEM lanes [32*(warp%4), +32).
+    // Phase 1 (lane = row): tcgen05.ld 32 columns, + bias, activation (or per-head RMSNorm), then
+    // transpose through a private 32x32 smem tile.  Phase 2 (lane = column): every global access of
+    // the warp is one contiguous row segment (128 B fp32 / 64 B bf16) -> 1 L1 wavefront per
+    // instruction instead of 32 (the per-thread-row layout was L1-wavefront bound on the residual
+    // epilogue: 375 TF/s on the K=1024 projections).
     const int quarter = warp & 3;
+    float* stage = stage_base + (warp - 2) * (32 * kStageLd);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
@@ -161,88 +173,91 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
       tile_coords(t, tm, tn);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const int m = tm * BM + quarter * 32 + lane;
-      const bool row_ok = m < p.M;
+      const int m_base = tm * BM + quarter * 32;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
-      const float* gate_row = nullptr;
-      if (p.out_kind == LN3_OUT_RESID_F32 && p.gate != nullptr && row_ok)
-        gate_row = p.gate + static_cast<long long>(m / p.gate_rows) * p.gate_ld;
+      constexpr int CW = HN ? 64 : 32;  // columns per pass
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32(t_row + c, v);
-        tmem_ld_wait();
+      for (int c = 0; c < BN; c += CW) {
         const int n0 = tn * BN + c;
-        float f[32];
+        float f[CW];
+        {
+          uint32_t v[CW];
+          tmem_ld_32x32(t_row + c, v);
+          if constexpr (HN) tmem_ld_32x32(t_row + c + 32, v + 32);
+          tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+          for (int i = 0; i < CW; ++i) f[i] = __uint_as_float(v[i]);
+        }
         if (p.bias != nullptr) {
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) {
+          for (int i = 0; i < CW; i += 4) {
             const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + i));
-            f[i] += b.x;
-            f[i + 1] += b.y;
-            f[i + 2] += b.z;
-            f[i + 3] += b.w;
+            f[i] += b.x; f[i + 1] += b.y; f[i + 2] += b.z; f[i + 3] += b.w;
           }
         }
-        if (p.act == LN3_ACT_GELU_ERF) {
+        if constexpr (HN) {
+          const int sec = n0 / p.hn_sec_cols;
+          if (sec < p.hn_nsec) {
+            float ss = 0.f;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] = gelu_erf(f[i]);
-        } else if (p.act == LN3_ACT_GELU_TANH) {
+            for (int i = 0; i < 64; ++i) ss = fmaf(f[i], f[i], ss);
+            const float r = rsqrtf(ss * (1.0f / 64.0f) + p.hn_eps);
+            const float* w = p.hn_w + sec * 64;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] = gelu_tanh(f[i]);
-        } else if (p.act == LN3_ACT_SILU) {
+            for (int i = 0; i < 64; i += 4) {
+              const float4 ww = __ldg(reinterpret_cast<const float4*>(w + i));
+              f[i] *= r * ww.x; f[i + 1] *= r * ww.y; f[i + 2] *= r * ww.z; f[i + 3] *= r * ww.w;
+            }
+          }
+        } else {
+          if (p.act == LN3_ACT_GELU_ERF) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] = silu(f[i]);
+            for (int i = 0; i < CW; ++i) f[i] = gelu_erf_fast(f[i]);
+          } else if (p.act == LN3_ACT_GELU_TANH) {
+#pragma unroll
+            for (int i = 0; i < CW; ++i) f[i] = gelu_tanh(f[i]);
+          } else if (p.act == LN3_ACT_SILU) {
+#pragma unroll
+            for (int i = 0; i < CW; ++i) f[i] = silu(f[i]);
+          }
         }
-        if (row_ok) {
-          if (p.out_kind == LN3_OUT_BF16) {
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + m * p.ldo + n0;
 #pragma unroll
-            for (int i = 0; i < 32; i += 8) {
-              uint4 q;
-              q.x = pack_bf16x2(f[i], f[i + 1]);
-              q.y = pack_bf16x2(f[i + 2], f[i + 3]);
-              q.z = pack_bf16x2(f[i + 4], f[i + 5]);
-              q.w = pack_bf16x2(f[i + 6], f[i + 7]);
-              *reinterpret_cast<uint4*>(o + i) = q;
+        for (int h = 0; h < CW; h += 32) {
+          // transpose 32x32 through smem (row stride 36 floats: conflict-free STS.128 / LDS.32)
+#pragma unroll
+          for (int i = 0; i < 32; i += 4)
+            *reinterpret_cast<float4*>(stage + lane * kStageLd + i) =
+                make_float4(f[h + i], f[h + i + 1], f[h + i + 2], f[h + i + 3]);
+          __syncwarp();
+          const int col = n0 + h + lane;
+          if (p.out_kind == LN3_OUT_BF16) {
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + col;
+#pragma unroll 8
+            for (int rr = 0; rr < 32; ++rr) {
+              const int m = m_base + rr;
+              if (m < p.M) o[m * p.ldo] = __float2bfloat16(stage[rr * kStageLd + lane]);
             }
           } else if (p.out_kind == LN3_OUT_F32) {
-            float* o = reinterpret_cast<float*>(p.out) + m * p.ldo + n0;
-#pragma unroll
-            for (int i = 0; i < 32; i += 4)
-              *reinterpret_cast<float4*>(o + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
-          } else {  // LN3_OUT_RESID_F32: x[m,n] += gate * f
-            float* o = reinterpret_cast<float*>(p.out) + m * p.ldo + n0;
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              float4 x = *reinterpret_cast<const float4*>(o + i);
-              float4 g = make_float4(1.f, 1.f, 1.f, 1.f);
-              if (gate_row != nullptr) g = __ldg(reinterpret_cast<const float4*>(gate_row + n0 + i));
-              x.x = fmaf(g.x, f[i], x.x);
-              x.y = fmaf(g.y, f[i + 1], x.y);
-              x.z = fmaf(g.z, f[i + 2], x.z);
-              x.w = fmaf(g.w, f[i + 3], x.w);
-              *reinterpret_cast<float4*>(o + i) = x;
-              f[i] = x.x;
-              f[i + 1] = x.y;
-              f[i + 2] = x.z;
-              f[i + 3] = x.w;
+            float* o = reinterpret_cast<float*>(p.out) + col;
+#pragma unroll 8
+            for (int rr = 0; rr < 32; ++rr) {
+              const int m = m_base + rr;
+              if (m < p.M) o[m * p.ldo] = stage[rr * kStageLd + lane];
             }
-            if (p.out2 != nullptr) {
-              __nv_bfloat16* o2 = p.out2 + m * p.ldo2 + n0;
-#pragma unroll
-              for (int i = 0; i < 32; i += 8) {
-                uint4 q;
-                q.x = pack_bf16x2(f[i], f[i + 1]);
-                q.y = pack_bf16x2(f[i + 2], f[i + 3]);
-                q.z = pack_bf16x2(f[i + 4], f[i + 5]);
-                q.w = pack_bf16x2(f[i + 6], f[i + 7]);
-                *reinterpret_cast<uint4*>(o2 + i) = q;
+          } else {  // LN3_OUT_RESID_F32: x[m,n] += gate * val  (+ bf16 copy of the new x)
+            float* o = reinterpret_cast<float*>(p.out) + col;
+#pragma unroll 4
+            for (int rr = 0; rr < 32; ++rr) {
+              const int m = m_base + rr;
+              if (m < p.M) {
+                const float g = p.gate ? __ldg(p.gate + static_cast<long long>(m / p.gate_rows) * p.gate_ld + col) : 1.f;
+                const float xn = fmaf(g, stage[rr * kStageLd + lane], o[m * p.ldo]);
+                o[m * p.ldo] = xn;
+                if (p.out2 != nullptr) p.out2[m * p.ldo2 + col] = __float2bfloat16(xn);
               }
             }
           }
+          __syncwarp();
         }
       }
       tc_fence_before();
@@ -262,13 +277,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
 }
 
 // ---------------------------------------------------------------------------------- host
-template <int BN>
+template <int BN, bool HN>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
                        int num_sms, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<BN>,
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<BN, HN>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::kSmemBytes);
     if (e != cudaSuccess) return set_error(LN3_ECUDA, "gemm: cudaFuncSetAttribute: %s",
@@ -277,7 +292,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
   }
   const int tiles = ((p.M + BM - 1) / BM) * (p.N / BN);
   const int grid = tiles < num_sms ? tiles : num_sms;
-  gemm_bf16_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+  gemm_bf16_kernel<BN, HN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(LN3_ECUDA, "gemm launch: %s", cudaGetErrorString(e));
   count_launch();
@@ -317,9 +332,21 @@ int gemm_bf16(const ln3_gemm_args* a, cudaStream_t stream) {
   p.gate = a->gate;
   p.gate_rows = a->gate_rows > 0 ? a->gate_rows : 1;
   p.gate_ld = a->gate_ld;
+  p.hn_w = a->head_norm_w;
+  p.hn_nsec = a->head_norm_nsec;
+  p.hn_sec_cols = a->head_norm_sec_cols;
+  p.hn_eps = a->head_norm_eps;
   const int sms = device_sm_count();
-  if (bn == 256) return launch_gemm<256>(ta, tb, p, sms, stream);
-  return launch_gemm<128>(ta, tb, p, sms, stream);
+  if (a->head_norm_w != nullptr) {
+    if (a->out_kind != LN3_OUT_BF16 || a->act != LN3_ACT_NONE)
+      return set_error(LN3_EINVAL, "gemm: head_norm needs LN3_OUT_BF16 and no activation");
+    if (a->head_norm_nsec <= 0 || a->head_norm_sec_cols <= 0 || a->head_norm_sec_cols % 64 != 0)
+      return set_error(LN3_EINVAL, "gemm: head_norm sections must be positive multiples of 64 columns");
+    if (bn == 256) return launch_gemm<256, true>(ta, tb, p, sms, stream);
+    return launch_gemm<128, true>(ta, tb, p, sms, stream);
+  }
+  if (bn == 256) return launch_gemm<256, false>(ta, tb, p, sms, stream);
+  return launch_gemm<128, false>(ta, tb, p, sms, stream);
 }
 
 }  // namespace ln3

@@ -31,7 +31,8 @@ def _cuda(t: torch.Tensor, name: str, dtype=None) -> None:
 def gemm(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None, *,
          act: int = ACT_NONE, out_kind: int = OUT_BF16, out: torch.Tensor | None = None,
          out2: torch.Tensor | None = None, gate: torch.Tensor | None = None,
-         gate_rows: int = 1) -> torch.Tensor:
+         gate_rows: int = 1, head_norm: torch.Tensor | None = None, head_norm_sec_cols: int = 0,
+         head_norm_eps: float = 1e-5) -> torch.Tensor:
     """out = epilogue(a @ w.T); a (M,K) bf16, w (N,K) bf16 (nn.Linear weight layout).
 
     OUT_RESID_F32: `out` is the fp32 residual stream (M,N), updated in place with
@@ -67,13 +68,20 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None, *,
         _req(gate.dim() == 2 and gate.shape[1] == N and gate.stride(1) == 1, "gate must be (G,N)")
         _req(gate.shape[0] * gate_rows >= M, "gate has too few rows")
         args.gate, args.gate_ld, args.gate_rows = gate.data_ptr(), gate.stride(0), gate_rows
+    if head_norm is not None:
+        _cuda(head_norm, "head_norm", torch.float32)
+        _req(head_norm.dim() == 2 and head_norm.shape[1] == 64 and head_norm.is_contiguous(),
+             "head_norm must be contiguous (nsec, 64)")
+        args.head_norm_w, args.head_norm_nsec = head_norm.data_ptr(), head_norm.shape[0]
+        args.head_norm_sec_cols, args.head_norm_eps = head_norm_sec_cols, head_norm_eps
     args.act, args.out_kind = act, out_kind
     _lib.check(_lib.lib().ln3_gemm_bf16(C.byref(args), _lib.current_stream()), "ln3_gemm_bf16")
     return out
 
 
 def fmha(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, *,
-         out: torch.Tensor | None = None, scale: float | None = None) -> torch.Tensor:
+         out: torch.Tensor | None = None, scale: float | None = None,
+         k2: torch.Tensor | None = None, v2: torch.Tensor | None = None) -> torch.Tensor:
     """softmax(q k^T * scale) v per head.  q (B,Lq,H*64), k/v (B,Lkv,H*64) bf16 views with unit
     inner stride (slices of a packed qkv buffer are fine); returns (B,Lq,H*64) bf16."""
     for name, t in (("q", q), ("k", k), ("v", v)):
@@ -95,6 +103,13 @@ def fmha(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, *,
     a.v_ld, a.v_bs = v.stride(1), v.stride(0)
     a.o_ld, a.o_bs = out.stride(1), out.stride(0)
     a.scale = float(scale if scale is not None else 64 ** -0.5)
+    if k2 is not None:
+        for name, t in (("k2", k2), ("v2", v2)):
+            _cuda(t, name, torch.bfloat16)
+            _req(t.dim() == 3 and t.stride(2) == 1 and t.shape[0] == B and t.shape[2] == C_, f"{name} must be (B,L2,H*64)")
+        _req(k2.shape == v2.shape, "k2/v2 shape mismatch")
+        a.k2, a.v2, a.Lkv2 = k2.data_ptr(), v2.data_ptr(), k2.shape[1]
+        a.k2_ld, a.k2_bs, a.v2_ld, a.v2_bs = k2.stride(1), k2.stride(0), v2.stride(1), v2.stride(0)
     _lib.check(_lib.lib().ln3_fmha_fwd(C.byref(a), _lib.current_stream()), "ln3_fmha_fwd")
     return out
 

@@ -34,6 +34,18 @@ def build_t23d(arch: str = "DiT-L/2", seed: int = 0, device: str | None = None):
     return m.to(device) if device else m
 
 
+def build_i23d(arch: str = "DiT-PixArt-L/2", seed: int = 0, device: str | None = None):
+    """I23D denoiser as the release builds it (DiT_models_i23d[arch](..., context_dim=1024,
+    pooling_ctx_dim=768), guided_diffusion/script_util.py:152-252)."""
+    from .dit.dit_i23d import DiT_models
+    torch.manual_seed(seed)
+    m = DiT_models[arch](input_size=32, num_classes=0, learn_sigma=False, in_channels=4, context_dim=1024,
+                         pooling_ctx_dim=768, roll_out=True)
+    derandomize_zero_init(m)
+    m.eval()
+    return m.to(device) if device else m
+
+
 def orbit_cameras(V: int, radius: float = 1.7, focal: float = 1.3889) -> torch.Tensor:
     """(V, 25) synthetic camera rows in the layout of the reference's assets/objv_eval_pose.pt:
     16 row-major cam2world (OpenCV convention, looking at the origin) + 9 normalised intrinsics

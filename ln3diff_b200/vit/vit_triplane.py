@@ -124,7 +124,7 @@ class RodinSR_256_fusionv6_ConvQuant_liteSR_dinoInit3DAttn_SD_B_3L_C_withrollout
         M = B * T
         _, sc_bf = ops.patch_embed_triplane(latent.float().contiguous(), P["up_w"], P["up_b"], in_mul)
         sc2 = sc_bf.view(M, D)                                   # SiLU(c), the adaLN operand of every block
-        x = P["pos"].expand(B, T, D).contiguous()
+        x = P["pos"].expand(B, T, D).clone()   # the residual stream is updated in place: never alias the weights
         x2 = x.view(M, D)
         dev = latent.device
         mod = torch.empty(M, 6 * D, device=dev, dtype=torch.float32)

@@ -180,3 +180,46 @@ def synth_state_dict(shapes: dict, seed: int = 7, keep: dict | None = None) -> d
         else:
             sd[k] = torch.randn(shp, generator=g) * 0.02
     return sd
+
+
+I23D_SIZES = {"DiT-PixArt-L/2": dict(depth=24, hidden=1024, heads=16),
+              "DiT-PixArt-B/2": dict(depth=12, hidden=768, heads=12)}
+
+
+def dit_i23d_pixart_forward(sd: dict, arch: str, x: torch.Tensor, timesteps: torch.Tensor,
+                            context: dict) -> torch.Tensor:
+    """DiT_I23D_PixelArt(vit_blk=ImageCondDiTBlockPixelArtRMSNorm, T2IFinalLayer).forward, fp32.
+
+    Restates dit/dit_i23d.py:173-290 (model), dit/dit_models_xformers.py:481-539,604-618 (block with
+    the shared adaLN + per-block scale_shift_table, RMSNorm pre-norms), :61-84 (T2IFinalLayer),
+    vit/vision_transformer.py:106-124 with qk_norm, ldm/modules/attention.py:278-307 with qk_norm.
+    context = {'vector': (B, pooling_ctx_dim), 'crossattn': (B, 256, 1024 clip | 1024 dino)}."""
+    cfg = I23D_SIZES[arch]
+    heads, depth = cfg["heads"], cfg["depth"]
+    sd = {k: v.float() for k, v in sd.items()}
+    x = x.float()
+    B = x.shape[0]
+    vec, ca = context["vector"].float(), context["crossattn"].float()
+    cls = F.linear(F.layer_norm(vec, (vec.shape[-1],), sd["cap_embedder.0.weight"], sd["cap_embedder.0.bias"], 1e-5),
+                   sd["cap_embedder.1.weight"], sd["cap_embedder.1.bias"])
+    clip = rms_norm(ca[..., :1024], sd["attention_y_norm.weight"], 1e-5)
+    dino = F.linear(F.gelu(F.linear(ca[..., 1024:], sd["dino_proj.y_proj.fc1.weight"], sd["dino_proj.y_proj.fc1.bias"]),
+                           approximate="tanh"), sd["dino_proj.y_proj.fc2.weight"], sd["dino_proj.y_proj.fc2.bias"])
+    t = timestep_embedding(timesteps.float())
+    t = F.linear(F.silu(F.linear(t, sd["t_embedder.mlp.0.weight"], sd["t_embedder.mlp.0.bias"])),
+                 sd["t_embedder.mlp.2.weight"], sd["t_embedder.mlp.2.bias"]) + cls
+    t0 = F.linear(F.silu(t), sd["adaLN_modulation.1.weight"], sd["adaLN_modulation.1.bias"])
+    h = patch_embed_rollout(sd, x) + sd["pos_embed"]
+    T = h.shape[1]
+    for i in range(depth):
+        p = f"blocks.{i}."
+        mod = sd[p + "scale_shift_table"][None] + t0.reshape(B, 6, -1)
+        sh_a, sc_a, g_a, sh_m, sc_m, g_m = mod.chunk(6, dim=1)  # each (B,1,D)
+        a_in = torch.cat([rms_norm(h, sd[p + "norm1.weight"], 1e-5) * (1 + sc_a) + sh_a, dino], dim=1)
+        h = h + g_a * self_attention(sd, p + "attn.", a_in, heads, qk_norm=True)[:, :T]
+        h = h + cross_attention(sd, p + "cross_attn.", h, clip, heads, qk_norm=True)
+        h = h + g_m * fused_mlp(sd, p + "mlp.", rms_norm(h, sd[p + "norm2.weight"], 1e-5) * (1 + sc_m) + sh_m)
+    shift, scale = (sd["final_layer.scale_shift_table"][None] + t[:, None]).chunk(2, dim=1)
+    h = layer_norm(h) * (1 + scale) + shift
+    h = F.linear(h, sd["final_layer.linear.weight"], sd["final_layer.linear.bias"])
+    return unpatchify_rollout(h, sd["final_layer.linear.weight"].shape[0] // 4).contiguous()

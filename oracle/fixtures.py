@@ -71,3 +71,24 @@ def decoder_state_dict(shapes: dict) -> dict:
 
 def decoder_latent():
     return torch.randn(1, 12, 32, 32, generator=torch.Generator().manual_seed(3))
+
+
+I23D_ARCH = "DiT-PixArt-B/2"
+
+
+def i23d_inputs():
+    g = torch.Generator().manual_seed(13)
+    x = torch.randn(2, 12, 32, 32, generator=g)
+    t = torch.tensor([0.1, 0.7])
+    ctx = {"vector": torch.randn(2, 768, generator=g), "crossattn": torch.randn(2, 256, 2048, generator=g)}
+    return x, t, ctx
+
+
+def i23d_state_dict(shapes: dict, pos_embed: torch.Tensor) -> dict:
+    from .dit import synth_state_dict
+    sd = synth_state_dict(shapes, seed=5, keep={"pos_embed": pos_embed})
+    for k in sd:
+        if (k.endswith("norm.weight") or "norm1.weight" in k or "norm2.weight" in k
+                or k == "cap_embedder.0.weight" or k.endswith("attention_y_norm.weight")):
+            sd[k] = 1 + sd[k]
+    return sd

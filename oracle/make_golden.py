@@ -55,6 +55,22 @@ def main():
                         pos_embed_checksum=np.float64(ref.state_dict()["pos_embed"].double().sum().item()))
     print("dit_t23d", y.shape, float(y.abs().max()))
 
+    # ---------------------------------------------------------------- DiT I23D (PixArt) forward
+    import dit.dit_i23d as di
+    with contextlib.redirect_stdout(io.StringIO()):
+        ref2 = di.DiT_models[fx.I23D_ARCH](input_size=32, num_classes=0, learn_sigma=False, in_channels=4,
+                                           context_dim=1024, pooling_ctx_dim=768, roll_out=True)
+    ref2.eval()
+    assert type(ref2).__name__ == "DiT_I23D_PixelArt" and type(ref2.blocks[0]).__name__ == "ImageCondDiTBlockPixelArtRMSNorm"
+    shapes2 = {k: tuple(v.shape) for k, v in ref2.state_dict().items()}
+    ref2.load_state_dict(fx.i23d_state_dict(shapes2, ref2.state_dict()["pos_embed"]))
+    xi, ti, ci = fx.i23d_inputs()
+    with torch.no_grad():
+        yi = ref2(xi, ti, ci)
+        yc = ref2.forward_with_cfg(xi, ti, ci, 4.0)
+    np.savez_compressed(os.path.join(OUT, "dit_i23d.npz"), out=yi.numpy(), out_cfg=yc.numpy())
+    print("dit_i23d", yi.shape, float(yi.abs().max()))
+
     # ---------------------------------------------------------------- samplers (toy network)
     from sgm.modules.diffusionmodules.denoiser import DiscreteDenoiser
     from sgm.modules.diffusionmodules.sampling import EulerEDMSampler

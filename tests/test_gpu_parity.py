@@ -396,3 +396,66 @@ def test_latent_to_pixels_end_to_end(dev, golden):
     # bf16 DiT2 features feed an fp32 renderer: pixels follow the decoder tolerance
     assert _rel(out["image_raw"][0], ref["image_raw"]) < 3e-2
     assert _rel(out["image_mask"][0], ref["image_mask"]) < 3e-2
+
+
+# ------------------------------------------------------------------ I23D (flow matching)
+def test_gemm_head_rmsnorm_and_fmha_second_kv(dev):
+    from ln3diff_b200 import ops
+    from oracle import dit as odit
+    g = torch.Generator().manual_seed(17)
+    M, D, H = 300, 256, 4
+    a = (torch.randn(M, 128, generator=g) * 0.5).bfloat16()
+    w = (torch.randn(3 * D, 128, generator=g) * 0.1).bfloat16()
+    b = torch.randn(3 * D, generator=g)
+    nw = 1 + 0.1 * torch.randn(2, 64, generator=g)
+    ref = (a.float() @ w.float().t() + b).reshape(M, 3, H, 64)
+    ref[:, 0] = odit.rms_norm(ref[:, 0], nw[0], 1e-5)
+    ref[:, 1] = odit.rms_norm(ref[:, 1], nw[1], 1e-5)
+    out = ops.gemm(a.to(dev), w.to(dev), b.to(dev), head_norm=nw.to(dev), head_norm_sec_cols=D)
+    assert _rel(out, ref.reshape(M, 3 * D)) < 4e-3
+    B, Lq, L1, L2 = 2, 200, 256, 77
+    q = torch.randn(B, Lq, D, generator=g).bfloat16()
+    k1, v1 = torch.randn(B, L1, D, generator=g).bfloat16(), torch.randn(B, L1, D, generator=g).bfloat16()
+    k2, v2 = torch.randn(B, L2, D, generator=g).bfloat16(), torch.randn(B, L2, D, generator=g).bfloat16()
+    out = ops.fmha(q.to(dev), k1.to(dev), v1.to(dev), H, k2=k2.to(dev), v2=v2.to(dev))
+    sp = lambda t_: t_.float().reshape(B, -1, H, 64).transpose(1, 2)
+    ref = F.scaled_dot_product_attention(sp(q), sp(torch.cat([k1, k2], 1)), sp(torch.cat([v1, v2], 1)))
+    assert _rel(out, ref.transpose(1, 2).reshape(B, Lq, D)) < 6e-3
+
+
+def test_dit_i23d_forward_matches_reference_golden(dev, golden):
+    from ln3diff_b200.utils import build_i23d
+    from oracle import fixtures as fx
+    g = golden("dit_i23d.npz")
+    m = build_i23d(fx.I23D_ARCH)
+    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    m.load_state_dict(fx.i23d_state_dict(shapes, m.state_dict()["pos_embed"]))
+    m = m.to(dev)
+    x, t, ctx = fx.i23d_inputs()
+    cd = {k: v.to(dev) for k, v in ctx.items()}
+    out = m(x.to(dev), t.to(dev), cd)
+    assert out.dtype == torch.float32 and out.shape == (2, 12, 32, 32)
+    assert _rel(out, g["out"]) < 2e-2
+    assert _rel(m.forward_with_cfg(x.to(dev), t.to(dev), cd, 4.0), g["out_cfg"]) < 3e-2
+
+
+def test_flow_euler_cfg_sampler_vs_oracle(dev):
+    """BASELINE configs[3] plumbing at small size: Sampler.sample_ode('euler') + forward_with_cfg."""
+    from ln3diff_b200.transport import Sampler, create_transport
+    from ln3diff_b200.utils import build_i23d
+    from oracle import dit as odit
+    from oracle import samplers as osmp
+    m = build_i23d("DiT-PixArt-B/2")
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    g = torch.Generator().manual_seed(42)
+    z = torch.randn(1, 12, 32, 32, generator=g)
+    c = {"vector": torch.randn(1, 768, generator=g), "crossattn": torch.randn(1, 256, 2048, generator=g)}
+    ctx = {k: torch.cat([v, torch.zeros_like(v)]) for k, v in c.items()}            # cond first, uc = 0
+    steps = 5
+    ref = osmp.flow_ode_cfg_sample(lambda xx, tt, cc: odit.dit_i23d_pixart_forward(sd, "DiT-PixArt-B/2", xx, tt, cc),
+                                   z, ctx, 4.0, steps)
+    m = m.to(dev)
+    fn = Sampler(create_transport(snr_type="lognorm")).sample_ode(sampling_method="euler", num_steps=steps)
+    traj = fn(torch.cat([z, z]).to(dev), m.forward_with_cfg, context={k: v.to(dev) for k, v in ctx.items()}, cfg_scale=4.0)
+    assert traj.shape == (steps, 2, 12, 32, 32)
+    assert _rel(traj[-1].chunk(2)[0], ref) < 2e-2

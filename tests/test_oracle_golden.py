@@ -103,3 +103,18 @@ def test_vae_decoder_matches_reference(golden):
     assert _rel(y[:, :, 40:56, 40:56], g["crop"]) < 1e-5
     assert _rel(y.mean(dim=(0, 2, 3)), g["chan_mean"]) < 1e-4
     assert _rel(y.abs().mean(dim=(0, 2, 3)), g["chan_absmean"]) < 1e-5
+
+
+def test_dit_i23d_forward_matches_reference(golden):
+    from ln3diff_b200.utils import build_i23d
+    g = golden("dit_i23d.npz")
+    m = build_i23d(fx.I23D_ARCH)
+    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    sd = fx.i23d_state_dict(shapes, m.state_dict()["pos_embed"])
+    x, t, ctx = fx.i23d_inputs()
+    with torch.no_grad():
+        y = odit.dit_i23d_pixart_forward(sd, fx.I23D_ARCH, x, t, ctx)
+    assert _rel(y, g["out"]) < 2e-6
+    c, u = y.chunk(2)
+    half = u + 4.0 * (c - u)
+    assert _rel(torch.cat([half, half]), g["out_cfg"]) < 2e-6
