@@ -10,6 +10,8 @@
 //   warp 1        : TMEM allocator; lane 0 issues tcgen05.mma (UMMA 128 x BN x 16, fp32 in TMEM)
 //   warps 2..5    : epilogue: tcgen05.ld -> registers -> bias/act/gate/residual -> global
 // Two TMEM accumulator stages let the epilogue of tile i overlap the main loop of tile i+1.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "ln3_internal.h"
 
@@ -43,10 +45,161 @@ struct GemmParams {
   const float* gate;       // RESID: gate[(m / gate_rows) * gate_ld + n]; null -> 1
   int gate_rows;
   long long gate_ld;
+  int epi_mode;            // bit0: stage bf16/f32 outputs through smem, bit1: stage residual updates
   const float* hn_w;       // per-head RMSNorm weights [nsec][64] (HN kernels only)
   int hn_nsec, hn_sec_cols;
   float hn_eps;
 };
+
+// One accumulator tile (this warp's 32 TMEM lanes x BN columns) -> global memory.
+// Phase 1 (lane = row): tcgen05.ld, + bias, activation (or per-head RMSNorm), transpose through a
+// private 32x32 smem tile.  Phase 2 (lane = column): every global access of the warp is one contiguous
+// row segment (128 B fp32 / 64 B bf16) -> 1 L1 wavefront per instruction instead of 32.
+template <int BN, bool HN>
+__device__ __forceinline__ void epilogue_tile(const GemmParams& p, float* stage, uint32_t t_row,
+                                              int m_base, int tn, int lane) {
+constexpr int CW = HN ? 64 : 32;  // columns per pass
+#pragma unroll 1
+for (int c = 0; c < BN; c += CW) {
+  const int n0 = tn * BN + c;
+  float f[CW];
+  {
+    uint32_t v[CW];
+    tmem_ld_32x32(t_row + c, v);
+    if constexpr (HN) tmem_ld_32x32(t_row + c + 32, v + 32);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < CW; ++i) f[i] = __uint_as_float(v[i]);
+  }
+  if (p.bias != nullptr) {
+#pragma unroll
+    for (int i = 0; i < CW; i += 4) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + i));
+      f[i] += b.x; f[i + 1] += b.y; f[i + 2] += b.z; f[i + 3] += b.w;
+    }
+  }
+  if constexpr (HN) {
+    const int sec = n0 / p.hn_sec_cols;
+    if (sec < p.hn_nsec) {
+      float ss = 0.f;
+#pragma unroll
+      for (int i = 0; i < 64; ++i) ss = fmaf(f[i], f[i], ss);
+      const float r = rsqrtf(ss * (1.0f / 64.0f) + p.hn_eps);
+      const float* w = p.hn_w + sec * 64;
+#pragma unroll
+      for (int i = 0; i < 64; i += 4) {
+        const float4 ww = __ldg(reinterpret_cast<const float4*>(w + i));
+        f[i] *= r * ww.x; f[i + 1] *= r * ww.y; f[i + 2] *= r * ww.z; f[i + 3] *= r * ww.w;
+      }
+    }
+  } else {
+    if (p.act == LN3_ACT_GELU_ERF) {
+#pragma unroll
+      for (int i = 0; i < CW; ++i) f[i] = gelu_erf_fast(f[i]);
+    } else if (p.act == LN3_ACT_GELU_TANH) {
+#pragma unroll
+      for (int i = 0; i < CW; ++i) f[i] = gelu_tanh(f[i]);
+    } else if (p.act == LN3_ACT_SILU) {
+#pragma unroll
+      for (int i = 0; i < CW; ++i) f[i] = silu(f[i]);
+    }
+  }
+  const bool staged = (p.out_kind == LN3_OUT_RESID_F32) ? (p.epi_mode & 2) != 0 : (p.epi_mode & 1) != 0;
+  if (!staged) {
+    // direct: thread = row, 16-byte vector accesses (each lane touches its own cache line)
+    const int m = m_base + lane;
+    if (m < p.M) {
+#pragma unroll
+      for (int h = 0; h < CW; h += 32) {
+        const int nn = n0 + h;
+        if (p.out_kind == LN3_OUT_BF16) {
+          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + m * p.ldo + nn;
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            uint4 q;
+            q.x = pack_bf16x2(f[h + i], f[h + i + 1]);
+            q.y = pack_bf16x2(f[h + i + 2], f[h + i + 3]);
+            q.z = pack_bf16x2(f[h + i + 4], f[h + i + 5]);
+            q.w = pack_bf16x2(f[h + i + 6], f[h + i + 7]);
+            *reinterpret_cast<uint4*>(o + i) = q;
+          }
+        } else if (p.out_kind == LN3_OUT_F32) {
+          float* o = reinterpret_cast<float*>(p.out) + m * p.ldo + nn;
+#pragma unroll
+          for (int i = 0; i < 32; i += 4)
+            *reinterpret_cast<float4*>(o + i) = make_float4(f[h + i], f[h + i + 1], f[h + i + 2], f[h + i + 3]);
+        } else {
+          float* o = reinterpret_cast<float*>(p.out) + m * p.ldo + nn;
+          const float* gate_row = p.gate ? p.gate + static_cast<long long>(m / p.gate_rows) * p.gate_ld + nn : nullptr;
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            float4 x = *reinterpret_cast<const float4*>(o + i);
+            float4 g = make_float4(1.f, 1.f, 1.f, 1.f);
+            if (gate_row != nullptr) g = __ldg(reinterpret_cast<const float4*>(gate_row + i));
+            x.x = fmaf(g.x, f[h + i], x.x);
+            x.y = fmaf(g.y, f[h + i + 1], x.y);
+            x.z = fmaf(g.z, f[h + i + 2], x.z);
+            x.w = fmaf(g.w, f[h + i + 3], x.w);
+            *reinterpret_cast<float4*>(o + i) = x;
+            f[h + i] = x.x; f[h + i + 1] = x.y; f[h + i + 2] = x.z; f[h + i + 3] = x.w;
+          }
+          if (p.out2 != nullptr) {
+            __nv_bfloat16* o2 = p.out2 + m * p.ldo2 + nn;
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+              uint4 q;
+              q.x = pack_bf16x2(f[h + i], f[h + i + 1]);
+              q.y = pack_bf16x2(f[h + i + 2], f[h + i + 3]);
+              q.z = pack_bf16x2(f[h + i + 4], f[h + i + 5]);
+              q.w = pack_bf16x2(f[h + i + 6], f[h + i + 7]);
+              *reinterpret_cast<uint4*>(o2 + i) = q;
+            }
+          }
+        }
+      }
+    }
+    continue;
+  }
+#pragma unroll
+  for (int h = 0; h < CW; h += 32) {
+    // transpose 32x32 through smem (row stride 36 floats: conflict-free STS.128 / LDS.32)
+#pragma unroll
+    for (int i = 0; i < 32; i += 4)
+      *reinterpret_cast<float4*>(stage + lane * kStageLd + i) =
+          make_float4(f[h + i], f[h + i + 1], f[h + i + 2], f[h + i + 3]);
+    __syncwarp();
+    const int col = n0 + h + lane;
+    if (p.out_kind == LN3_OUT_BF16) {
+      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + col;
+#pragma unroll 8
+      for (int rr = 0; rr < 32; ++rr) {
+        const int m = m_base + rr;
+        if (m < p.M) o[m * p.ldo] = __float2bfloat16(stage[rr * kStageLd + lane]);
+      }
+    } else if (p.out_kind == LN3_OUT_F32) {
+      float* o = reinterpret_cast<float*>(p.out) + col;
+#pragma unroll 8
+      for (int rr = 0; rr < 32; ++rr) {
+        const int m = m_base + rr;
+        if (m < p.M) o[m * p.ldo] = stage[rr * kStageLd + lane];
+      }
+    } else {  // LN3_OUT_RESID_F32: x[m,n] += gate * val  (+ bf16 copy of the new x)
+      float* o = reinterpret_cast<float*>(p.out) + col;
+#pragma unroll 4
+      for (int rr = 0; rr < 32; ++rr) {
+        const int m = m_base + rr;
+        if (m < p.M) {
+          const float g = p.gate ? __ldg(p.gate + static_cast<long long>(m / p.gate_rows) * p.gate_ld + col) : 1.f;
+          const float xn = fmaf(g, stage[rr * kStageLd + lane], o[m * p.ldo]);
+          o[m * p.ldo] = xn;
+          if (p.out2 != nullptr) p.out2[m * p.ldo2 + col] = __float2bfloat16(xn);
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+}
 
 template <int BN, bool HN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
@@ -175,91 +328,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
       tc_fence_after();
       const int m_base = tm * BM + quarter * 32;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
-      constexpr int CW = HN ? 64 : 32;  // columns per pass
-#pragma unroll 1
-      for (int c = 0; c < BN; c += CW) {
-        const int n0 = tn * BN + c;
-        float f[CW];
-        {
-          uint32_t v[CW];
-          tmem_ld_32x32(t_row + c, v);
-          if constexpr (HN) tmem_ld_32x32(t_row + c + 32, v + 32);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < CW; ++i) f[i] = __uint_as_float(v[i]);
-        }
-        if (p.bias != nullptr) {
-#pragma unroll
-          for (int i = 0; i < CW; i += 4) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + i));
-            f[i] += b.x; f[i + 1] += b.y; f[i + 2] += b.z; f[i + 3] += b.w;
-          }
-        }
-        if constexpr (HN) {
-          const int sec = n0 / p.hn_sec_cols;
-          if (sec < p.hn_nsec) {
-            float ss = 0.f;
-#pragma unroll
-            for (int i = 0; i < 64; ++i) ss = fmaf(f[i], f[i], ss);
-            const float r = rsqrtf(ss * (1.0f / 64.0f) + p.hn_eps);
-            const float* w = p.hn_w + sec * 64;
-#pragma unroll
-            for (int i = 0; i < 64; i += 4) {
-              const float4 ww = __ldg(reinterpret_cast<const float4*>(w + i));
-              f[i] *= r * ww.x; f[i + 1] *= r * ww.y; f[i + 2] *= r * ww.z; f[i + 3] *= r * ww.w;
-            }
-          }
-        } else {
-          if (p.act == LN3_ACT_GELU_ERF) {
-#pragma unroll
-            for (int i = 0; i < CW; ++i) f[i] = gelu_erf_fast(f[i]);
-          } else if (p.act == LN3_ACT_GELU_TANH) {
-#pragma unroll
-            for (int i = 0; i < CW; ++i) f[i] = gelu_tanh(f[i]);
-          } else if (p.act == LN3_ACT_SILU) {
-#pragma unroll
-            for (int i = 0; i < CW; ++i) f[i] = silu(f[i]);
-          }
-        }
-#pragma unroll
-        for (int h = 0; h < CW; h += 32) {
-          // transpose 32x32 through smem (row stride 36 floats: conflict-free STS.128 / LDS.32)
-#pragma unroll
-          for (int i = 0; i < 32; i += 4)
-            *reinterpret_cast<float4*>(stage + lane * kStageLd + i) =
-                make_float4(f[h + i], f[h + i + 1], f[h + i + 2], f[h + i + 3]);
-          __syncwarp();
-          const int col = n0 + h + lane;
-          if (p.out_kind == LN3_OUT_BF16) {
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + col;
-#pragma unroll 8
-            for (int rr = 0; rr < 32; ++rr) {
-              const int m = m_base + rr;
-              if (m < p.M) o[m * p.ldo] = __float2bfloat16(stage[rr * kStageLd + lane]);
-            }
-          } else if (p.out_kind == LN3_OUT_F32) {
-            float* o = reinterpret_cast<float*>(p.out) + col;
-#pragma unroll 8
-            for (int rr = 0; rr < 32; ++rr) {
-              const int m = m_base + rr;
-              if (m < p.M) o[m * p.ldo] = stage[rr * kStageLd + lane];
-            }
-          } else {  // LN3_OUT_RESID_F32: x[m,n] += gate * val  (+ bf16 copy of the new x)
-            float* o = reinterpret_cast<float*>(p.out) + col;
-#pragma unroll 4
-            for (int rr = 0; rr < 32; ++rr) {
-              const int m = m_base + rr;
-              if (m < p.M) {
-                const float g = p.gate ? __ldg(p.gate + static_cast<long long>(m / p.gate_rows) * p.gate_ld + col) : 1.f;
-                const float xn = fmaf(g, stage[rr * kStageLd + lane], o[m * p.ldo]);
-                o[m * p.ldo] = xn;
-                if (p.out2 != nullptr) p.out2[m * p.ldo2 + col] = __float2bfloat16(xn);
-              }
-            }
-          }
-          __syncwarp();
-        }
-      }
+      epilogue_tile<BN, HN>(p, stage, t_row, m_base, tn, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
@@ -299,6 +368,183 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
   return LN3_OK;
 }
 
+
+// ---------------------------------------------------------------------------------- CTA-pair GEMM
+// cta_group::2 variant: a cluster of two CTAs (one TPC) computes a 256 x 256 tile.  Each CTA loads its
+// own 128 rows of A and HALF of the W tile (128 of the 256 output columns) per k-block -- 32 KB instead
+// of 48 KB -- so the L2 -> SM operand traffic that bounds the 1-CTA kernel (148 x 96 B/clk > the ~6.3
+// KB/clk L2 can deliver) drops by a third; the tensor cores of both SMs read both W halves.
+//   both CTAs  : TMA producer (own A rows + own W half, bytes credited to the LEADER's full barrier),
+//                TMEM allocation (cta_group::2), 4 epilogue warps on their own 128 accumulator rows
+//   leader CTA : single-thread tcgen05.mma.cta_group::2 issuer (UMMA 256 x 256 x 16); its commits are
+//                multicast to the empty / tmem_full barriers of both CTAs
+//   tmem_empty : epilogue warps of both CTAs arrive on the leader's barrier (remote mbarrier arrive)
+static constexpr int kStages2 = 6;
+static constexpr int kStageBytes2 = (BM * BK + 128 * BK) * 2;  // A 128x64 + W half 128x64 = 32 KB
+static constexpr int kSmemBytes2 = kStages2 * kStageBytes2 + 1024 + 256 + 4 * 32 * kStageLd * 4;
+
+template <bool HN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                  const GemmParams p) {
+  constexpr int BN = 256;
+  constexpr int kABytes = BM * BK * 2, kBBytes = 128 * BK * 2;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kStages2 * kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages2 * kStageBytes2);
+  uint64_t* full_bar = bars;                  // [kStages2]  (the leader's copy is the live one)
+  uint64_t* empty_bar = bars + kStages2;      // [kStages2]  one per CTA, fed by multicast commits
+  uint64_t* tmem_full = bars + 2 * kStages2;  // [2]         one per CTA, fed by multicast commits
+  uint64_t* tmem_empty = tmem_full + 2;       // [2]         leader's copy: 8 arrivals (4 warps x 2 CTAs)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* stage_base = reinterpret_cast<float*>(smem + kStages2 * kStageBytes2 + 256);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+
+  const int tiles_m = (p.M + 2 * BM - 1) / (2 * BM);
+  const int tiles_n = p.N / BN;
+  const int num_tiles = tiles_m * tiles_n;
+  const int num_kb = p.K / BK;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int i = 0; i < kStages2; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 8);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_2sm(tmem_slot, 2 * BN);
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before();
+  cluster_sync_all();  // barriers of both CTAs initialised before any remote signal
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto tile_coords = [&](int t, int& tm, int& tn) {
+    tm = t % tiles_m;
+    tn = t / tiles_m;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = pair; t < num_tiles; t += num_pairs) {
+        int tm, tn;
+        tile_coords(t, tm, tn);
+        const int row_a = tm * 2 * BM + static_cast<int>(rank) * BM;
+        const int row_b = tn * BN + static_cast<int>(rank) * 128;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          const uint32_t full_leader = mapa_u32(&full_bar[stage], 0);
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * kStageBytes2);  // bytes of both CTAs
+          tma_load_2d_2sm(smem_a + stage * kABytes, &tmap_a, full_leader, kb * BK, row_a);
+          tma_load_2d_2sm(smem_b + stage * kBBytes, &tmap_b, full_leader, kb * BK, row_b);
+          if (++stage == kStages2) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int t = pair; t < num_tiles; t += num_pairs) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem_a + stage * kABytes);
+          const uint32_t b_addr = smem_u32(smem_b + stage * kBBytes);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma_f16_ss_2sm(d_tmem, make_smem_desc_sw128(a_addr + k * 32, 0, 1024),
+                            make_smem_desc_sw128(b_addr + k * 32, 0, 1024), idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit_2sm(&empty_bar[stage], 0b11);  // frees this stage in both CTAs
+          if (++stage == kStages2) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit_2sm(&tmem_full[acc], 0b11);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    float* stage_buf = stage_base + (warp - 2) * (32 * kStageLd);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = pair; t < num_tiles; t += num_pairs) {
+      int tm, tn;
+      tile_coords(t, tm, tn);
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const int m_base = tm * 2 * BM + static_cast<int>(rank) * BM + quarter * 32;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
+      epilogue_tile<BN, HN>(p, stage_buf, t_row, m_base, tn, lane);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(&tmem_empty[acc], 0));
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // no CTA exits (or frees TMEM) while its peer can still signal it
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc_2sm(tmem_base, 2 * BN);
+}
+
+template <bool HN>
+static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int num_sms,
+                        cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm2_bf16_kernel<HN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         kSmemBytes2);
+    if (e != cudaSuccess)
+      return set_error(LN3_ECUDA, "gemm2: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int tiles = ((p.M + 2 * BM - 1) / (2 * BM)) * (p.N / 256);
+  int pairs = num_sms / 2;
+  if (tiles < pairs) pairs = tiles;
+  gemm2_bf16_kernel<HN><<<2 * pairs, kGemmThreads, kSmemBytes2, stream>>>(ta, tb, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(LN3_ECUDA, "gemm2 launch: %s", cudaGetErrorString(e));
+  count_launch();
+  return LN3_OK;
+}
+
 int gemm_bf16(const ln3_gemm_args* a, cudaStream_t stream) {
   if (a->M <= 0 || a->N <= 0 || a->K <= 0) return set_error(LN3_EINVAL, "gemm: empty problem");
   if (a->K % BK != 0) return set_error(LN3_EINVAL, "gemm: K=%d must be a multiple of %d", a->K, BK);
@@ -311,11 +557,13 @@ int gemm_bf16(const ln3_gemm_args* a, cudaStream_t stream) {
   if (a->out_kind == LN3_OUT_RESID_F32 && a->gate != nullptr && a->gate_rows <= 0)
     return set_error(LN3_EINVAL, "gemm: gate_rows must be > 0");
   const int bn = (a->N % 256 == 0) ? 256 : 128;
+  static const bool force_1cta = getenv("LN3_GEMM_1CTA") != nullptr;
+  const bool use_pair = !force_1cta && bn == 256 && a->M >= 256;
 
   CUtensorMap ta, tb;
   int rc = make_tmap_2d_bf16(&ta, a->A, a->M, a->K, a->lda, BM, BK);
   if (rc) return rc;
-  rc = make_tmap_2d_bf16(&tb, a->W, a->N, a->K, a->ldw, bn, BK);
+  rc = make_tmap_2d_bf16(&tb, a->W, a->N, a->K, a->ldw, use_pair ? 128 : bn, BK);
   if (rc) return rc;
 
   GemmParams p;
@@ -332,11 +580,23 @@ int gemm_bf16(const ln3_gemm_args* a, cudaStream_t stream) {
   p.gate = a->gate;
   p.gate_rows = a->gate_rows > 0 ? a->gate_rows : 1;
   p.gate_ld = a->gate_ld;
+  static const int epi_mode = getenv("LN3_GEMM_EPI") ? atoi(getenv("LN3_GEMM_EPI")) : 2;
+  p.epi_mode = epi_mode;
   p.hn_w = a->head_norm_w;
   p.hn_nsec = a->head_norm_nsec;
   p.hn_sec_cols = a->head_norm_sec_cols;
   p.hn_eps = a->head_norm_eps;
   const int sms = device_sm_count();
+  if (use_pair) {
+    if (a->head_norm_w != nullptr) {
+      if (a->out_kind != LN3_OUT_BF16 || a->act != LN3_ACT_NONE)
+        return set_error(LN3_EINVAL, "gemm: head_norm needs LN3_OUT_BF16 and no activation");
+      if (a->head_norm_nsec <= 0 || a->head_norm_sec_cols <= 0 || a->head_norm_sec_cols % 64 != 0)
+        return set_error(LN3_EINVAL, "gemm: head_norm sections must be positive multiples of 64 columns");
+      return launch_gemm2<true>(ta, tb, p, sms, stream);
+    }
+    return launch_gemm2<false>(ta, tb, p, sms, stream);
+  }
   if (a->head_norm_w != nullptr) {
     if (a->out_kind != LN3_OUT_BF16 || a->act != LN3_ACT_NONE)
       return set_error(LN3_EINVAL, "gemm: head_norm needs LN3_OUT_BF16 and no activation");

@@ -67,18 +67,24 @@ def run_case(M, N, K, act=ops.ACT_NONE, out_kind=ops.OUT_BF16, bias=True, gate=F
     return case
 
 
-def bench(M, N, K, iters=20):
+def bench(M, N, K, iters=20, resid=False, act=ops.ACT_NONE):
     a = (torch.randn(M, K, device=dev) * 0.5).bfloat16()
     w = (torch.randn(N, K, device=dev) * 0.05).bfloat16()
     b = torch.randn(N, device=dev)
-    out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    if resid:
+        out = torch.zeros(M, N, device=dev, dtype=torch.float32)
+        kw = dict(out_kind=ops.OUT_RESID_F32, out=out, gate=torch.randn(M // 768 + 1, N, device=dev), gate_rows=768,
+                  out2=torch.empty(M, N, device=dev, dtype=torch.bfloat16))
+    else:
+        out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+        kw = dict(out=out, act=act)
     for _ in range(3):
-        ops.gemm(a, w, b, out=out)
+        ops.gemm(a, w, b, **kw)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
     e0.record()
     for _ in range(iters):
-        ops.gemm(a, w, b, out=out)
+        ops.gemm(a, w, b, **kw)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
@@ -93,7 +99,7 @@ def bench(M, N, K, iters=20):
     e1.record()
     torch.cuda.synchronize()
     ms2 = e0.elapsed_time(e1) / iters
-    r = {"M": M, "N": N, "K": K, "ms": ms, "tflops": tf, "cublas_ms": ms2,
+    r = {"M": M, "N": N, "K": K, "resid": resid, "act": act, "ms": ms, "tflops": tf, "cublas_ms": ms2,
          "cublas_tflops": 2.0 * M * N * K / ms2 / 1e9}
     print(r, flush=True)
     return r
@@ -112,7 +118,8 @@ try:
     run_case(1536, 1024, 1024, out_kind=ops.OUT_RESID_F32, gate=False)
     run_case(300, 1024, 256, act=ops.ACT_SILU)
     run_case(12288, 3072, 1024)
-    res["bench"] = [bench(12288, 3072, 1024), bench(12288, 4096, 1024), bench(12288, 1024, 4096),
+    res["bench"] = [bench(12288, 3072, 1024), bench(12288, 4096, 1024, act=ops.ACT_GELU_ERF),
+                    bench(12288, 1024, 4096, resid=True), bench(12288, 1024, 1024, resid=True),
                     bench(12288, 1024, 1024)]
     res["ok"] = all(c["rel_l2"] < 1e-2 for c in res["cases"])
 except Exception as e:  # noqa
