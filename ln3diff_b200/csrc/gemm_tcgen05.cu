@@ -580,7 +580,7 @@ int gemm_bf16(const ln3_gemm_args* a, cudaStream_t stream) {
   p.gate = a->gate;
   p.gate_rows = a->gate_rows > 0 ? a->gate_rows : 1;
   p.gate_ld = a->gate_ld;
-  static const int epi_mode = getenv("LN3_GEMM_EPI") ? atoi(getenv("LN3_GEMM_EPI")) : 2;
+  static const int epi_mode = getenv("LN3_GEMM_EPI") ? atoi(getenv("LN3_GEMM_EPI")) : 0;
   p.epi_mode = epi_mode;
   p.hn_w = a->head_norm_w;
   p.hn_nsec = a->head_norm_nsec;

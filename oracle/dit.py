@@ -33,7 +33,7 @@ DIT_SIZES = {  # dit/dit_models_xformers.py:1029-1106 ; dit/dit_trilatent.py:270
 def timestep_embedding(t: torch.Tensor, dim: int = 256, max_period: float = 10000.0) -> torch.Tensor:
     """dit_models_xformers.py:97-121: [cos(t f), sin(t f)], f_i = exp(-ln(1e4) i / half)."""
     half = dim // 2
-    freqs = torch.exp(-math.log(max_period) * torch.arange(half, dtype=torch.float32) / half)
+    freqs = torch.exp(-math.log(max_period) * torch.arange(half, dtype=torch.float32) / half).to(t.device)
     args = t[:, None].float() * freqs[None]
     return torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
 
