@@ -369,6 +369,118 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
 }
 
 
+
+// Compile-time specialised, software-pipelined epilogue of the CTA-pair kernel: this warp's 32 TMEM
+// lanes x columns [c_begin, c_end) of one accumulator tile.  The tcgen05.ld of chunk c+1 is in flight
+// while chunk c is converted and stored; activation / output kind are template parameters (the
+// runtime switch compiled to an indirect branch + constant loads that stalled the warp ~15 %).
+template <int ACT, int OUT, bool HN>
+__device__ __forceinline__ void epilogue_cols(const GemmParams& p, uint32_t t_row, int m, int n_tile0,
+                                              int c_begin, int c_end) {
+  constexpr int CW = HN ? 64 : 32;
+  const bool row_ok = m < p.M;
+  uint32_t v[CW], vn[CW];
+  tmem_ld_32x32(t_row + c_begin, v);
+  if constexpr (HN) tmem_ld_32x32(t_row + c_begin + 32, v + 32);
+  tmem_ld_wait();
+#pragma unroll 1
+  for (int c = c_begin; c < c_end; c += CW) {
+    const bool more = c + CW < c_end;
+    if (more) {
+      tmem_ld_32x32(t_row + c + CW, vn);
+      if constexpr (HN) tmem_ld_32x32(t_row + c + CW + 32, vn + 32);
+    }
+    const int n0 = n_tile0 + c;
+    float f[CW];
+#pragma unroll
+    for (int i = 0; i < CW; ++i) f[i] = __uint_as_float(v[i]);
+    if (p.bias != nullptr) {
+#pragma unroll
+      for (int i = 0; i < CW; i += 4) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + i));
+        f[i] += b.x; f[i + 1] += b.y; f[i + 2] += b.z; f[i + 3] += b.w;
+      }
+    }
+    if constexpr (HN) {
+      const int sec = n0 / p.hn_sec_cols;
+      if (sec < p.hn_nsec) {
+        float ss = 0.f;
+#pragma unroll
+        for (int i = 0; i < 64; ++i) ss = fmaf(f[i], f[i], ss);
+        const float r = rsqrtf(ss * (1.0f / 64.0f) + p.hn_eps);
+        const float* w = p.hn_w + sec * 64;
+#pragma unroll
+        for (int i = 0; i < 64; i += 4) {
+          const float4 ww = __ldg(reinterpret_cast<const float4*>(w + i));
+          f[i] *= r * ww.x; f[i + 1] *= r * ww.y; f[i + 2] *= r * ww.z; f[i + 3] *= r * ww.w;
+        }
+      }
+    }
+    if constexpr (ACT == LN3_ACT_GELU_ERF) {
+#pragma unroll
+      for (int i = 0; i < CW; ++i) f[i] = gelu_erf_fast(f[i]);
+    } else if constexpr (ACT == LN3_ACT_GELU_TANH) {
+#pragma unroll
+      for (int i = 0; i < CW; ++i) f[i] = gelu_tanh(f[i]);
+    } else if constexpr (ACT == LN3_ACT_SILU) {
+#pragma unroll
+      for (int i = 0; i < CW; ++i) f[i] = silu(f[i]);
+    }
+    if (row_ok) {
+      if constexpr (OUT == LN3_OUT_BF16) {
+        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + m * p.ldo + n0;
+#pragma unroll
+        for (int i = 0; i < CW; i += 8) {
+          uint4 q;
+          q.x = pack_bf16x2(f[i], f[i + 1]);
+          q.y = pack_bf16x2(f[i + 2], f[i + 3]);
+          q.z = pack_bf16x2(f[i + 4], f[i + 5]);
+          q.w = pack_bf16x2(f[i + 6], f[i + 7]);
+          *reinterpret_cast<uint4*>(o + i) = q;
+        }
+      } else if constexpr (OUT == LN3_OUT_F32) {
+        float* o = reinterpret_cast<float*>(p.out) + m * p.ldo + n0;
+#pragma unroll
+        for (int i = 0; i < CW; i += 4)
+          *reinterpret_cast<float4*>(o + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+      } else {  // LN3_OUT_RESID_F32
+        float* o = reinterpret_cast<float*>(p.out) + m * p.ldo + n0;
+        const float* gate_row = p.gate ? p.gate + static_cast<long long>(m / p.gate_rows) * p.gate_ld + n0 : nullptr;
+        float4 x[CW / 4];
+#pragma unroll
+        for (int i = 0; i < CW / 4; ++i) x[i] = *reinterpret_cast<const float4*>(o + 4 * i);
+#pragma unroll
+        for (int i = 0; i < CW / 4; ++i) {
+          float4 g = make_float4(1.f, 1.f, 1.f, 1.f);
+          if (gate_row != nullptr) g = __ldg(reinterpret_cast<const float4*>(gate_row + 4 * i));
+          x[i].x = fmaf(g.x, f[4 * i], x[i].x);
+          x[i].y = fmaf(g.y, f[4 * i + 1], x[i].y);
+          x[i].z = fmaf(g.z, f[4 * i + 2], x[i].z);
+          x[i].w = fmaf(g.w, f[4 * i + 3], x[i].w);
+          *reinterpret_cast<float4*>(o + 4 * i) = x[i];
+        }
+        if (p.out2 != nullptr) {
+          __nv_bfloat16* o2 = p.out2 + m * p.ldo2 + n0;
+#pragma unroll
+          for (int i = 0; i < CW / 4; i += 2) {
+            uint4 q;
+            q.x = pack_bf16x2(x[i].x, x[i].y);
+            q.y = pack_bf16x2(x[i].z, x[i].w);
+            q.z = pack_bf16x2(x[i + 1].x, x[i + 1].y);
+            q.w = pack_bf16x2(x[i + 1].z, x[i + 1].w);
+            *reinterpret_cast<uint4*>(o2 + 4 * i) = q;
+          }
+        }
+      }
+    }
+    if (more) {
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < CW; ++i) v[i] = vn[i];
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------- CTA-pair GEMM
 // cta_group::2 variant: a cluster of two CTAs (one TPC) computes a 256 x 256 tile.  Each CTA loads its
 // own 128 rows of A and HALF of the W tile (128 of the 256 output columns) per k-block -- 32 KB instead
@@ -381,10 +493,11 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
 //   tmem_empty : epilogue warps of both CTAs arrive on the leader's barrier (remote mbarrier arrive)
 static constexpr int kStages2 = 6;
 static constexpr int kStageBytes2 = (BM * BK + 128 * BK) * 2;  // A 128x64 + W half 128x64 = 32 KB
-static constexpr int kSmemBytes2 = kStages2 * kStageBytes2 + 1024 + 256 + 4 * 32 * kStageLd * 4;
+static constexpr int kSmemBytes2 = kStages2 * kStageBytes2 + 1024 + 256;
+static constexpr int kGemmThreads2 = 320;  // TMA warp, MMA warp, 8 epilogue warps (2 per TMEM lane quarter)
 
-template <bool HN>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+template <int ACT, int OUT, bool HN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads2, 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const GemmParams p) {
   constexpr int BN = 256;
@@ -398,9 +511,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   uint64_t* full_bar = bars;                  // [kStages2]  (the leader's copy is the live one)
   uint64_t* empty_bar = bars + kStages2;      // [kStages2]  one per CTA, fed by multicast commits
   uint64_t* tmem_full = bars + 2 * kStages2;  // [2]         one per CTA, fed by multicast commits
-  uint64_t* tmem_empty = tmem_full + 2;       // [2]         leader's copy: 8 arrivals (4 warps x 2 CTAs)
+  uint64_t* tmem_empty = tmem_full + 2;       // [2]         leader's copy: 16 arrivals (8 warps x 2 CTAs)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  float* stage_base = reinterpret_cast<float*>(smem + kStages2 * kStageBytes2 + 256);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -422,7 +534,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 8);
+      mbar_init(&tmem_empty[i], 16);
     }
     fence_barrier_init();
   }
@@ -497,7 +609,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     }
   } else {
     const int quarter = warp & 3;
-    float* stage_buf = stage_base + (warp - 2) * (32 * kStageLd);
+    const int half = (warp - 2) >> 2;  // which half of the tile's columns
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = pair; t < num_tiles; t += num_pairs) {
@@ -505,9 +617,9 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       tile_coords(t, tm, tn);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const int m_base = tm * 2 * BM + static_cast<int>(rank) * BM + quarter * 32;
+      const int m = tm * 2 * BM + static_cast<int>(rank) * BM + quarter * 32 + lane;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
-      epilogue_tile<BN, HN>(p, stage_buf, t_row, m_base, tn, lane);
+      epilogue_cols<ACT, OUT, HN>(p, t_row, m, tn * BN, half * (BN / 2), (half + 1) * (BN / 2));
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_u32(&tmem_empty[acc], 0));
@@ -524,12 +636,12 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   if (warp == 1) tmem_dealloc_2sm(tmem_base, 2 * BN);
 }
 
-template <bool HN>
+template <int ACT, int OUT, bool HN>
 static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int num_sms,
                         cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm2_bf16_kernel<HN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm2_bf16_kernel<ACT, OUT, HN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          kSmemBytes2);
     if (e != cudaSuccess)
       return set_error(LN3_ECUDA, "gemm2: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
@@ -538,7 +650,7 @@ static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const Gemm
   const int tiles = ((p.M + 2 * BM - 1) / (2 * BM)) * (p.N / 256);
   int pairs = num_sms / 2;
   if (tiles < pairs) pairs = tiles;
-  gemm2_bf16_kernel<HN><<<2 * pairs, kGemmThreads, kSmemBytes2, stream>>>(ta, tb, p);
+  gemm2_bf16_kernel<ACT, OUT, HN><<<2 * pairs, kGemmThreads2, kSmemBytes2, stream>>>(ta, tb, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(LN3_ECUDA, "gemm2 launch: %s", cudaGetErrorString(e));
   count_launch();
@@ -593,9 +705,23 @@ int gemm_bf16(const ln3_gemm_args* a, cudaStream_t stream) {
         return set_error(LN3_EINVAL, "gemm: head_norm needs LN3_OUT_BF16 and no activation");
       if (a->head_norm_nsec <= 0 || a->head_norm_sec_cols <= 0 || a->head_norm_sec_cols % 64 != 0)
         return set_error(LN3_EINVAL, "gemm: head_norm sections must be positive multiples of 64 columns");
-      return launch_gemm2<true>(ta, tb, p, sms, stream);
+      return launch_gemm2<LN3_ACT_NONE, LN3_OUT_BF16, true>(ta, tb, p, sms, stream);
     }
-    return launch_gemm2<false>(ta, tb, p, sms, stream);
+    if (a->out_kind == LN3_OUT_RESID_F32) {
+      if (a->act != LN3_ACT_NONE) return set_error(LN3_EINVAL, "gemm: residual epilogue takes no activation");
+      return launch_gemm2<LN3_ACT_NONE, LN3_OUT_RESID_F32, false>(ta, tb, p, sms, stream);
+    }
+    if (a->out_kind == LN3_OUT_F32) {
+      if (a->act != LN3_ACT_NONE) return set_error(LN3_EUNSUPPORTED, "gemm: fp32 output with activation");
+      return launch_gemm2<LN3_ACT_NONE, LN3_OUT_F32, false>(ta, tb, p, sms, stream);
+    }
+    switch (a->act) {
+      case LN3_ACT_NONE: return launch_gemm2<LN3_ACT_NONE, LN3_OUT_BF16, false>(ta, tb, p, sms, stream);
+      case LN3_ACT_GELU_ERF: return launch_gemm2<LN3_ACT_GELU_ERF, LN3_OUT_BF16, false>(ta, tb, p, sms, stream);
+      case LN3_ACT_GELU_TANH: return launch_gemm2<LN3_ACT_GELU_TANH, LN3_OUT_BF16, false>(ta, tb, p, sms, stream);
+      case LN3_ACT_SILU: return launch_gemm2<LN3_ACT_SILU, LN3_OUT_BF16, false>(ta, tb, p, sms, stream);
+      default: return set_error(LN3_EINVAL, "gemm: unknown activation %d", a->act);
+    }
   }
   if (a->head_norm_w != nullptr) {
     if (a->out_kind != LN3_OUT_BF16 || a->act != LN3_ACT_NONE)
