@@ -46,6 +46,7 @@ struct GemmParams {
   int gate_rows;
   long long gate_ld;
   int epi_mode;            // bit0: stage bf16/f32 outputs through smem, bit1: stage residual updates
+  int wide_ok;             // out / out2 rows are 32-byte aligned -> 256-bit global accesses
   const float* hn_w;       // per-head RMSNorm weights [nsec][64] (HN kernels only)
   int hn_nsec, hn_sec_cols;
   float hn_eps;
@@ -429,46 +430,60 @@ __device__ __forceinline__ void epilogue_cols(const GemmParams& p, uint32_t t_ro
     if (row_ok) {
       if constexpr (OUT == LN3_OUT_BF16) {
         __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + m * p.ldo + n0;
+        if (p.wide_ok) {
 #pragma unroll
-        for (int i = 0; i < CW; i += 8) {
-          uint4 q;
-          q.x = pack_bf16x2(f[i], f[i + 1]);
-          q.y = pack_bf16x2(f[i + 2], f[i + 3]);
-          q.z = pack_bf16x2(f[i + 4], f[i + 5]);
-          q.w = pack_bf16x2(f[i + 6], f[i + 7]);
-          *reinterpret_cast<uint4*>(o + i) = q;
+          for (int i = 0; i < CW; i += 16) {
+            uint32_t q[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) q[j] = pack_bf16x2(f[i + 2 * j], f[i + 2 * j + 1]);
+            stg256_b32(o + i, q);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < CW; i += 8) {
+            uint4 q;
+            q.x = pack_bf16x2(f[i], f[i + 1]);
+            q.y = pack_bf16x2(f[i + 2], f[i + 3]);
+            q.z = pack_bf16x2(f[i + 4], f[i + 5]);
+            q.w = pack_bf16x2(f[i + 6], f[i + 7]);
+            *reinterpret_cast<uint4*>(o + i) = q;
+          }
         }
       } else if constexpr (OUT == LN3_OUT_F32) {
         float* o = reinterpret_cast<float*>(p.out) + m * p.ldo + n0;
+        if (p.wide_ok) {
 #pragma unroll
-        for (int i = 0; i < CW; i += 4)
-          *reinterpret_cast<float4*>(o + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
-      } else {  // LN3_OUT_RESID_F32
+          for (int i = 0; i < CW; i += 8) stg256_f32(o + i, f + i);
+        } else {
+#pragma unroll
+          for (int i = 0; i < CW; i += 4)
+            *reinterpret_cast<float4*>(o + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+        }
+      } else {  // LN3_OUT_RESID_F32: x += gate * val (256-bit accesses; wide_ok checked on the host)
         float* o = reinterpret_cast<float*>(p.out) + m * p.ldo + n0;
         const float* gate_row = p.gate ? p.gate + static_cast<long long>(m / p.gate_rows) * p.gate_ld + n0 : nullptr;
-        float4 x[CW / 4];
+        float x[CW];
 #pragma unroll
-        for (int i = 0; i < CW / 4; ++i) x[i] = *reinterpret_cast<const float4*>(o + 4 * i);
+        for (int i = 0; i < CW; i += 8) ldg256_na(o + i, x + i);
 #pragma unroll
-        for (int i = 0; i < CW / 4; ++i) {
+        for (int i = 0; i < CW; i += 4) {
           float4 g = make_float4(1.f, 1.f, 1.f, 1.f);
-          if (gate_row != nullptr) g = __ldg(reinterpret_cast<const float4*>(gate_row + 4 * i));
-          x[i].x = fmaf(g.x, f[4 * i], x[i].x);
-          x[i].y = fmaf(g.y, f[4 * i + 1], x[i].y);
-          x[i].z = fmaf(g.z, f[4 * i + 2], x[i].z);
-          x[i].w = fmaf(g.w, f[4 * i + 3], x[i].w);
-          *reinterpret_cast<float4*>(o + 4 * i) = x[i];
+          if (gate_row != nullptr) g = __ldg(reinterpret_cast<const float4*>(gate_row + i));
+          x[i] = fmaf(g.x, f[i], x[i]);
+          x[i + 1] = fmaf(g.y, f[i + 1], x[i + 1]);
+          x[i + 2] = fmaf(g.z, f[i + 2], x[i + 2]);
+          x[i + 3] = fmaf(g.w, f[i + 3], x[i + 3]);
         }
+#pragma unroll
+        for (int i = 0; i < CW; i += 8) stg256_f32(o + i, x + i);
         if (p.out2 != nullptr) {
           __nv_bfloat16* o2 = p.out2 + m * p.ldo2 + n0;
 #pragma unroll
-          for (int i = 0; i < CW / 4; i += 2) {
-            uint4 q;
-            q.x = pack_bf16x2(x[i].x, x[i].y);
-            q.y = pack_bf16x2(x[i].z, x[i].w);
-            q.z = pack_bf16x2(x[i + 1].x, x[i + 1].y);
-            q.w = pack_bf16x2(x[i + 1].z, x[i + 1].w);
-            *reinterpret_cast<uint4*>(o2 + 4 * i) = q;
+          for (int i = 0; i < CW; i += 16) {
+            uint32_t q[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) q[j] = pack_bf16x2(x[i + 2 * j], x[i + 2 * j + 1]);
+            stg256_b32(o2 + i, q);
           }
         }
       }
@@ -670,7 +685,13 @@ int gemm_bf16(const ln3_gemm_args* a, cudaStream_t stream) {
     return set_error(LN3_EINVAL, "gemm: gate_rows must be > 0");
   const int bn = (a->N % 256 == 0) ? 256 : 128;
   static const bool force_1cta = getenv("LN3_GEMM_1CTA") != nullptr;
-  const bool use_pair = !force_1cta && bn == 256 && a->M >= 256;
+  bool use_pair = !force_1cta && bn == 256 && a->M >= 256;
+  if (use_pair && a->out_kind != LN3_OUT_BF16 && a->act != LN3_ACT_NONE) use_pair = false;  // rare combos: generic kernel
+  if (use_pair && a->out_kind == LN3_OUT_RESID_F32) {
+    bool ok = (reinterpret_cast<uintptr_t>(a->out) % 32 == 0) && ((a->ldo * 4) % 32 == 0);
+    if (a->out2 != nullptr) ok = ok && (reinterpret_cast<uintptr_t>(a->out2) % 32 == 0) && ((a->ldo2 * 2) % 32 == 0);
+    if (!ok) use_pair = false;
+  }
 
   CUtensorMap ta, tb;
   int rc = make_tmap_2d_bf16(&ta, a->A, a->M, a->K, a->lda, BM, BK);
@@ -694,6 +715,12 @@ int gemm_bf16(const ln3_gemm_args* a, cudaStream_t stream) {
   p.gate_ld = a->gate_ld;
   static const int epi_mode = getenv("LN3_GEMM_EPI") ? atoi(getenv("LN3_GEMM_EPI")) : 0;
   p.epi_mode = epi_mode;
+  {
+    const size_t esz = (a->out_kind == LN3_OUT_BF16) ? 2 : 4;
+    bool ok = (reinterpret_cast<uintptr_t>(a->out) % 32 == 0) && ((a->ldo * esz) % 32 == 0);
+    if (a->out2 != nullptr) ok = ok && (reinterpret_cast<uintptr_t>(a->out2) % 32 == 0) && ((a->ldo2 * 2) % 32 == 0);
+    p.wide_ok = ok ? 1 : 0;
+  }
   p.hn_w = a->head_norm_w;
   p.hn_nsec = a->head_norm_nsec;
   p.hn_sec_cols = a->head_norm_sec_cols;
