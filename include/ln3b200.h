@@ -123,8 +123,8 @@ int ln3_fmha_fwd(const ln3_fmha_args* args, void* stream);
 enum { LN3_NORM_NONE = 0, LN3_NORM_LAYER = 1, LN3_NORM_RMS = 2 };
 
 typedef struct ln3_norm_modulate_args {
-  const float* x;     /* [rows, ldx] */
-  void* out;          /* bf16 [rows, ldo] */
+  const float* x;     /* [rows, ldx]; updated in place when `resid` is given */
+  void* out;          /* bf16 [rows, ldo] (NULL allowed with `resid`) */
   const float* shift; /* [groups, mod_ld] or NULL */
   const float* scale;
   const float* shift_tab; /* [D] or NULL: PixArt scale_shift_table rows */
@@ -136,6 +136,16 @@ typedef struct ln3_norm_modulate_args {
   int norm;
   int act;            /* applied last (only with LN3_NORM_NONE) */
   float eps;
+  /* optional fused residual update executed first, in place on x:
+   *   x[r,:] += resid_gate[(r / resid_gate_rows), :] * resid[r,:]      (gate NULL -> 1)
+   * i.e. the `x = x + gate * f(...)` of the DiT blocks (dit/dit_models_xformers.py:289-294,
+   * 311-321) applied to the bf16 output of the preceding projection GEMM, so the residual stream is
+   * read and written once, coalesced, by the kernel that normalises it anyway.  out may be NULL
+   * (residual update only). */
+  const void* resid;       /* bf16 [rows, resid_ld] or NULL */
+  const float* resid_gate; /* fp32 [groups, resid_gate_ld] or NULL */
+  long long resid_ld, resid_gate_ld;
+  int resid_gate_rows;
 } ln3_norm_modulate_args;
 
 int ln3_norm_modulate(const ln3_norm_modulate_args* args, void* stream);

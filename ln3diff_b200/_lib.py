@@ -52,6 +52,8 @@ class NormModulateArgs(C.Structure):
         ("rows", C.c_int), ("D", C.c_int),
         ("ldx", C.c_longlong), ("ldo", C.c_longlong), ("mod_ld", C.c_longlong),
         ("mod_rows", C.c_int), ("norm", C.c_int), ("act", C.c_int), ("eps", C.c_float),
+        ("resid", C.c_void_p), ("resid_gate", C.c_void_p), ("resid_ld", C.c_longlong),
+        ("resid_gate_ld", C.c_longlong), ("resid_gate_rows", C.c_int),
     ]
 
 

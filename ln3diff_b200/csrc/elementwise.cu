@@ -35,6 +35,27 @@ norm_modulate_kernel(const ln3_norm_modulate_args a) {
   float4 v[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) v[i] = *reinterpret_cast<const float4*>(x + (i * 32 + lane) * 4);
+  if (a.resid != nullptr) {
+    // fused residual update: x += gate * resid (bf16), written back in place
+    const __nv_bfloat16* rr = reinterpret_cast<const __nv_bfloat16*>(a.resid) + static_cast<long long>(row) * a.resid_ld;
+    const float* gg = a.resid_gate ? a.resid_gate + static_cast<long long>(row / a.resid_gate_rows) * a.resid_gate_ld : nullptr;
+    float* xw = const_cast<float*>(x);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      const uint2 rb = *reinterpret_cast<const uint2*>(rr + c);
+      const __nv_bfloat162 r01 = *reinterpret_cast<const __nv_bfloat162*>(&rb.x);
+      const __nv_bfloat162 r23 = *reinterpret_cast<const __nv_bfloat162*>(&rb.y);
+      float4 g = make_float4(1.f, 1.f, 1.f, 1.f);
+      if (gg != nullptr) g = __ldg(reinterpret_cast<const float4*>(gg + c));
+      v[i].x = fmaf(g.x, __low2float(r01), v[i].x);
+      v[i].y = fmaf(g.y, __high2float(r01), v[i].y);
+      v[i].z = fmaf(g.z, __low2float(r23), v[i].z);
+      v[i].w = fmaf(g.w, __high2float(r23), v[i].w);
+      *reinterpret_cast<float4*>(xw + c) = v[i];
+    }
+    if (a.out == nullptr) return;
+  }
 
   float mean = 0.f, rstd = 1.f;
   if (a.norm == LN3_NORM_LAYER) {
@@ -110,6 +131,12 @@ int norm_modulate(const ln3_norm_modulate_args* a, cudaStream_t stream) {
     return set_error(LN3_EINVAL, "norm_modulate: mod_rows must be > 0");
   if (a->ldx % 4 || a->ldo % 4 || (a->shift && a->mod_ld % 4))
     return set_error(LN3_EINVAL, "norm_modulate: leading dimensions must be multiples of 4");
+  if (a->out == nullptr && a->resid == nullptr) return set_error(LN3_EINVAL, "norm_modulate: out is NULL");
+  if (a->resid != nullptr) {
+    if (a->resid_ld % 4) return set_error(LN3_EINVAL, "norm_modulate: resid_ld must be a multiple of 4");
+    if (a->resid_gate != nullptr && (a->resid_gate_rows <= 0 || a->resid_gate_ld % 4))
+      return set_error(LN3_EINVAL, "norm_modulate: bad resid_gate_rows / resid_gate_ld");
+  }
   const int warps = 8;
   dim3 grid((a->rows + warps - 1) / warps), block(warps * 32);
   switch (a->D / 128) {

@@ -191,7 +191,7 @@ class DiT_I23D_PixelArt(nn.Module):
             e = lambda *s, dt=torch.bfloat16: torch.empty(*s, device=dev, dtype=dt)
             ws = dict(tfeat=e(B, 256), th=e(B, D), t=e(B, D, dt=torch.float32), st=e(B, D),
                       t0=e(B, 6 * D, dt=torch.float32), mod=e(self.depth, B, 6 * D, dt=torch.float32),
-                      x=e(B, T, D, dt=torch.float32), xb=e(M, D), a=e(M, D), qkv=e(M, 3 * D), att=e(M, D), q=e(M, D),
+                      x=e(B, T, D, dt=torch.float32), xb=e(M, D), a=e(M, D), v=e(M, D), qkv=e(M, 3 * D), att=e(M, D), q=e(M, D),
                       h=e(M, int(self.mlp_ratio) * D))
             self._ws[B] = ws
         return ws
@@ -222,23 +222,28 @@ class DiT_I23D_PixelArt(nn.Module):
         xs = ops.patch_embed(x.float().contiguous(), P["pe_w"], P["pe_b"], P["pos"], out=ws["x"])
         x2 = xs.view(M, D)
         qkv3, att3, q3 = ws["qkv"].view(B, T, 3 * D), ws["att"].view(B, T, D), ws["q"].view(B, T, D)
+        val, pend_gate = ws["v"], None   # deferred residuals (see dit_trilatent._forward_impl)
         for l, W in enumerate(P["blocks"]):
             mod = ws["mod"][l]
             sl = lambda j: mod[:, j * D:(j + 1) * D]
-            ops.norm_modulate(x2, norm=NORM_RMS, weight=W["n1_w"], eps=1e-5, shift=sl(0), scale=sl(1), mod_rows=T, out=ws["a"])
+            ops.norm_modulate(x2, norm=NORM_RMS, weight=W["n1_w"], eps=1e-5, shift=sl(0), scale=sl(1), mod_rows=T, out=ws["a"],
+                              resid=val if l > 0 else None, resid_gate=pend_gate, resid_gate_rows=T)
             ops.gemm(ws["a"], W["qkv_w"], W["qkv_b"], out=ws["qkv"], head_norm=W["qk_norm"], head_norm_sec_cols=D)
             dkv = cx["dkv"][l]
             ops.fmha(qkv3[:, :, :D], qkv3[:, :, D:2 * D], qkv3[:, :, 2 * D:], H, out=att3,
                      k2=dkv[:, :, :D], v2=dkv[:, :, D:])
-            ops.gemm(ws["att"], W["proj_w"], W["proj_b"], out_kind=ops.OUT_RESID_F32, out=x2, gate=sl(2), gate_rows=T,
-                     out2=ws["xb"])
+            ops.gemm(ws["att"], W["proj_w"], W["proj_b"], out=val)
+            ops.norm_modulate(x2, norm=NORM_NONE, out=ws["xb"], resid=val, resid_gate=sl(2), resid_gate_rows=T)
             ops.gemm(ws["xb"], W["cq_w"], out=ws["q"], head_norm=W["cq_norm"], head_norm_sec_cols=D)
             ckv = cx["ckv"][l]
             ops.fmha(q3, ckv[:, :, :D], ckv[:, :, D:], H, out=att3)
-            ops.gemm(ws["att"], W["co_w"], W["co_b"], out_kind=ops.OUT_RESID_F32, out=x2)
-            ops.norm_modulate(x2, norm=NORM_RMS, weight=W["n2_w"], eps=1e-5, shift=sl(3), scale=sl(4), mod_rows=T, out=ws["a"])
+            ops.gemm(ws["att"], W["co_w"], W["co_b"], out=val)
+            ops.norm_modulate(x2, norm=NORM_RMS, weight=W["n2_w"], eps=1e-5, shift=sl(3), scale=sl(4), mod_rows=T, out=ws["a"],
+                              resid=val)
             ops.gemm(ws["a"], W["fc1_w"], W["fc1_b"], act=ops.ACT_GELU_ERF, out=ws["h"])
-            ops.gemm(ws["h"], W["fc2_w"], W["fc2_b"], out_kind=ops.OUT_RESID_F32, out=x2, gate=sl(5), gate_rows=T)
+            ops.gemm(ws["h"], W["fc2_w"], W["fc2_b"], out=val)
+            pend_gate = sl(5)
+        ops.norm_modulate(x2, norm=NORM_NONE, resid=val, resid_gate=pend_gate, resid_gate_rows=T, want_out=False)
         # T2IFinalLayer: shift = table[0] + t, scale = table[1] + t
         return ops.final_layer(xs, ws["t"], ws["t"], P["fin_w"], P["fin_b"], self.input_size,
                                shift_tab=P["fin_tab"][0].contiguous(), scale_tab=P["fin_tab"][1].contiguous())

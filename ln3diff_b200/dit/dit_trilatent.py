@@ -155,7 +155,7 @@ class DiT_TriLatent(nn.Module):
             e = lambda *s, dt=torch.bfloat16: torch.empty(*s, device=dev, dtype=dt)
             ws = dict(tfeat=e(B, 256), th=e(B, D), st=e(B, D),
                       mod=e(B, self._prep["ada_w"].shape[0], dt=torch.float32),
-                      x=e(B, T, D, dt=torch.float32), xb=e(M, D), a=e(M, D), qkv=e(M, 3 * D),
+                      x=e(B, T, D, dt=torch.float32), xb=e(M, D), a=e(M, D), v=e(M, D), qkv=e(M, 3 * D),
                       att=e(M, D), q=e(M, D), h=e(M, int(self.mlp_ratio) * D))
             self._ws[B] = ws
         return ws
@@ -216,22 +216,29 @@ class DiT_TriLatent(nn.Module):
         qkv3 = ws["qkv"].view(B, T, 3 * D)
         att3 = ws["att"].view(B, T, D)
         q3 = ws["q"].view(B, T, D)
+        # Residual adds are deferred: every projection GEMM writes its bf16 output `val`; the next
+        # norm kernel applies x += gate * val while it reads x anyway (one coalesced pass instead of a
+        # thread-per-row read-modify-write in the GEMM epilogue).
+        val, pend_gate = ws["v"], None
         for l, W in enumerate(P["blocks"]):
             m0 = l * 6 * D
             sl = lambda j: mod[:, m0 + j * D: m0 + (j + 1) * D]
-            ops.norm_modulate(x2, norm=NORM_LAYER, shift=sl(0), scale=sl(1), mod_rows=T, out=ws["a"])
+            ops.norm_modulate(x2, norm=NORM_LAYER, shift=sl(0), scale=sl(1), mod_rows=T, out=ws["a"],
+                              resid=val if l > 0 else None, resid_gate=pend_gate, resid_gate_rows=T)
             ops.gemm(ws["a"], W["qkv_w"], W["qkv_b"], out=ws["qkv"])
             ops.fmha(qkv3[:, :, 0:D], qkv3[:, :, D:2 * D], qkv3[:, :, 2 * D:3 * D], H, out=att3)
-            ops.gemm(ws["att"], W["proj_w"], W["proj_b"], out_kind=ops.OUT_RESID_F32, out=x2,
-                     gate=sl(2), gate_rows=T, out2=ws["xb"])
-            # cross-attention on the raw (un-normalised) stream: x += to_out(attn(to_q(x), K, V))
+            ops.gemm(ws["att"], W["proj_w"], W["proj_b"], out=val)
+            # x += gate_msa * attn ; xb = bf16(x): the un-normalised query input of the cross-attention
+            ops.norm_modulate(x2, norm=NORM_NONE, out=ws["xb"], resid=val, resid_gate=sl(2), resid_gate_rows=T)
             ops.gemm(ws["xb"], W["q_w"], out=ws["q"])
             ops.fmha(q3, kv[:, :, l, 0], kv[:, :, l, 1], H, out=att3)
-            ops.gemm(ws["att"], W["o_w"], W["o_b"], out_kind=ops.OUT_RESID_F32, out=x2)
-            ops.norm_modulate(x2, norm=NORM_LAYER, shift=sl(3), scale=sl(4), mod_rows=T, out=ws["a"])
+            ops.gemm(ws["att"], W["o_w"], W["o_b"], out=val)
+            # x += cross_attn (no gate) ; a = modulate(LN(x))
+            ops.norm_modulate(x2, norm=NORM_LAYER, shift=sl(3), scale=sl(4), mod_rows=T, out=ws["a"], resid=val)
             ops.gemm(ws["a"], W["fc1_w"], W["fc1_b"], act=ops.ACT_GELU_ERF, out=ws["h"])
-            ops.gemm(ws["h"], W["fc2_w"], W["fc2_b"], out_kind=ops.OUT_RESID_F32, out=x2,
-                     gate=sl(5), gate_rows=T)
+            ops.gemm(ws["h"], W["fc2_w"], W["fc2_b"], out=val)
+            pend_gate = sl(5)
+        ops.norm_modulate(x2, norm=NORM_NONE, resid=val, resid_gate=pend_gate, resid_gate_rows=T, want_out=False)
         f0 = self.depth * 6 * D
         return ops.final_layer(xs, mod[:, f0:f0 + D], mod[:, f0 + D:f0 + 2 * D], P["fin_w"],
                                P["fin_b"], self.input_size)

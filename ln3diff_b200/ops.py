@@ -118,19 +118,37 @@ def norm_modulate(x: torch.Tensor, *, norm: int, shift: torch.Tensor | None = No
                   scale: torch.Tensor | None = None, mod_rows: int = 1,
                   shift_tab: torch.Tensor | None = None, scale_tab: torch.Tensor | None = None,
                   weight: torch.Tensor | None = None, eps: float = 1e-6, act: int = ACT_NONE,
-                  out: torch.Tensor | None = None) -> torch.Tensor:
+                  out: torch.Tensor | None = None, resid: torch.Tensor | None = None,
+                  resid_gate: torch.Tensor | None = None, resid_gate_rows: int = 1,
+                  want_out: bool = True) -> torch.Tensor | None:
     """bf16( norm(x) * (1 + scale[g]) + shift[g] ), x fp32 (rows, D); shift/scale 2-D fp32 views
-    (groups, D) with unit inner stride and equal row stride; row r uses group r // mod_rows."""
+    (groups, D) with unit inner stride and equal row stride; row r uses group r // mod_rows.
+    With `resid` (bf16 (rows, D)) the residual update x += resid_gate[r // resid_gate_rows] * resid is
+    applied first, IN PLACE on x; want_out=False then skips the normalised output."""
     _cuda(x, "x", torch.float32)
     _req(x.dim() == 2 and x.stride(1) == 1, "x must be (rows, D) with unit inner stride")
     rows, D = x.shape
-    if out is None:
-        out = torch.empty((rows, D), device=x.device, dtype=torch.bfloat16)
-    _cuda(out, "out", torch.bfloat16)
-    _req(out.shape == (rows, D) and out.stride(1) == 1, "out must be (rows, D)")
     a = _lib.NormModulateArgs()
-    a.x, a.out, a.rows, a.D = x.data_ptr(), out.data_ptr(), rows, D
-    a.ldx, a.ldo = x.stride(0), out.stride(0)
+    if want_out:
+        if out is None:
+            out = torch.empty((rows, D), device=x.device, dtype=torch.bfloat16)
+        _cuda(out, "out", torch.bfloat16)
+        _req(out.shape == (rows, D) and out.stride(1) == 1, "out must be (rows, D)")
+        a.out, a.ldo = out.data_ptr(), out.stride(0)
+    else:
+        _req(resid is not None, "want_out=False needs a residual update")
+        out = None
+    if resid is not None:
+        _cuda(resid, "resid", torch.bfloat16)
+        _req(resid.shape == (rows, D) and resid.stride(1) == 1, "resid must be (rows, D) bf16")
+        a.resid, a.resid_ld = resid.data_ptr(), resid.stride(0)
+        if resid_gate is not None:
+            _cuda(resid_gate, "resid_gate", torch.float32)
+            _req(resid_gate.dim() == 2 and resid_gate.shape[1] == D and resid_gate.stride(1) == 1
+                 and resid_gate.shape[0] * resid_gate_rows >= rows, "resid_gate must be a (groups, D) view")
+            a.resid_gate, a.resid_gate_ld, a.resid_gate_rows = resid_gate.data_ptr(), resid_gate.stride(0), resid_gate_rows
+    a.x, a.rows, a.D = x.data_ptr(), rows, D
+    a.ldx = x.stride(0)
     if shift is not None:
         _cuda(shift, "shift", torch.float32)
         _cuda(scale, "scale", torch.float32)

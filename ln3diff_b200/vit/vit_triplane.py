@@ -132,10 +132,16 @@ class RodinSR_256_fusionv6_ConvQuant_liteSR_dinoInit3DAttn_SD_B_3L_C_withrollout
         qkv = torch.empty(M, 3 * D, device=dev, dtype=torch.bfloat16)
         att = torch.empty(M, D, device=dev, dtype=torch.bfloat16)
         hbuf = torch.empty(M, int(vd.mlp_ratio) * D, device=dev, dtype=torch.bfloat16)
+        val = torch.empty(M, D, device=dev, dtype=torch.bfloat16)
+        gate_prev = torch.empty(M, D, device=dev, dtype=torch.float32)   # gate_mlp of the previous block
         for i, W in enumerate(P["blocks"]):
+            # deferred residual of the previous block's MLP uses that block's per-token gate
+            if i > 0:
+                gate_prev.copy_(mod[:, 5 * D:6 * D])
             ops.gemm(sc2, W["ada_w"], W["ada_b"], out_kind=ops.OUT_F32, out=mod)   # per-token adaLN (B*768, 6D)
             sl = lambda j: mod[:, j * D:(j + 1) * D]
-            ops.norm_modulate(x2, norm=NORM_LAYER, shift=sl(0), scale=sl(1), mod_rows=1, out=a)
+            ops.norm_modulate(x2, norm=NORM_LAYER, shift=sl(0), scale=sl(1), mod_rows=1, out=a,
+                              resid=val if i > 0 else None, resid_gate=gate_prev if i > 0 else None, resid_gate_rows=1)
             ops.gemm(a, W["qkv_w"], W["qkv_b"], out=qkv)
             if i % 2 == 0:   # attention within each plane: 'b (n l) c -> (b n) l c'
                 q3 = qkv.view(B * 3, T // 3, 3 * D)
@@ -143,10 +149,12 @@ class RodinSR_256_fusionv6_ConvQuant_liteSR_dinoInit3DAttn_SD_B_3L_C_withrollout
             else:            # global attention over the 3 planes
                 q3 = qkv.view(B, T, 3 * D)
                 ops.fmha(q3[:, :, :D], q3[:, :, D:2 * D], q3[:, :, 2 * D:], H, out=att.view(B, T, D))
-            ops.gemm(att, W["proj_w"], W["proj_b"], out_kind=ops.OUT_RESID_F32, out=x2, gate=sl(2), gate_rows=1)
-            ops.norm_modulate(x2, norm=NORM_LAYER, shift=sl(3), scale=sl(4), mod_rows=1, out=a)
+            ops.gemm(att, W["proj_w"], W["proj_b"], out=val)
+            ops.norm_modulate(x2, norm=NORM_LAYER, shift=sl(3), scale=sl(4), mod_rows=1, out=a,
+                              resid=val, resid_gate=sl(2), resid_gate_rows=1)
             ops.gemm(a, W["fc1_w"], W["fc1_b"], act=ops.ACT_GELU_ERF, out=hbuf)
-            ops.gemm(hbuf, W["fc2_w"], W["fc2_b"], out_kind=ops.OUT_RESID_F32, out=x2, gate=sl(5), gate_rows=1)
+            ops.gemm(hbuf, W["fc2_w"], W["fc2_b"], out=val)
+        ops.norm_modulate(x2, norm=NORM_LAYER, resid=val, resid_gate=mod[:, 5 * D:6 * D], resid_gate_rows=1, want_out=False)
         # tokens (B, 3*16*16, D) are already NHWC (3B, 16, 16, D)
         S = P["sr"]
         ts = self.token_size
