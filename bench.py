@@ -296,7 +296,8 @@ def run_ours(args):
         achieved = gemm_fl / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
         roofline = {"kernel": "ln3::gemm_bf16_kernel<256> (tcgen05 128x256x64, fused epilogues)",
                     "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                    "frac": achieved / peak_tf, "peak_source": peak_src, "traffic": None,
+                    "frac": achieved / peak_tf, "peak_source": peak_src,
+                    "traffic": 54.65e6,  # dram read+write of the captured qkv launch (profiles/r1_ncu_gemm_pair_v0.txt)
                     "launches_measured": len(big), "avg_launch_us": 1e3 * gemm_ms / max(len(big), 1),
                     "flops_per_launch_avg": gemm_fl / max(len(big), 1),
                     "note": "events add launch gaps; gemm share of the forward in profiles/"}
@@ -336,6 +337,28 @@ def run_ours(args):
         except Exception as e:  # noqa
             views = {"error": repr(e)}
 
+        # ---- VAE decode (DiT2-L/2 + conv upsampler) throughput: latent -> channels-last tri-plane
+        vae = None
+        try:
+            from ln3diff_b200.utils import build_ae_decoder
+            dec = build_ae_decoder("DiT2-L/2", device=dev)
+            lat8 = torch.randn(B, 12, 32, 32, device=dev)
+            for _ in range(2):
+                dec.decode_to_channels_last(lat8, in_mul=0.96806)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                dec.decode_to_channels_last(lat8, in_mul=0.96806)
+            e1.record()
+            torch.cuda.synchronize()
+            dms = e0.elapsed_time(e1) / 3
+            vae = {"value": B / (dms / 1e3), "unit": "latents/s", "batch": B, "ms": dms,
+                   "what": "latent (12,32,32) -> tri-plane (3,128,128,32): PatchEmbedTriplane + DiT2-L/2 + SD conv decoder"}
+            del dec
+        except Exception as e:  # noqa
+            vae = {"error": repr(e)}
+
         cpu = None
         if n_gpus == 1:
             v, dt, cores = cpu_reference_sample(n_steps_sample=1, prompts=1)
@@ -350,7 +373,7 @@ def run_ours(args):
                         "h2d_bytes_per_step": randn_h.numel() * 4 + ctx_h.numel() * 4,
                         "d2h_bytes_per_step": out_h.numel() * 4},
                 "gpu_launches": int(launches), "clocks": clk, "roofline": roofline,
-                "model_tflops": model_tf, "rendered_views": views, "cpu_baseline": cpu}
+                "model_tflops": model_tf, "rendered_views": views, "vae_decode": vae, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

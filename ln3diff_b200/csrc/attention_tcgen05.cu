@@ -11,13 +11,21 @@
 //   warps 0-3 / 4-7 : softmax warpgroup of tile 0 / 1; thread r owns query row r (= TMEM lane r), so
 //                     the row max / sum need no cross-thread reduction.  S (128 fp32) is read once
 //                     from TMEM into registers, P = exp2(S*scale - m) goes to 128B-swizzled smem as bf16.
-//   warp 8          : TMA producer (Q once, K/V tiles double buffered)
+//   warp 8          : TMA producer (Q double buffered per item, K/V ring of 3 blocks)
 //   warp 9          : tcgen05.mma issuer:  S_t = Q_t K^T (128x128x16 x4),  O_t += P_t V (128x64x16 x8,
-//                     V MN-major straight from the TMA layout).  While warpgroup 0 runs its softmax the
-//                     tensor core computes S_1 / P_1 V and vice versa.
+//                     V MN-major straight from the TMA layout).  S_t of block g+1 is issued as soon as
+//                     the warpgroup has pulled S_t of block g into registers (s_empty), i.e. BEFORE its
+//                     exponentials, so a warpgroup never waits for the tensor core in steady state.
+// The softmax is MUFU-bound at head_dim 64 (16 ex2/clk/SM against 2 x 128x128 elements per step), so
+// kPolyPer8 of every 8 exponentials are evaluated on the FMA pipe instead (Cody-Waite split + degree-3
+// minimax polynomial, rel. error 8.8e-5 -- below the bf16 rounding of P).
 // O accumulates in TMEM across KV blocks.  The running max is only refreshed when it grew by more
 // than 2^8 (then the owning thread rescales its O row in TMEM); otherwise P is computed against the
 // stale max, which is exact after the final 1/l normalisation.
+#include <type_traits>
+
+#include <cstdlib>
+
 #include "common.cuh"
 #include "ln3_internal.h"
 
@@ -27,8 +35,36 @@ static constexpr int kQT = 128;   // query rows per tile (2 tiles per CTA)
 static constexpr int kKT = 128;   // kv rows per block
 static constexpr int kHD = 64;    // head dim
 static constexpr int kTileBytes = 128 * kHD * 2;  // 16 KB
-// Q[2 buffers][2 tiles] | K[2] | V[2] | P0 (2 atoms) P1 (2 atoms)
-static constexpr int kFmhaSmem = 1024 + kTileBytes * (4 + 2 + 2 + 4) + 256;
+static constexpr int kKVStages = 3;
+// Q[2 buffers][2 tiles] | K[3] | V[3] | P0 (2 atoms) P1 (2 atoms)
+static constexpr int kFmhaSmem = 1024 + kTileBytes * (4 + 2 * kKVStages + 4) + 256;
+static constexpr int kPolyPer8Default = 0;  // exponentials per 8 evaluated on the FMA pipe (LN3_FMHA_POLY)
+
+#ifdef LN3_FMHA_TRACE
+// Debug timeline (tools/microbench/fmha_trace.cu): CTA 0, first 64 KV blocks; role 0/1 = softmax
+// warpgroup 0/1 (thread 0 of the group), role 2 = MMA thread; 8 clock64 slots per block.
+__device__ long long g_fmha_trace[3][64][12];
+#define LN3_TR(role, blk, slot)                                                          \
+  do {                                                                                   \
+    if (blockIdx.x == 0 && (blk) < 64) g_fmha_trace[role][blk][slot] = clock64();        \
+  } while (0)
+#else
+#define LN3_TR(role, blk, slot) do {} while (0)
+#endif
+
+// 2^x for x <= ~8 on the FMA pipe: x = floor(x) + f, 2^f by a degree-3 minimax polynomial, the integer
+// part added straight into the exponent field (the round-down add leaves floor(x) in the low mantissa
+// bits of t).  x is clamped at -126 (result 2^-126 instead of 0: irrelevant after the bf16 rounding).
+__device__ __forceinline__ float exp2_poly(float x) {
+  x = fmaxf(x, -126.f);
+  float t;
+  asm("add.rm.ftz.f32 %0, %1, %2;" : "=f"(t) : "f"(x), "f"(12582912.f));
+  const float f = x - (t - 12582912.f);
+  float q = fmaf(f, 0.077119089663028717041015625f, 0.227564394474029541015625f);
+  q = fmaf(f, q, 0.695146143436431884765625f);
+  q = fmaf(f, q, 1.f);
+  return __uint_as_float(__float_as_uint(q) + (__float_as_uint(t) << 23));
+}
 static constexpr int kFmhaTmemCols = 512;  // S0 [0,128) S1 [128,256) O0 [256,320) O1 [320,384)
 static constexpr int kFmhaThreads = 320;
 static constexpr float kRescaleThreshold = 8.0f;  // log2 units
@@ -37,9 +73,8 @@ struct FmhaParams {
   int Lq, Lkv;
   int Lkv2;  // rows of the optional second K/V source (0 = none)
   int B, H, nq;  // work items = B * H * nq query-row pairs (256 rows each)
+  float rcp_nq, rcp_H;  // 1 / nq, 1 / H (item index decomposition)
   float scale_log2;  // softmax scale * log2(e)
-  __nv_bfloat16* out;
-  long long out_ld, out_bs;  // row / batch stride (elements); head h at column h*64
 };
 
 // Persistent: each CTA walks work items w = blockIdx.x, +gridDim.x, ... (item = one (batch, head,
@@ -47,44 +82,50 @@ struct FmhaParams {
 // buffered, so the TMA warp prefetches the next item's Q / K / V while the current item is still in its
 // softmax -- the per-CTA prologue (TMEM allocation, barrier init, first-load latency) is paid once per
 // SM instead of once per item (it was ~30 % of a self-attention item and most of a cross-attention one).
+template <int kPolyPer8, bool PINGPONG>
 __global__ void __launch_bounds__(kFmhaThreads, 1)
 fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_k2,
-                const __grid_constant__ CUtensorMap tmap_v2, const FmhaParams p) {
+                const __grid_constant__ CUtensorMap tmap_v2, const __grid_constant__ CUtensorMap tmap_o,
+                const FmhaParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* sQ = smem;                  // [2 buffers][2 tiles]
-  uint8_t* sK = sQ + 4 * kTileBytes;   // [2]
-  uint8_t* sV = sK + 2 * kTileBytes;   // [2]
-  uint8_t* sP = sV + 2 * kTileBytes;   // [2 tiles][2 atoms]
+  uint8_t* sK = sQ + 4 * kTileBytes;           // [kKVStages]
+  uint8_t* sV = sK + kKVStages * kTileBytes;   // [kKVStages]
+  uint8_t* sP = sV + kKVStages * kTileBytes;   // [2 tiles][2 atoms]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 4 * kTileBytes);
   uint64_t* q_full = bars;         // [2]
   uint64_t* q_empty = bars + 2;    // [2]
-  uint64_t* kv_full = bars + 4;    // [2]
-  uint64_t* kv_empty = bars + 6;   // [2]
-  uint64_t* s_full = bars + 8;     // [2 tiles]
-  uint64_t* p_full = bars + 10;    // [2 tiles], 128 arrivals
-  uint64_t* o_full = bars + 12;    // [2 tiles]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t* kv_full = bars + 4;    // [kKVStages]
+  uint64_t* kv_empty = bars + 8;   // [kKVStages]
+  uint64_t* s_full = bars + 12;    // [2 tiles]
+  uint64_t* s_empty = bars + 14;   // [2 tiles], 128 arrivals: S_t is in registers
+  uint64_t* p_full = bars + 16;    // [2 tiles], 128 arrivals
+  uint64_t* o_full = bars + 18;    // [2 tiles]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   const int nkv1 = (p.Lkv + kKT - 1) / kKT;  // with a second source Lkv is a multiple of 128
   const int nkv = nkv1 + (p.Lkv2 + kKT - 1) / kKT;
   const int nitems = p.B * p.H * p.nq;
+  // w = (batch * H + head) * nq + qp; divisions by reciprocal multiply (exact for w < 2^20, checked on
+  // the host): a 32-bit integer division is ~150 dependent cycles and sat on every item boundary.
   auto item_coords = [&](int w, int& q0, int& head, int& batch) {
-    const int qp = w % p.nq;
-    const int bh = w / p.nq;
+    const int bh = __float2int_rz((static_cast<float>(w) + 0.5f) * p.rcp_nq);
+    const int qp = w - bh * p.nq;
     q0 = qp * 2 * kQT;
-    head = bh % p.H;
-    batch = bh / p.H;
+    batch = __float2int_rz((static_cast<float>(bh) + 0.5f) * p.rcp_H);
+    head = bh - batch * p.H;
   };
 
   if (tid == 0) {
     tma_prefetch_desc(&tmap_q);
     tma_prefetch_desc(&tmap_k);
     tma_prefetch_desc(&tmap_v);
+    tma_prefetch_desc(&tmap_o);
     if (p.Lkv2 > 0) {
       tma_prefetch_desc(&tmap_k2);
       tma_prefetch_desc(&tmap_v2);
@@ -92,11 +133,14 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     for (int i = 0; i < 2; ++i) {
       mbar_init(&q_full[i], 1);
       mbar_init(&q_empty[i], 1);
-      mbar_init(&kv_full[i], 1);
-      mbar_init(&kv_empty[i], 1);
       mbar_init(&s_full[i], 1);
+      mbar_init(&s_empty[i], 128);
       mbar_init(&p_full[i], 128);
       mbar_init(&o_full[i], 1);
+    }
+    for (int i = 0; i < kKVStages; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
     }
     fence_barrier_init();
   }
@@ -112,7 +156,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   if (warp == 8) {
     // ------------------------------------------------------------ TMA producer
     if ((tid & 31) == 0) {
-      int it = 0, g = 0;
+      int it = 0, kst = 0, kph = 0;
       for (int w = blockIdx.x; w < nitems; w += gridDim.x, ++it) {
         int q0, head, batch;
         item_coords(w, q0, head, batch);
@@ -121,9 +165,10 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         mbar_arrive_expect_tx(&q_full[qb], 2 * kTileBytes);
         for (int t = 0; t < 2; ++t)
           tma_load_3d(sQ + (qb * 2 + t) * kTileBytes, &tmap_q, &q_full[qb], head * kHD, q0 + t * kQT, batch);
-        for (int j = 0; j < nkv; ++j, ++g) {
-          const int b = g & 1;
-          mbar_wait(&kv_empty[b], ((g >> 1) & 1) ^ 1);
+        for (int j = 0; j < nkv; ++j) {
+          const int b = kst;
+          mbar_wait(&kv_empty[b], kph ^ 1);
+          if (++kst == kKVStages) kst = 0, kph ^= 1;
           mbar_arrive_expect_tx(&kv_full[b], 2 * kTileBytes);
           if (j < nkv1) {
             tma_load_3d(sK + b * kTileBytes, &tmap_k, &kv_full[b], head * kHD, j * kKT, batch);
@@ -137,55 +182,78 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     }
   } else if (warp == 9) {
     // ------------------------------------------------------------ MMA issuer
-    if ((tid & 31) == 0) {
+    // The whole warp walks this loop with warp-uniform values (so descriptors live in uniform
+    // registers); elect_one_sync() guards only the tcgen05 instructions themselves.
+    {
       constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
       constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);  // B (= V) is MN-major
-      auto issue_qk = [&](int t, int qb, int gblk) {
-        const uint32_t qa = smem_u32(sQ + (qb * 2 + t) * kTileBytes), ka = smem_u32(sK + (gblk & 1) * kTileBytes);
+      const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint64_t dQ = make_smem_desc_sw128(smem_u32(sQ), 0, 1024);      // + tile * (kTileBytes >> 4)
+      const uint64_t dK = make_smem_desc_sw128(smem_u32(sK), 0, 1024);
+      const uint64_t dV = make_smem_desc_sw128(smem_u32(sV), 1024, 1024);
+      const uint64_t dP = make_smem_desc_sw128(smem_u32(sP), 0, 1024);
+      constexpr uint32_t kTileD = kTileBytes >> 4;  // descriptor address units (16 B)
+      const int n_my = (nitems - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
+                       static_cast<int>(gridDim.x);
+      const int G = n_my * nkv;  // KV blocks this CTA walks, over all of its items
+      // All ring / item bookkeeping is incremental (no divisions on the issue path).
+      int q_it = 0, q_j = 0, q_st = 0, q_ph = 0;  // next S block to issue: item, block in item, kv stage/phase
+      auto issue_qk_block = [&](int gb) {
+        const int qb = q_it & 1;
+        if (q_j == 0) mbar_wait(&q_full[qb], (q_it >> 1) & 1);
+        mbar_wait(&kv_full[q_st], q_ph);
+        LN3_TR(2, gb, 0);  // K of block gb landed
+        const uint64_t kd = dK + static_cast<uint32_t>(q_st) * kTileD;
 #pragma unroll
-        for (int k = 0; k < kHD / 16; ++k)
-          umma_f16_ss(tmem_base + t * 128, make_smem_desc_sw128(qa + k * 32, 0, 1024),
-                      make_smem_desc_sw128(ka + k * 32, 0, 1024), idesc_s, k != 0);
-        umma_commit(&s_full[t]);
-      };
-      int it = 0, g = 0;
-      for (int w = blockIdx.x; w < nitems; w += gridDim.x, ++it) {
-        const int qb = it & 1;
-        const bool has_next_item = w + static_cast<int>(gridDim.x) < nitems;
-        if (it == 0) {  // very first block of this CTA: nothing has been issued ahead
-          mbar_wait(&q_full[0], 0);
-          mbar_wait(&kv_full[0], 0);
+        for (int t = 0; t < 2; ++t) {
+          if (gb > 0) mbar_wait(&s_empty[t], (gb - 1) & 1);  // S_t of block gb-1 is in registers
           tc_fence_after();
-          issue_qk(0, 0, 0);
-          issue_qk(1, 0, 0);
+          const uint64_t qd = dQ + static_cast<uint32_t>(qb * 2 + t) * kTileD;
+          if (elect_one_sync()) {
+#pragma unroll
+            for (int k = 0; k < kHD / 16; ++k)
+              umma_f16_ss(tm + t * 128, qd + 2 * k, kd + 2 * k, idesc_s, k != 0);
+            umma_commit(&s_full[t]);
+          }
+          __syncwarp();
+          LN3_TR(2, gb, 1 + t);  // QK_t(gb) issued
         }
-        for (int j = 0; j < nkv; ++j, ++g) {
-          const bool last = j + 1 == nkv;
-          const bool next_exists = !last || has_next_item;
-          const int next_qb = last ? ((it + 1) & 1) : qb;
-          for (int t = 0; t < 2; ++t) {
-            mbar_wait(&p_full[t], g & 1);  // P_t in smem, S_t consumed, O_t rescaled if needed
-            tc_fence_after();
-            const uint32_t pa = smem_u32(sP + t * 2 * kTileBytes);
-            const uint32_t va = smem_u32(sV + (g & 1) * kTileBytes);
+        if (++q_j == nkv) {
+          if (elect_one_sync()) umma_commit(&q_empty[qb]);  // every QK of this item has been issued
+          __syncwarp();
+          q_j = 0;
+          ++q_it;
+        }
+        if (++q_st == kKVStages) q_st = 0, q_ph ^= 1;
+      };
+      if (G > 0) issue_qk_block(0);
+      int j = 0, st = 0;
+      for (int g = 0; g < G; ++g) {
+        if (g + 1 < G) issue_qk_block(g + 1);
+        const int kv_valid = (j < nkv1) ? p.Lkv - j * kKT : p.Lkv2 - (j - nkv1) * kKT;
+        const int ksteps = kv_valid >= kKT ? kKT / 16 : (kv_valid + 15) >> 4;  // P beyond is never written
+        const uint64_t vd = dV + static_cast<uint32_t>(st) * kTileD;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          mbar_wait(&p_full[t], g & 1);  // P_t in smem, O_t rescaled if needed
+          LN3_TR(2, g, 3 + 2 * t);  // p_full seen
+          tc_fence_after();
+          const uint64_t pd = dP + static_cast<uint32_t>(t * 2) * kTileD;
+          if (elect_one_sync()) {
 #pragma unroll
             for (int k = 0; k < kKT / 16; ++k)
-              umma_f16_ss(tmem_base + 256 + t * 64,
-                          make_smem_desc_sw128(pa + (k >> 2) * kTileBytes + (k & 3) * 32, 0, 1024),
-                          make_smem_desc_sw128(va + k * 16 * 128, 1024, 1024), idesc_o, (j | k) != 0);
+              if (k < ksteps)
+                umma_f16_ss(tm + 256 + t * 64, pd + (k >> 2) * kTileD + (k & 3) * 2, vd + k * 128, idesc_o,
+                            (j | k) != 0);
             umma_commit(&o_full[t]);
-            if (next_exists) {  // S of the next block (possibly the first block of the next item)
-              if (t == 0) {
-                if (last) mbar_wait(&q_full[next_qb], ((it + 1) >> 1) & 1);
-                mbar_wait(&kv_full[(g + 1) & 1], ((g + 1) >> 1) & 1);
-                tc_fence_after();
-              }
-              issue_qk(t, next_qb, g + 1);
-            }
           }
-          umma_commit(&kv_empty[g & 1]);  // every MMA that read K / V of block g has been issued
-          if (last) umma_commit(&q_empty[qb]);  // ... and every QK of this item
+          __syncwarp();
+          LN3_TR(2, g, 4 + 2 * t);  // PV_t(g) issued
         }
+        if (elect_one_sync()) umma_commit(&kv_empty[st]);  // every MMA that read K / V of block g has been issued
+        __syncwarp();
+        if (++j == nkv) j = 0;
+        if (++st == kKVStages) st = 0;
       }
     }
   } else if (warp < 8) {
@@ -198,13 +266,20 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     const uint32_t p_row = smem_u32(sP + t * 2 * kTileBytes) + row * 128;
     const int swz = row & 7;
     int g = 0;
+    bool o_store_pending = false;  // thread 0 of the group: a bulk store may still be reading P_t's smem
+    // XU baton: the two warpgroups take turns in the exponential phase (named barriers 1 + t, 256
+    // participants = 128 waiting + 128 arriving).  Left alone they fall into lock-step -- both in the
+    // MUFU-bound phase together, then both idle on the tensor core -- and the XU pipe sits at ~45 %.
+    if (PINGPONG && t == 1) named_bar_arrive(1, 256);  // warpgroup 0 goes first
     for (int w = blockIdx.x; w < nitems; w += gridDim.x) {
       int q0, head, batch;
       item_coords(w, q0, head, batch);
       float m_ref = -INFINITY, l_run = 0.f;
       for (int j = 0; j < nkv; ++j, ++g) {
         const int kv_valid = (j < nkv1) ? p.Lkv - j * kKT : p.Lkv2 - (j - nkv1) * kKT;  // >= 1
+        if (row == 0) LN3_TR(t, g, 0);  // start waiting for S
         mbar_wait(&s_full[t], g & 1);
+        if (row == 0) LN3_TR(t, g, 1);  // S ready
         tc_fence_after();
         uint32_t s[128];
         tmem_ld_32x32(tS + 0, s);
@@ -212,15 +287,31 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         tmem_ld_32x32(tS + 64, s + 64);
         tmem_ld_32x32(tS + 96, s + 96);
         tmem_ld_wait();
+        if (row == 0) LN3_TR(t, g, 2);  // S in registers
+        tc_fence_before();
+        mbar_arrive(&s_empty[t]);  // the tensor core may overwrite S_t with the next block now
         if (kv_valid < kKT) {
 #pragma unroll
           for (int i = 0; i < 128; ++i)
             if (i >= kv_valid) s[i] = 0xff800000u;  // -inf
         }
-        float mx = fmax3(__uint_as_float(s[0]), __uint_as_float(s[1]), __uint_as_float(s[2]));
+        const int c_end = kv_valid >= kKT ? kKT : (kv_valid + 15) & ~15;  // = 16 * PV k-steps
+        // four independent 3-input max chains (a single chain is 64 dependent FMNMX3 deep)
+        float mq[4];
 #pragma unroll
-        for (int i = 3; i < 127; i += 2) mx = fmax3(mx, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
-        mx = fmaxf(mx, __uint_as_float(s[127]));
+        for (int a = 0; a < 4; ++a) {
+          const int b0 = 32 * a;
+          mq[a] = fmax3(__uint_as_float(s[b0]), __uint_as_float(s[b0 + 1]), __uint_as_float(s[b0 + 2]));
+        }
+#pragma unroll
+        for (int i = 3; i < 31; i += 2) {
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+            mq[a] = fmax3(mq[a], __uint_as_float(s[32 * a + i]), __uint_as_float(s[32 * a + i + 1]));
+        }
+        const float mx = fmax3(fmax3(mq[0], mq[1], mq[2]), mq[3],
+                               fmax3(__uint_as_float(s[31]), __uint_as_float(s[63]),
+                                     fmaxf(__uint_as_float(s[95]), __uint_as_float(s[127]))));
         const float m_cand = mx * p.scale_log2;
         float alpha = 1.f;
         bool need = false;
@@ -232,23 +323,46 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           m_ref = m_cand;
           l_run *= alpha;
         }
-        float rs = 0.f;
-#pragma unroll
-        for (int c = 0; c < 128; c += 8) {
-          float e[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) e[i] = fast_exp2(fmaf(__uint_as_float(s[c + i]), p.scale_log2, -m_ref));
-          rs += ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));
-          const uint32_t addr = p_row + (c >> 6) * kTileBytes + ((((c & 63) >> 3) ^ swz) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pack_bf16x2(e[0], e[1])),
-                       "r"(pack_bf16x2(e[2], e[3])), "r"(pack_bf16x2(e[4], e[5])),
-                       "r"(pack_bf16x2(e[6], e[7]))
-                       : "memory");
+        // P_t (smem) is still being read by P_t V of the previous block until o_full fires; S of this
+        // block was issued ahead of that MMA, so s_full alone no longer orders the two.
+        if (row == 0) LN3_TR(t, g, 3);  // max done
+        if (j == 0 && g > 0) {  // previous item's O tile left this buffer?  (long done; one barrier per item)
+          if (row == 0 && o_store_pending) tma_store_wait_read();
+          named_bar_sync(3 + t, 128);
         }
+        if (g > 0) mbar_wait(&o_full[t], (g - 1) & 1);
+        if (row == 0) LN3_TR(t, g, 4);  // O of previous block complete
+        if (PINGPONG) named_bar_sync(1 + t, 256);
+        if (row == 0) LN3_TR(t, g, 5);  // baton
+        float rs = 0.f;
+        // FULL blocks: one straight-line region of 128 exponentials (the scheduler interleaves MUFU,
+        // polynomial and st.shared across chunks); ragged last block: stop at c_end.
+        auto exp_store = [&](auto full_tag) {
+          constexpr bool FULL = decltype(full_tag)::value;
+#pragma unroll
+          for (int c = 0; c < 128; c += 8) {
+            if (!FULL && c >= c_end) break;
+            float e[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float x = fmaf(__uint_as_float(s[c + i]), p.scale_log2, -m_ref);
+              e[i] = (i < kPolyPer8) ? exp2_poly(x) : fast_exp2(x);
+            }
+            rs += ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));
+            const uint32_t addr = p_row + (c >> 6) * kTileBytes + ((((c & 63) >> 3) ^ swz) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pack_bf16x2(e[0], e[1])),
+                         "r"(pack_bf16x2(e[2], e[3])), "r"(pack_bf16x2(e[4], e[5])),
+                         "r"(pack_bf16x2(e[6], e[7]))
+                         : "memory");
+          }
+        };
+        if (kv_valid >= kKT) exp_store(std::true_type{});
+        else exp_store(std::false_type{});
+        if (row == 0) LN3_TR(t, g, 6);  // exponentials done
+        if (PINGPONG) named_bar_arrive(2 - t, 256);
         l_run += rs;
         if (j > 0 && __any_sync(0xffffffffu, need)) {
-          // O_t of the previous block must be complete before it is rescaled in place
-          mbar_wait(&o_full[t], (g - 1) & 1);
+          // O_t of the previous block is complete (o_full waited above): rescale it in place
           tc_fence_after();
 #pragma unroll
           for (int c = 0; c < kHD; c += 32) {
@@ -264,30 +378,43 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         fence_proxy_async_smem();  // P (generic-proxy stores) -> visible to the tensor core
         tc_fence_before();
         mbar_arrive(&p_full[t]);
+        if (row == 0) LN3_TR(t, g, 7);  // P handed to the tensor core
       }
+      if (row == 0) LN3_TR(t, g - 1, 8);   // epilogue: start waiting for the last P V
       mbar_wait(&o_full[t], (g - 1) & 1);
+      if (row == 0) LN3_TR(t, g - 1, 9);   // O complete
       tc_fence_after();
       const float inv = 1.f / l_run;
-      const int qrow = q0 + t * kQT + row;
-      __nv_bfloat16* dst = p.out + batch * p.out_bs + static_cast<long long>(qrow) * p.out_ld + head * kHD;
+      // O_t -> bf16 -> this tile's (now idle) P buffer in the 128B-swizzled TMA layout -> one bulk tensor
+      // store per tile.  (Per-thread row stores touched 32 lines per instruction: ~2000 cycles per item.)
 #pragma unroll
       for (int c = 0; c < kHD; c += 32) {
         uint32_t v[32];
         tmem_ld_32x32(tO + c, v);
         tmem_ld_wait();
-        if (qrow < p.Lq) {
 #pragma unroll
-          for (int i = 0; i < 32; i += 8) {
-            uint4 q;
-            q.x = pack_bf16x2(__uint_as_float(v[i]) * inv, __uint_as_float(v[i + 1]) * inv);
-            q.y = pack_bf16x2(__uint_as_float(v[i + 2]) * inv, __uint_as_float(v[i + 3]) * inv);
-            q.z = pack_bf16x2(__uint_as_float(v[i + 4]) * inv, __uint_as_float(v[i + 5]) * inv);
-            q.w = pack_bf16x2(__uint_as_float(v[i + 6]) * inv, __uint_as_float(v[i + 7]) * inv);
-            *reinterpret_cast<uint4*>(dst + c + i) = q;
-          }
+        for (int i = 0; i < 32; i += 8) {
+          const uint32_t addr = p_row + ((((c + i) >> 3) ^ swz) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr),
+                       "r"(pack_bf16x2(__uint_as_float(v[i]) * inv, __uint_as_float(v[i + 1]) * inv)),
+                       "r"(pack_bf16x2(__uint_as_float(v[i + 2]) * inv, __uint_as_float(v[i + 3]) * inv)),
+                       "r"(pack_bf16x2(__uint_as_float(v[i + 4]) * inv, __uint_as_float(v[i + 5]) * inv)),
+                       "r"(pack_bf16x2(__uint_as_float(v[i + 6]) * inv, __uint_as_float(v[i + 7]) * inv))
+                       : "memory");
         }
       }
+      fence_proxy_async_smem();
+      tc_fence_before();  // the TMEM reads above precede the next item's first P_t V (accumulate = 0)
+      named_bar_sync(3 + t, 128);
+      if (row == 0) {
+        tma_store_3d(sP + t * 2 * kTileBytes, &tmap_o, head * kHD, q0 + t * kQT, batch);
+        tma_store_commit();
+        o_store_pending = true;
+      }
+      if (row == 0) LN3_TR(t, g - 1, 10);  // O stored
     }
+    if (PINGPONG && t == 0) named_bar_sync(1, 256);  // consume warpgroup 1's last hand-over
+    if (row == 0 && o_store_pending) tma_store_wait_all();  // smem must outlive the bulk store
   }
 
   tc_fence_before();
@@ -305,13 +432,25 @@ int fmha_fwd(const ln3_fmha_args* a, cudaStream_t stream) {
   if ((reinterpret_cast<uintptr_t>(a->q) | reinterpret_cast<uintptr_t>(a->k) |
        reinterpret_cast<uintptr_t>(a->v) | reinterpret_cast<uintptr_t>(a->out)) & 15)
     return set_error(LN3_EINVAL, "fmha: pointers must be 16-byte aligned");
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(fmha_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         kFmhaSmem);
-    if (e != cudaSuccess)
-      return set_error(LN3_ECUDA, "fmha: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr_set = true;
+  // tuning knobs, read once: LN3_FMHA_POLY = exponentials per 8 on the FMA pipe (0, 2, 3, 4);
+  // LN3_FMHA_PINGPONG = 1 enables the XU baton between the two softmax warpgroups (measured: no gain)
+  static int variant = -1;
+  if (variant < 0) {
+    const char* ev = getenv("LN3_FMHA_POLY");
+    int v = ev ? atoi(ev) : kPolyPer8Default;
+    if (v != 0 && v != 2 && v != 3 && v != 4) v = kPolyPer8Default;
+    const char* pp = getenv("LN3_FMHA_PINGPONG");
+    const int ping = (pp && atoi(pp) != 0) ? 1 : 0;
+    cudaError_t e = cudaSuccess;
+    auto set = [&](auto* k) {
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kFmhaSmem);
+    };
+    set(fmha_fwd_kernel<0, false>); set(fmha_fwd_kernel<0, true>);
+    set(fmha_fwd_kernel<2, false>); set(fmha_fwd_kernel<2, true>);
+    set(fmha_fwd_kernel<3, false>); set(fmha_fwd_kernel<3, true>);
+    set(fmha_fwd_kernel<4, false>); set(fmha_fwd_kernel<4, true>);
+    if (e != cudaSuccess) return set_error(LN3_ECUDA, "fmha: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    variant = v * 2 + ping;
   }
   if (a->k2 != nullptr || a->v2 != nullptr) {
     if (!a->k2 || !a->v2 || a->Lkv2 <= 0) return set_error(LN3_EINVAL, "fmha: k2/v2/Lkv2 must be given together");
@@ -320,12 +459,13 @@ int fmha_fwd(const ln3_fmha_args* a, cudaStream_t stream) {
         ((reinterpret_cast<uintptr_t>(a->k2) | reinterpret_cast<uintptr_t>(a->v2)) & 15))
       return set_error(LN3_EINVAL, "fmha: k2/v2 alignment");
   }
-  CUtensorMap tq, tk, tv, tk2, tv2;
+  CUtensorMap tq, tk, tv, tk2, tv2, to;
   int rc;
   const long long cols = static_cast<long long>(a->H) * kHD;
   if ((rc = make_tmap_3d_bf16(&tq, a->q, cols, a->Lq, a->B, a->q_ld, a->q_bs, kHD, kQT))) return rc;
   if ((rc = make_tmap_3d_bf16(&tk, a->k, cols, a->Lkv, a->B, a->k_ld, a->k_bs, kHD, kKT))) return rc;
   if ((rc = make_tmap_3d_bf16(&tv, a->v, cols, a->Lkv, a->B, a->v_ld, a->v_bs, kHD, kKT))) return rc;
+  if ((rc = make_tmap_3d_bf16(&to, a->out, cols, a->Lq, a->B, a->o_ld, a->o_bs, kHD, kQT))) return rc;
   const bool two = a->k2 != nullptr;
   if (two) {
     if ((rc = make_tmap_3d_bf16(&tk2, a->k2, cols, a->Lkv2, a->B, a->k2_ld, a->k2_bs, kHD, kKT))) return rc;
@@ -339,20 +479,33 @@ int fmha_fwd(const ln3_fmha_args* a, cudaStream_t stream) {
   p.Lkv = a->Lkv;
   p.Lkv2 = two ? a->Lkv2 : 0;
   p.scale_log2 = a->scale * 1.4426950408889634f;
-  p.out = reinterpret_cast<__nv_bfloat16*>(a->out);
-  p.out_ld = a->o_ld;
-  p.out_bs = a->o_bs;
   p.B = a->B;
   p.H = a->H;
   p.nq = (a->Lq + 2 * kQT - 1) / (2 * kQT);
+  p.rcp_nq = 1.0f / static_cast<float>(p.nq);
+  p.rcp_H = 1.0f / static_cast<float>(p.H);
   const long long nitems = static_cast<long long>(p.B) * p.H * p.nq;
+  if (nitems >= (1 << 20)) return set_error(LN3_EUNSUPPORTED, "fmha: more than 2^20 (batch, head, 256-row) work items");
   const int sms = device_sm_count();
   const int grid = static_cast<int>(nitems < sms ? nitems : sms);
-  fmha_fwd_kernel<<<grid, kFmhaThreads, kFmhaSmem, stream>>>(tq, tk, tv, tk2, tv2, p);
+  switch (variant) {
+#define LN3_FMHA_CASE(P, G) \
+  case (P) * 2 + (G): fmha_fwd_kernel<P, (G) != 0><<<grid, kFmhaThreads, kFmhaSmem, stream>>>(tq, tk, tv, tk2, tv2, to, p); break;
+    LN3_FMHA_CASE(0, 0) LN3_FMHA_CASE(0, 1) LN3_FMHA_CASE(2, 0) LN3_FMHA_CASE(2, 1)
+    LN3_FMHA_CASE(3, 0) LN3_FMHA_CASE(3, 1) LN3_FMHA_CASE(4, 0) LN3_FMHA_CASE(4, 1)
+#undef LN3_FMHA_CASE
+    default: return set_error(LN3_EINVAL, "fmha: bad variant");
+  }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(LN3_ECUDA, "fmha launch: %s", cudaGetErrorString(e));
   count_launch();
   return LN3_OK;
 }
+
+#ifdef LN3_FMHA_TRACE
+int fmha_trace_copy(long long* host) {
+  return cudaMemcpyFromSymbol(host, g_fmha_trace, sizeof(g_fmha_trace)) == cudaSuccess ? 0 : 1;
+}
+#endif
 
 }  // namespace ln3

@@ -93,6 +93,18 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// smem -> global tile store (bulk async group); rows / columns outside the tensor are clipped.
+__device__ __forceinline__ void tma_store_3d(const void* smem_src, const CUtensorMap* m, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all of this thread's bulk stores have finished READING their smem source
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // ------------------------------------------------------------------ tcgen05 / TMEM
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
@@ -159,6 +171,24 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t* v)
       "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]),
       "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
       : "memory");
+}
+// One lane of the (converged) warp.  Code that feeds tcgen05.mma should run warp-uniformly and guard
+// only the issue itself with this: inside an `if (lane == 0)` region ptxas cannot prove descriptors
+// uniform and wraps every UTCHMMA in an ELECT / R2UR.BROADCAST waterfall (~100 cycles per MMA).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
   float d;
@@ -292,15 +322,34 @@ __device__ __forceinline__ void stg256_b32(void* p, const uint32_t* v) {
 __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }
-// erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7) with MUFU rcp / ex2: ~12 instructions instead of
-// erff's ~25; used where the result is rounded to bf16 anyway (FusedMLP epilogue).
+// GELU(x) = x * Phi(x) with erfc by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7):
+//   erfc(z) = t(a1 + t(a2 + t(a3 + t(a4 + t a5)))) exp(-z^2),  t = 1/(1 + p z),  z = |x|/sqrt2
+//   GELU(x) = relu(x) - |x| * 0.5 erfc(z)          (both signs of x)
+// Written with s = |x| * sqrt(log2(e)/2) so that exp(-z^2) = 2^(-s*s), the 0.5 folded into the a_i, and
+// raw MUFU rcp/ex2 (.ftz: no range fix-up code): 5 FMUL + 5 FFMA + FMNMX + FADD + 2 MUFU per element,
+// against ~25 for the __fdividef/__expf form and ~40 for erff.  Used where the result is rounded to bf16.
+__device__ __forceinline__ float rcp_approx_ftz(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float ex2_approx_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float gelu_erf_fast(float x) {
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __fdividef(1.f, fmaf(0.3275911f, z, 1.f));
-  const float poly = t * (0.254829592f + t * (-0.284496736f + t * (1.421413741f + t * (-1.453152027f + t * 1.061405429f))));
-  const float e = poly * __expf(-z * z);           // 1 - erf(z)
-  const float erf_abs = 1.f - e;
-  return 0.5f * x * (1.f + copysignf(erf_abs, x));
+  constexpr float kS = 0.84932180028801904272f;                 // sqrt(log2(e) / 2)
+  constexpr float kP = 0.3275911f * 0.70710678118654752440f / kS;  // p * z = kP * s
+  const float s = fabsf(x) * kS;
+  const float t = rcp_approx_ftz(fmaf(kP, s, 1.f));
+  float q = fmaf(t, 0.5f * 1.061405429f, 0.5f * -1.453152027f);
+  q = fmaf(t, q, 0.5f * 1.421413741f);
+  q = fmaf(t, q, 0.5f * -0.284496736f);
+  q = fmaf(t, q, 0.5f * 0.254829592f);
+  const float e = ex2_approx_ftz(s * -s);
+  const float w = (q * t) * (e * x);                            // x * 0.5 erfc(z), sign of x
+  return fmaxf(x, 0.f) - fabsf(w);
 }
 __device__ __forceinline__ float gelu_tanh(float x) {
   const float k0 = 0.7978845608028654f, k1 = 0.044715f;

@@ -28,9 +28,10 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 template <int NV>
 __global__ void __launch_bounds__(256)
 norm_modulate_kernel(const ln3_norm_modulate_args a) {
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= a.rows) return;
   const int lane = threadIdx.x & 31;
+  // grid-stride over rows: the host sizes the grid to one resident wave, so there is no partial last wave
+  for (int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < a.rows;
+       row += gridDim.x * (blockDim.x >> 5)) {
   const float* x = a.x + static_cast<long long>(row) * a.ldx;
   float4 v[NV];
 #pragma unroll
@@ -54,7 +55,7 @@ norm_modulate_kernel(const ln3_norm_modulate_args a) {
       v[i].w = fmaf(g.w, __high2float(r23), v[i].w);
       *reinterpret_cast<float4*>(xw + c) = v[i];
     }
-    if (a.out == nullptr) return;
+    if (a.out == nullptr) continue;
   }
 
   float mean = 0.f, rstd = 1.f;
@@ -117,6 +118,7 @@ norm_modulate_kernel(const ln3_norm_modulate_args a) {
     pk.y = pack_bf16x2(y.z, y.w);
     *reinterpret_cast<uint2*>(o + c) = pk;
   }
+  }  // row loop
 }
 
 int norm_modulate(const ln3_norm_modulate_args* a, cudaStream_t stream) {
@@ -138,7 +140,9 @@ int norm_modulate(const ln3_norm_modulate_args* a, cudaStream_t stream) {
       return set_error(LN3_EINVAL, "norm_modulate: bad resid_gate_rows / resid_gate_ld");
   }
   const int warps = 8;
-  dim3 grid((a->rows + warps - 1) / warps), block(warps * 32);
+  const int blocks_needed = (a->rows + warps - 1) / warps;
+  const int wave = device_sm_count() * 4;  // 4 x 256-thread blocks resident per SM (<= 64 regs/thread)
+  dim3 grid(blocks_needed < wave ? blocks_needed : wave), block(warps * 32);
   switch (a->D / 128) {
 #define LN3_NM_CASE(n) \
   case n: norm_modulate_kernel<n><<<grid, block, 0, stream>>>(*a); break;
@@ -207,12 +211,63 @@ patch_embed_kernel(const ln3_patch_embed_args a) {
   }
 }
 
+// Cin == 4 fast path (the tri-latent: K = 16).  Block = 16 consecutive tokens; each thread keeps the
+// 16 weights of its output channel in registers and walks the tokens, so the weight matrix is read once
+// per block instead of once per token and every store is a coalesced 1 KB row segment.
+constexpr int kPeTok = 16;
+__global__ void __launch_bounds__(256)
+patch_embed_k16_kernel(const ln3_patch_embed_args a) {
+  __shared__ float xin[kPeTok][16];
+  const int P = a.S / 2, L = P * P;
+  const int ntok = a.B * 3 * L;
+  const int tok0 = blockIdx.x * kPeTok;
+  {
+    const int t = threadIdx.x >> 4, k = threadIdx.x & 15;
+    const int tok = tok0 + t;
+    if (tok < ntok) {
+      const int b = tok / (3 * L);
+      const int nl = tok - b * 3 * L;
+      const int n = nl / L, l = nl - n * L;
+      const int pi = l / P, pj = l - pi * P;
+      const int c = k >> 2, p = (k >> 1) & 1, q = k & 1;
+      const float s = a.in_scale ? a.in_scale[b] : 1.f;
+      xin[t][k] = s * a.x[((static_cast<long long>(b) * 12 + c * 3 + n) * a.S + 2 * pi + p) * a.S + 2 * pj + q];
+    }
+  }
+  __syncthreads();
+  for (int d = threadIdx.x; d < a.D; d += 256) {
+    float w[16];
+    const float4* wp = reinterpret_cast<const float4*>(a.weight + static_cast<long long>(d) * 16);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 v = __ldg(wp + i);
+      w[4 * i] = v.x, w[4 * i + 1] = v.y, w[4 * i + 2] = v.z, w[4 * i + 3] = v.w;
+    }
+    const float bias = a.bias ? a.bias[d] : 0.f;
+    const int nl0 = tok0 % (3 * L);  // 3L is a multiple of kPeTok for every supported S, so no wrap inside a block
+#pragma unroll
+    for (int t = 0; t < kPeTok; ++t) {
+      const int tok = tok0 + t;
+      float acc = bias;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) acc = fmaf(w[k], xin[t][k], acc);
+      if (tok < ntok) {
+        if (a.pos_embed) acc += __ldg(a.pos_embed + static_cast<long long>((nl0 + t) % (3 * L)) * a.D + d);
+        a.tokens[static_cast<long long>(tok) * a.D + d] = acc;
+      }
+    }
+  }
+}
+
 int patch_embed(const ln3_patch_embed_args* a, cudaStream_t stream) {
   if (a->B <= 0) return LN3_OK;
   if (a->S % 2 || a->Cin <= 0 || a->Cin > 16 || a->D <= 0)
     return set_error(LN3_EINVAL, "patch_embed: need even S, 1 <= Cin <= 16");
   const int L = (a->S / 2) * (a->S / 2);
-  patch_embed_kernel<<<a->B * 3 * L, 256, 0, stream>>>(*a);
+  if (a->Cin == 4)
+    patch_embed_k16_kernel<<<(a->B * 3 * L + kPeTok - 1) / kPeTok, 256, 0, stream>>>(*a);
+  else
+    patch_embed_kernel<<<a->B * 3 * L, 256, 0, stream>>>(*a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(LN3_ECUDA, "patch_embed launch: %s", cudaGetErrorString(e));
   count_launch();

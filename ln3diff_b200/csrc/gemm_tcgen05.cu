@@ -277,8 +277,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {  // warp-uniform; elect_one_sync() only around the tcgen05 instructions (see the pair kernel)
       constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
+      const uint32_t tm_base = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint64_t a_desc0 = make_smem_desc_sw128(smem_u32(smem_a), 0, 1024);
+      const uint64_t b_desc0 = make_smem_desc_sw128(smem_u32(smem_b), 0, 1024);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -286,25 +289,25 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
+        const uint32_t d_tmem = tm_base + acc * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem_a + stage * Cfg::kABytes);
-          const uint32_t b_addr = smem_u32(smem_b + stage * Cfg::kBBytes);
+          const uint64_t da = a_desc0 + static_cast<uint32_t>(stage) * (Cfg::kABytes >> 4);
+          const uint64_t db = b_desc0 + static_cast<uint32_t>(stage) * (Cfg::kBBytes >> 4);
+          if (elect_one_sync()) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t da = make_smem_desc_sw128(a_addr + k * 32, 0, 1024);
-            const uint64_t db = make_smem_desc_sw128(b_addr + k * 32, 0, 1024);
-            umma_f16_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k) umma_f16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_commit(&empty_bar[stage]);  // frees this smem stage when the MMAs retire
           }
-          umma_commit(&empty_bar[stage]);  // frees this smem stage when the MMAs retire
+          __syncwarp();
           if (++stage == Cfg::kStages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+        if (elect_one_sync()) umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+        __syncwarp();
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
@@ -590,8 +593,13 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       }
     }
   } else if (warp == 1) {
-    if (leader && lane == 0) {
+    // Warp-uniform control flow + elect_one_sync() around the tcgen05 instructions only: with an
+    // `if (lane == 0)` region ptxas wraps every UTCHMMA in an ELECT / R2UR.BROADCAST waterfall.
+    if (leader) {
       constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN, 0, 0);
+      const uint32_t tm_base = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint64_t a_desc0 = make_smem_desc_sw128(smem_u32(smem_a), 0, 1024);
+      const uint64_t b_desc0 = make_smem_desc_sw128(smem_u32(smem_b), 0, 1024);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -599,23 +607,26 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       for (int t = pair; t < num_tiles; t += num_pairs) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
+        const uint32_t d_tmem = tm_base + acc * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem_a + stage * kABytes);
-          const uint32_t b_addr = smem_u32(smem_b + stage * kBBytes);
+          const uint64_t a_desc = a_desc0 + static_cast<uint32_t>(stage) * (kABytes >> 4);
+          const uint64_t b_desc = b_desc0 + static_cast<uint32_t>(stage) * (kBBytes >> 4);
+          if (elect_one_sync()) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)
-            umma_f16_ss_2sm(d_tmem, make_smem_desc_sw128(a_addr + k * 32, 0, 1024),
-                            make_smem_desc_sw128(b_addr + k * 32, 0, 1024), idesc, (kb | k) != 0 ? 1u : 0u);
-          umma_commit_2sm(&empty_bar[stage], 0b11);  // frees this stage in both CTAs
+            for (int k = 0; k < BK / 16; ++k)
+              umma_f16_ss_2sm(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_commit_2sm(&empty_bar[stage], 0b11);  // frees this stage in both CTAs
+          }
+          __syncwarp();
           if (++stage == kStages2) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit_2sm(&tmem_full[acc], 0b11);
+        if (elect_one_sync()) umma_commit_2sm(&tmem_full[acc], 0b11);
+        __syncwarp();
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;

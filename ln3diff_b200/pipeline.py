@@ -76,3 +76,42 @@ def sample_t23d(model, randn: torch.Tensor, c: dict, uc: dict, num_steps: int = 
         ops.sampler_affine_update(xa, tables["coef"][i], net[:B], net[B:], out=xb)
         xa, xb = xb, xa
     return xa
+
+
+@torch.no_grad()
+def decode_and_render(decoder, latents: torch.Tensor, cameras: torch.Tensor, resolution: int = 128,
+                      scaling_divider: float = 0.96806, noise: tuple | None = None):
+    """`TrainLoopDiffusionWithRec.render_video_given_triplane` (nsr/train_util_diffusion.py:176-382)
+    without the host round trips: latents (B,12,32,32) -> tri-planes (decoded ONCE; the reference
+    decodes twice, :204-206 and :268-270) -> every camera of `cameras` (V,25) for every latent in
+    one fused renderer launch.  Per-view global reductions (group_size=1) reproduce the reference's
+    one-view-per-call loop (:292-302).  Returns image_raw (B,V,3,H,W) in [-1,1], image_depth
+    (B,V,1,H,W), image_mask (B,V,1,H,W).  `noise` = (coarse, fine) tensors of shape (B*V, H*W, 64) to
+    override the device RNG (tests)."""
+    if not latents.is_cuda:
+        raise RuntimeError("decode_and_render runs on CUDA only (no CPU fallback)")
+    B, V = latents.shape[0], cameras.shape[0]
+    planes_cl = decoder.decode_to_channels_last(latents, in_mul=scaling_divider)     # (B,3,128,128,32)
+    cams = cameras.to(latents.device, torch.float32).repeat(B, 1).contiguous()       # (B*V, 25)
+    ray_o, ray_d = ops.generate_rays(cams, resolution)
+    M = resolution * resolution
+    if noise is None:
+        noise = (torch.rand(B * V, M, 64, device=latents.device), torch.rand(B * V, M, 64, device=latents.device))
+    kw = decoder.rendering_kwargs
+    out = ops.render_views(planes_cl, ray_o, ray_d, noise[0].contiguous(), noise[1].contiguous(),
+                           decoder.triplane_decoder.decoder.raw_parameters(), views_per_obj=V, group_size=1,
+                           box_warp=kw.get("box_warp", 0.9), bbox_min=kw.get("sampler_bbox_min", -0.45),
+                           bbox_max=kw.get("sampler_bbox_max", 0.45), white_back=kw.get("white_back", True))
+    H = W = resolution
+    w = out["weights"].view(B, V, 1, H, W)
+    return dict(image_raw=out["rgb"].view(B, V, 3, H, W), image_depth=out["depth"].view(B, V, 1, H, W),
+                weights_samples=w, image_mask=w * (1 + 2 * 0.001) - 0.001)
+
+
+@torch.no_grad()
+def generate_t23d(model, decoder, randn, c, uc, cameras, num_steps: int = 250, scale: float = 6.5,
+                  resolution: int = 128):
+    """Text-to-3D end to end on one GPU: sample -> decode -> render (the body of
+    DiffusionEngineLSGM.eval_cldm, nsr/lsgm/sgm_DiffusionEngine.py:410-523, minus conditioner + video sink)."""
+    latents = sample_t23d(model, randn, c, uc, num_steps, scale)
+    return latents, decode_and_render(decoder, latents, cameras, resolution)

@@ -1,0 +1,93 @@
+// The FMHA softmax exponential phase in isolation: per "block" each thread turns 128 fp32 scores (registers)
+// into 128 bf16 probabilities in swizzled smem + a row sum.  W warps per SM, no tensor core, no barriers.
+#include <cstdint>
+#include <cstdio>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+__device__ __forceinline__ float fast_exp2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ float exp2_poly(float x) {
+  x = fmaxf(x, -126.f);
+  float t;
+  asm("add.rm.ftz.f32 %0, %1, %2;" : "=f"(t) : "f"(x), "f"(12582912.f));
+  const float f = x - (t - 12582912.f);
+  float q = fmaf(f, 0.077119089663028717041015625f, 0.227564394474029541015625f);
+  q = fmaf(f, q, 0.695146143436431884765625f);
+  q = fmaf(f, q, 1.f);
+  return __uint_as_float(__float_as_uint(q) + (__float_as_uint(t) << 23));
+}
+
+template <int POLY, int MODE>
+__global__ void __launch_bounds__(320, 1) k(const float* in, float* out, int iters, long long* cyc, float scale) {
+  extern __shared__ uint8_t smem[];
+  const int row = threadIdx.x & 127;
+  const uint32_t p_row = (uint32_t)__cvta_generic_to_shared(smem) + (threadIdx.x >> 7) * 32768 + row * 128;
+  const int swz = row & 7;
+  uint32_t s[128];
+#pragma unroll
+  for (int i = 0; i < 128; ++i) s[i] = __float_as_uint(in[(threadIdx.x * 128 + i) & 4095]);
+  float l_run = 0.f, m_ref = in[threadIdx.x & 255];
+  __syncthreads();
+  long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+    float rs = 0.f;
+    if (MODE == 0) {
+#pragma unroll
+      for (int c = 0; c < 128; c += 8) {
+        float e[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float x = fmaf(__uint_as_float(s[c + i]), scale, -m_ref);
+          e[i] = (i < POLY) ? exp2_poly(x) : fast_exp2(x);
+        }
+        rs += ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));
+        const uint32_t addr = p_row + (c >> 6) * 16384 + ((((c & 63) >> 3) ^ swz) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pack_bf16x2(e[0], e[1])),
+                     "r"(pack_bf16x2(e[2], e[3])), "r"(pack_bf16x2(e[4], e[5])), "r"(pack_bf16x2(e[6], e[7])) : "memory");
+      }
+    }
+    l_run += rs;
+    m_ref += 1e-6f * rs;   // loop-carried dependence so iterations cannot be merged
+#pragma unroll
+    for (int i = 0; i < 128; i += 16) s[i] ^= (it & 1);  // keep s live / varying
+  }
+  long long t1 = clock64();
+  out[blockIdx.x * blockDim.x + threadIdx.x] = l_run;
+  if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+}
+
+template <int POLY>
+void run(int warps, const float* in, float* out, long long* cyc) {
+  const int iters = 200;
+  cudaFuncSetAttribute(k<POLY, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536 * 2);
+  for (int rep = 0; rep < 2; ++rep) {
+    k<POLY, 0><<<148, warps * 32, 65536 * 2>>>(in, out, iters, cyc, 0.18f);
+    cudaDeviceSynchronize();
+  }
+  long long h[148];
+  cudaMemcpy(h, cyc, sizeof(h), cudaMemcpyDeviceToHost);
+  double c = 0;
+  for (int i = 0; i < 148; ++i) c += h[i];
+  printf("poly=%d warps/SM=%d: %.0f cycles per 128-element block per warp\n", POLY, warps, c / 148 / iters);
+}
+
+int main() {
+  float *in, *out;
+  long long* cyc;
+  cudaMalloc(&in, 4096 * 4);
+  cudaMemset(in, 0, 4096 * 4);
+  cudaMalloc(&out, 148 * 1024 * 4);
+  cudaMalloc(&cyc, 148 * 8);
+  for (int warps : {4, 8}) {
+    run<0>(warps, in, out, cyc);
+    run<2>(warps, in, out, cyc);
+    run<3>(warps, in, out, cyc);
+    run<4>(warps, in, out, cyc);
+  }
+  printf("%s\n", cudaGetErrorString(cudaGetLastError()));
+  return 0;
+}
