@@ -359,6 +359,29 @@ def run_ours(args):
         except Exception as e:  # noqa
             vae = {"error": repr(e)}
 
+        # ---- mesh-extraction lattice: 192^3 point queries (triplane_decode_grid) on one object
+        grid = None
+        try:
+            from ln3diff_b200 import ops as _ops
+            gen = torch.Generator(device=dev).manual_seed(5)
+            pl = torch.randn(1, 3, 128, 128, 32, device=dev, generator=gen)
+            osg_w = (torch.randn(64, 32, device=dev, generator=gen), torch.zeros(64, device=dev),
+                     torch.randn(4, 64, device=dev, generator=gen), torch.zeros(4, device=dev))
+            for _ in range(2):
+                _ops.query_points(pl, osg_w, grid_size=192)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                _ops.query_points(pl, osg_w, grid_size=192)
+            e1.record()
+            torch.cuda.synchronize()
+            gms = e0.elapsed_time(e1) / 3
+            grid = {"value": 192 ** 3 / (gms / 1e3) / 1e6, "unit": "Mpoints/s", "ms_per_192cubed_grid": gms,
+                    "what": "tri-plane gather + OSG decoder on the 192^3 mesh-extraction lattice (one launch)"}
+        except Exception as e:  # noqa
+            grid = {"error": repr(e)}
+
         cpu = None
         if n_gpus == 1:
             v, dt, cores = cpu_reference_sample(n_steps_sample=1, prompts=1)
@@ -373,7 +396,7 @@ def run_ours(args):
                         "h2d_bytes_per_step": randn_h.numel() * 4 + ctx_h.numel() * 4,
                         "d2h_bytes_per_step": out_h.numel() * 4},
                 "gpu_launches": int(launches), "clocks": clk, "roofline": roofline,
-                "model_tflops": model_tf, "rendered_views": views, "vae_decode": vae, "cpu_baseline": cpu}
+                "model_tflops": model_tf, "rendered_views": views, "vae_decode": vae, "point_queries": grid, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -270,6 +270,32 @@ typedef struct ln3_render_args {
 size_t ln3_render_workspace_bytes(int V, int M, int group_size);
 int ln3_render_views(const ln3_render_args* args, void* stream);
 
+/* ------------------------------------------------------------------ tri-plane point queries
+ * ImportanceRenderer._run_model (nsr/volumetric_rendering/renderer.py:310-322) as driven by
+ * forward_points / triplane_decode_grid (vit/vit_triplane.py:2009-2120) for mesh extraction:
+ * sample_from_planes (bilinear, zeros padding, box_warp) + OSGDecoder at arbitrary points; no in-box
+ * filter, no compositing.  sigma[n_obj][P] is the raw density logit, rgb[n_obj][P][3] the sigmoid
+ * colour.  points == NULL -> the kernel generates the reference's grid itself (torch.linspace per axis
+ * over [aabb_min, aabb_max], meshgrid 'ij'), P = grid_size^3: no 85 MB coordinate tensor, no
+ * 2^16-point chunking, no empty_cache() between chunks.
+ */
+typedef struct ln3_query_points_args {
+  const float* planes_cl; /* [n_obj][3][H][W][C] channels-last */
+  const float* points;    /* [n_obj][P][3] or NULL (grid mode) */
+  const float* w1;
+  const float* b1;
+  const float* w2;
+  const float* b2;
+  float* sigma;
+  float* rgb;
+  long long P;
+  int n_obj, C, H, W, hidden_dim, decoder_output_dim, grid_size;
+  float aabb_min_x, aabb_min_y, aabb_min_z, aabb_max_x, aabb_max_y, aabb_max_z;
+  double box_warp;
+} ln3_query_points_args;
+
+int ln3_query_points(const ln3_query_points_args* args, void* stream);
+
 /* RaySampler.forward (nsr/volumetric_rendering/ray_sampler.py:180-257): cams fp32 [V, 25]
  * (16 cam2world row-major + 9 intrinsics) -> ray_o, ray_d fp32 [V, res*res, 3], ray m = y*res + x. */
 int ln3_generate_rays(const float* cams, int V, int res, float* ray_o, float* ray_d, void* stream);

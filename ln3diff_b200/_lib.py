@@ -99,6 +99,19 @@ class RenderArgs(C.Structure):
     ]
 
 
+class QueryPointsArgs(C.Structure):
+    _fields_ = [
+        ("planes_cl", C.c_void_p), ("points", C.c_void_p), ("w1", C.c_void_p), ("b1", C.c_void_p),
+        ("w2", C.c_void_p), ("b2", C.c_void_p), ("sigma", C.c_void_p), ("rgb", C.c_void_p),
+        ("P", C.c_longlong),
+        ("n_obj", C.c_int), ("C", C.c_int), ("H", C.c_int), ("W", C.c_int), ("hidden_dim", C.c_int),
+        ("decoder_output_dim", C.c_int), ("grid_size", C.c_int),
+        ("aabb_min_x", C.c_float), ("aabb_min_y", C.c_float), ("aabb_min_z", C.c_float),
+        ("aabb_max_x", C.c_float), ("aabb_max_y", C.c_float), ("aabb_max_z", C.c_float),
+        ("box_warp", C.c_double),
+    ]
+
+
 class ConvArgs(C.Structure):
     _fields_ = [
         ("x", C.c_void_p), ("w", C.c_void_p), ("bias", C.c_void_p), ("in_scale", C.c_void_p),

@@ -138,6 +138,10 @@ int ln3_render_views(const ln3_render_args* args, void* stream) {
   if (!args) return set_error(LN3_EINVAL, "render: null args");
   return render_views(args, static_cast<cudaStream_t>(stream));
 }
+int ln3_query_points(const ln3_query_points_args* args, void* stream) {
+  if (!args) return set_error(LN3_EINVAL, "query_points: null args");
+  return query_points(args, static_cast<cudaStream_t>(stream));
+}
 int ln3_generate_rays(const float* cams, int V, int res, float* ray_o, float* ray_d, void* stream) {
   if (!cams || !ray_o || !ray_d) return set_error(LN3_EINVAL, "generate_rays: null pointer");
   return generate_rays(cams, V, res, ray_o, ray_d, static_cast<cudaStream_t>(stream));

@@ -334,9 +334,12 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         if (row == 0) LN3_TR(t, g, 4);  // O of previous block complete
         if (PINGPONG) named_bar_sync(1 + t, 256);
         if (row == 0) LN3_TR(t, g, 5);  // baton
-        float rs = 0.f;
         // FULL blocks: one straight-line region of 128 exponentials (the scheduler interleaves MUFU,
         // polynomial and st.shared across chunks); ragged last block: stop at c_end.
+        float rs = 0.f;
+        // FULL blocks: one straight-line region of 128 exponentials (the scheduler interleaves MUFU and
+        // st.shared across chunks); ragged last block: stop at c_end.  (Packed FFMA2/FADD2 here measured
+        // slower: the 64-bit register pairs push the 168-register budget into spills.)
         auto exp_store = [&](auto full_tag) {
           constexpr bool FULL = decltype(full_tag)::value;
 #pragma unroll

@@ -30,6 +30,7 @@ int final_layer(const ln3_final_layer_args* a, cudaStream_t stream);
 int sampler_affine_update(const ln3_sampler_update_args* a, cudaStream_t stream);
 size_t render_workspace_bytes(int V, int M, int group_size);
 int render_views(const ln3_render_args* a, cudaStream_t stream);
+int query_points(const ln3_query_points_args* a, cudaStream_t stream);
 int generate_rays(const float* cams, int V, int res, float* ray_o, float* ray_d, cudaStream_t stream);
 int planes_to_channels_last(const float* planes, int n_obj, int C, int H, int W, float* out,
                             cudaStream_t stream);

@@ -109,6 +109,7 @@ struct RenderParams {
   float coord_scale;  // 2 / box_warp (rounded to fp32 like the reference's scalar multiply)
   float bbox_min, bbox_max;
   int white_back;
+  int no_filter;  // 1: raw decoder output for every point (ImportanceRenderer._run_model), no in-box filter
   // optional debug outputs (tests): in-box masks / importance indices / sort permutation
   unsigned char* dbg_inbox;  // [V*M][128]
   int* dbg_inds;             // [V*M][64]
@@ -266,7 +267,7 @@ __device__ __forceinline__ void eval_batch(const RenderParams& p, const BlockSme
     y3 = fmaf(h, bs.w2[3][j], y3);
   }
   __syncwarp();
-  if (inbox) {
+  if (inbox || p.no_filter) {
     sigma = y0;
     cr = 1.f / (1.f + expf(-y1)) * 1.002f - 0.001f;
     cg = 1.f / (1.f + expf(-y2)) * 1.002f - 0.001f;
@@ -572,6 +573,7 @@ int render_views(const ln3_render_args* a, cudaStream_t stream) {
   p.coord_scale = static_cast<float>(2.0 / a->box_warp);
   p.bbox_min = static_cast<float>(a->bbox_min); p.bbox_max = static_cast<float>(a->bbox_max);
   p.white_back = a->white_back;
+  p.no_filter = 0;
   p.dbg_inbox = a->dbg_inbox; p.dbg_inds = a->dbg_inds; p.dbg_order = a->dbg_order;
   p.dbg_zfine = a->dbg_zfine;
 
@@ -591,6 +593,123 @@ int render_views(const ln3_render_args* a, cudaStream_t stream) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(LN3_ECUDA, "render launch: %s", cudaGetErrorString(e));
   count_launch(4);
+  return LN3_OK;
+}
+
+// ------------------------------------------------------------------ point queries (mesh extraction)
+// ImportanceRenderer._run_model (renderer.py:310-322) as called by forward_points /
+// triplane_decode_grid (vit/vit_triplane.py:2009-2120): tri-plane gather + OSG decoder at arbitrary
+// points, no in-box filter, no compositing.  Points come from memory or are generated in the kernel as
+// the reference's grid: torch.linspace per axis (fp32: start + i*step below the midpoint, end - (n-1-i)*step
+// above it), meshgrid 'ij', flattened (i*G + j)*G + k.
+struct QueryParams {
+  const float* points;  // [n_obj][P][3] or null -> grid mode
+  float* sigma;         // [n_obj][P]
+  float* rgb;           // [n_obj][P][3]
+  long long P;
+  int n_obj, grid;
+  float lo[3], hi[3], step[3];
+};
+
+__device__ __forceinline__ float linspace_at(float lo, float hi, float step, int n, int i) {
+  return i < n / 2 ? __fadd_rn(lo, __fmul_rn(step, static_cast<float>(i)))
+                   : __fsub_rn(hi, __fmul_rn(step, static_cast<float>(n - i - 1)));
+}
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 2)
+query_points_kernel(const RenderParams p, const QueryParams q) {
+  extern __shared__ uint8_t smem_raw[];
+  BlockSmem& bs = *reinterpret_cast<BlockSmem*>(smem_raw);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < kHid * kC; i += blockDim.x)
+    (&bs.w1[0][0])[i] = __fmul_rn(p.w1[i], 0.17677669529663687f);
+  for (int i = threadIdx.x; i < 4 * kHid; i += blockDim.x) (&bs.w2[0][0])[i] = __fmul_rn(p.w2[i], 0.125f);
+  if (threadIdx.x < kHid) bs.b1[threadIdx.x] = p.b1[threadIdx.x];
+  if (threadIdx.x < 4) bs.b2[threadIdx.x] = p.b2[threadIdx.x];
+  __syncthreads();
+  WarpSmem& ws = bs.warp[warp];
+  const long long chunks_per_obj = (q.P + 31) / 32;
+  const long long total = chunks_per_obj * q.n_obj;
+  const long long stride = static_cast<long long>(gridDim.x) * kWarpsPerBlock;
+  for (long long ch = static_cast<long long>(blockIdx.x) * kWarpsPerBlock + warp; ch < total; ch += stride) {
+    const int obj = static_cast<int>(ch / chunks_per_obj);
+    const long long i = (ch - obj * chunks_per_obj) * 32 + lane;
+    const bool live = i < q.P;
+    const long long ii = live ? i : q.P - 1;
+    float px, py, pz;
+    if (q.points != nullptr) {
+      const float* pt = q.points + (static_cast<long long>(obj) * q.P + ii) * 3;
+      px = pt[0], py = pt[1], pz = pt[2];
+    } else {
+      const int G = q.grid;
+      const int iz = static_cast<int>(ii % G), iy = static_cast<int>((ii / G) % G), ix = static_cast<int>(ii / (static_cast<long long>(G) * G));
+      px = linspace_at(q.lo[0], q.hi[0], q.step[0], G, ix);
+      py = linspace_at(q.lo[1], q.hi[1], q.step[1], G, iy);
+      pz = linspace_at(q.lo[2], q.hi[2], q.step[2], G, iz);
+    }
+    const float* planes_obj = p.planes + static_cast<long long>(obj) * 3 * p.H * p.W * kC;
+    bool inbox;
+    float sg, cr, cg, cb;
+    eval_batch(p, bs, ws, planes_obj, lane, px, py, pz, inbox, sg, cr, cg, cb);
+    if (live) {
+      const long long o = static_cast<long long>(obj) * q.P + i;
+      q.sigma[o] = sg;
+      q.rgb[o * 3 + 0] = cr;
+      q.rgb[o * 3 + 1] = cg;
+      q.rgb[o * 3 + 2] = cb;
+    }
+  }
+}
+
+int query_points(const ln3_query_points_args* a, cudaStream_t stream) {
+  if (a->n_obj <= 0) return LN3_OK;
+  if (a->C != kC || a->hidden_dim != kHid || a->decoder_output_dim != 3)
+    return set_error(LN3_EUNSUPPORTED, "query_points: needs 32 plane channels and a 32 -> 64 -> 1+3 OSG decoder");
+  if (!a->planes_cl || !a->sigma || !a->rgb || !a->w1 || !a->b1 || !a->w2 || !a->b2)
+    return set_error(LN3_EINVAL, "query_points: null pointer");
+  QueryParams q;
+  q.points = a->points;
+  q.sigma = a->sigma;
+  q.rgb = a->rgb;
+  q.n_obj = a->n_obj;
+  q.grid = a->grid_size;
+  if (a->points == nullptr) {
+    if (a->grid_size < 2 || a->grid_size > 2048) return set_error(LN3_EINVAL, "query_points: grid_size must be in [2, 2048]");
+    q.P = static_cast<long long>(a->grid_size) * a->grid_size * a->grid_size;
+    const float lo[3] = {a->aabb_min_x, a->aabb_min_y, a->aabb_min_z};
+    const float hi[3] = {a->aabb_max_x, a->aabb_max_y, a->aabb_max_z};
+    for (int d = 0; d < 3; ++d) {
+      q.lo[d] = lo[d];
+      q.hi[d] = hi[d];
+      q.step[d] = (hi[d] - lo[d]) / static_cast<float>(a->grid_size - 1);  // torch.linspace, fp32
+    }
+  } else {
+    if (a->P <= 0) return LN3_OK;
+    q.P = a->P;
+    for (int d = 0; d < 3; ++d) q.lo[d] = q.hi[d] = q.step[d] = 0.f;
+  }
+  RenderParams p = {};
+  p.planes = a->planes_cl;
+  p.w1 = a->w1; p.b1 = a->b1; p.w2 = a->w2; p.b2 = a->b2;
+  p.H = a->H; p.W = a->W;
+  p.coord_scale = static_cast<float>(2.0 / a->box_warp);
+  p.bbox_min = 0.f; p.bbox_max = 0.f;
+  p.no_filter = 1;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(query_points_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(sizeof(BlockSmem)));
+    if (e != cudaSuccess) return set_error(LN3_ECUDA, "query_points: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const long long chunks = ((q.P + 31) / 32) * q.n_obj;
+  long long blocks = (chunks + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  const int sms = device_sm_count();
+  if (blocks > 2LL * sms) blocks = 2LL * sms;
+  query_points_kernel<<<static_cast<unsigned>(blocks), kWarpsPerBlock * 32, sizeof(BlockSmem), stream>>>(p, q);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(LN3_ECUDA, "query_points launch: %s", cudaGetErrorString(e));
+  count_launch();
   return LN3_OK;
 }
 

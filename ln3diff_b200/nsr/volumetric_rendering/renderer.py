@@ -69,3 +69,25 @@ class ImportanceRenderer(torch.nn.Module):
         if return_meta:
             ret.update({"all_coords": None, "feature_volume": None, "weights": None})
         return ret
+
+    @torch.no_grad()
+    def _run_model(self, planes, decoder, sample_coordinates, sample_directions, options):
+        """Point queries (reference renderer.py:310-322): tri-plane gather + OSG decoder at
+        `sample_coordinates` (N, P, 3); `sample_directions` is unused by OSGDecoder (nsr/triplane.py:356).
+        `planes` is (N, 3, C, H, W) / (N, 3*C, H, W) NCHW, or (N, 3, H, W, C) channels-last when it comes
+        from `decode_to_channels_last`.  Returns {'rgb': (N,P,3), 'sigma': (N,P,1)} with no in-box filter."""
+        if not planes.is_cuda:
+            raise RuntimeError("ln3diff_b200 ImportanceRenderer runs on CUDA only (no CPU fallback)")
+        if options.get("density_noise", 0) > 0:
+            raise NotImplementedError("density_noise is a training-time option")
+        sigma, rgb = ops.query_points(self._as_channels_last(planes), decoder.raw_parameters(),
+                                      points=sample_coordinates.float().contiguous(), box_warp=options["box_warp"])
+        return {"rgb": rgb, "sigma": sigma}
+
+    def _as_channels_last(self, planes):
+        if planes.dim() == 5 and planes.shape[-1] == 32 and planes.shape[2] != 32:
+            return planes.contiguous()                      # already (N,3,H,W,32)
+        if planes.dim() == 4:
+            planes = planes.reshape(planes.shape[0], 3, -1, planes.shape[-2], planes.shape[-1])
+        return self._planes_cl(planes)
+

@@ -358,6 +358,42 @@ def render_views(planes_cl: torch.Tensor, ray_o: torch.Tensor, ray_d: torch.Tens
     return out
 
 
+def query_points(planes_cl: torch.Tensor, osg: tuple, *, points: torch.Tensor | None = None,
+                 grid_size: int = 0, aabb_min=(-0.45,) * 3, aabb_max=(0.45,) * 3, box_warp: float = 0.9):
+    """ImportanceRenderer._run_model at arbitrary points: planes_cl (N,3,H,W,32) channels-last,
+    points (N,P,3) fp32 or None for the reference's linspace grid of grid_size^3 points over the aabb.
+    Returns sigma (N,P,1) (raw density logit) and rgb (N,P,3)."""
+    _cuda(planes_cl, "planes_cl", torch.float32)
+    _req(planes_cl.dim() == 5 and planes_cl.shape[1] == 3 and planes_cl.shape[4] == 32 and planes_cl.is_contiguous(),
+         "planes_cl must be contiguous (N,3,H,W,32)")
+    N = planes_cl.shape[0]
+    a = _lib.QueryPointsArgs()
+    if points is not None:
+        _cuda(points, "points", torch.float32)
+        _req(points.dim() == 3 and points.shape[0] == N and points.shape[2] == 3 and points.is_contiguous(),
+             "points must be contiguous (N,P,3)")
+        P = points.shape[1]
+        a.points = points.data_ptr()
+    else:
+        _req(grid_size >= 2, "need points or grid_size >= 2")
+        P = grid_size ** 3
+        a.grid_size = grid_size
+        a.aabb_min_x, a.aabb_min_y, a.aabb_min_z = (float(v) for v in aabb_min)
+        a.aabb_max_x, a.aabb_max_y, a.aabb_max_z = (float(v) for v in aabb_max)
+    w1, b1, w2, b2 = osg
+    for nm, t_, shp in (("w1", w1, (64, 32)), ("b1", b1, (64,)), ("w2", w2, (4, 64)), ("b2", b2, (4,))):
+        _cuda(t_, nm, torch.float32)
+        _req(tuple(t_.shape) == shp and t_.is_contiguous(), f"{nm} must be contiguous {shp}")
+    sigma = torch.empty((N, P, 1), device=planes_cl.device, dtype=torch.float32)
+    rgb = torch.empty((N, P, 3), device=planes_cl.device, dtype=torch.float32)
+    a.planes_cl, a.sigma, a.rgb, a.P = planes_cl.data_ptr(), sigma.data_ptr(), rgb.data_ptr(), P
+    a.w1, a.b1, a.w2, a.b2 = w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr()
+    a.n_obj, a.C, a.H, a.W = N, 32, planes_cl.shape[2], planes_cl.shape[3]
+    a.hidden_dim, a.decoder_output_dim, a.box_warp = 64, 3, box_warp
+    _lib.check(_lib.lib().ln3_query_points(C.byref(a), _lib.current_stream()), "ln3_query_points")
+    return sigma, rgb
+
+
 def conv_nhwc(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor | None, *, ksize: int,
               upsample: bool = False, gn: tuple | None = None, swish: bool = False,
               residual: torch.Tensor | None = None, out: torch.Tensor | None = None) -> torch.Tensor:

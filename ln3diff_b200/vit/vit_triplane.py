@@ -192,3 +192,48 @@ class RodinSR_256_fusionv6_ConvQuant_liteSR_dinoInit3DAttn_SD_B_3L_C_withrollout
         ret = self.triplane_decoder(latent_after_vit, c, return_raw_only=return_raw_only, **kwargs)
         ret.update({"latent_after_vit": latent_after_vit, **vit_decode_out})
         return ret
+
+    # ------------------------------------------------------------------ mesh-extraction queries
+    @torch.no_grad()
+    def forward_points(self, planes, points: torch.Tensor, chunk_size: int = 2 ** 16):
+        """reference vit_triplane.py:2009-2050.  One launch for all points: `chunk_size` (the reference's
+        guard against its own (N,P,3,32) feature temporaries + empty_cache() per chunk) is accepted and
+        ignored.  Returns {'rgb': (N,P,3), 'sigma': (N,P,1)}."""
+        return self.triplane_decoder.renderer._run_model(
+            planes=planes, decoder=self.triplane_decoder.decoder, sample_coordinates=points,
+            sample_directions=None, options=self.rendering_kwargs)
+
+    @torch.no_grad()
+    def triplane_decode_grid(self, vit_decode_out, grid_size, aabb: torch.Tensor = None, **kwargs):
+        """reference vit_triplane.py:2052-2120: density / colour on a grid_size^3 lattice over the sampler
+        bbox (or `aabb` (N,2,3)).  The lattice is generated inside the kernel with torch.linspace's
+        arithmetic; no coordinate tensor exists.  Returns {'rgb': (N,G,G,G,3), 'sigma': (N,G,G,G,1)}."""
+        assert isinstance(vit_decode_out, dict)
+        planes = vit_decode_out["latent_after_vit"]
+        kw = self.rendering_kwargs
+        ren = self.triplane_decoder.renderer
+        planes_cl = ren._as_channels_last(planes)
+        N = planes_cl.shape[0]
+        if aabb is None:
+            if "sampler_bbox_min" in kw:
+                lo, hi = [kw["sampler_bbox_min"]] * 3, [kw["sampler_bbox_max"]] * 3
+            else:
+                lo, hi = [-kw["box_warp"] / 2] * 3, [kw["box_warp"] / 2] * 3
+            boxes = [(lo, hi)] * N
+            uniform = True
+        else:
+            assert planes_cl.shape[0] == aabb.shape[0], "Batch size mismatch for planes and aabb"
+            ab = aabb.detach().float().cpu()
+            boxes = [(ab[i, 0].tolist(), ab[i, 1].tolist()) for i in range(N)]
+            uniform = all(b == boxes[0] for b in boxes)
+        osg = self.triplane_decoder.decoder.raw_parameters()
+        if uniform:
+            sigma, rgb = ops.query_points(planes_cl, osg, grid_size=grid_size, aabb_min=boxes[0][0],
+                                          aabb_max=boxes[0][1], box_warp=kw["box_warp"])
+        else:
+            parts = [ops.query_points(planes_cl[i:i + 1], osg, grid_size=grid_size, aabb_min=boxes[i][0],
+                                      aabb_max=boxes[i][1], box_warp=kw["box_warp"]) for i in range(N)]
+            sigma, rgb = torch.cat([p_[0] for p_ in parts]), torch.cat([p_[1] for p_ in parts])
+        G = grid_size
+        return {"rgb": rgb.reshape(N, G, G, G, -1), "sigma": sigma.reshape(N, G, G, G, -1)}
+

@@ -129,6 +129,21 @@ def run_model(planes, osg, coords, opts):
     return rgb, sigma, inbox
 
 
+def run_model_points(planes, osg, coords, box_warp: float):
+    """ImportanceRenderer._run_model (renderer.py:310-322): planes (3,C,H,W); coords (P,3) ->
+    rgb (P,3), sigma (P,1).  No in-box filter (that lives in _forward_pass, not here)."""
+    rgb, sigma, _ = run_model(planes, osg, coords, {"box_warp": box_warp, "sampler_bbox_min": 0.0,
+                                                    "sampler_bbox_max": 0.0, "filter_out_of_bbox": False})
+    return rgb, sigma
+
+
+def grid_points(aabb_min, aabb_max, grid_size: int) -> torch.Tensor:
+    """The lattice of triplane_decode_grid (vit/vit_triplane.py:2092-2108): per-axis torch.linspace,
+    meshgrid 'ij', stacked and flattened -> (G^3, 3)."""
+    axes = [torch.linspace(float(aabb_min[d]), float(aabb_max[d]), grid_size) for d in range(3)]
+    return torch.stack(torch.meshgrid(*axes, indexing="ij"), dim=-1).reshape(-1, 3)
+
+
 def ray_march(colors, densities, depths, white_back=True, dmin=None, dmax=None):
     """MipRayMarcher2.run_forward on (R,S,3), (R,S,1), (R,S,1)."""
     deltas = depths[:, 1:] - depths[:, :-1]

@@ -485,3 +485,56 @@ def test_decode_and_render_pipeline_vs_oracle(dev, golden):
         ref = orender.render_view(planes_ref, osg, cams[v], res, orender.OBJAVERSE_OPTS, nc[v], nf[v])
         assert _rel(out["image_raw"][0, v], ref["image_raw"]) < 3e-2       # bf16 DiT2 features upstream
         assert _rel(out["image_mask"][0, v], ref["image_mask"]) < 3e-2
+
+
+def test_query_points_vs_reference_golden(dev, golden):
+    """ln3_query_points (explicit points and in-kernel lattice) vs the reference's _run_model outputs, and
+    the mirror's forward_points / triplane_decode_grid entry points."""
+    from ln3diff_b200 import ops
+    from oracle import fixtures as fx
+    from oracle import render as orender
+    g = golden("points.npz")
+    planes, osg, _, _ = fx.render_inputs(8)
+    cl = ops.planes_to_channels_last(planes[None].to(dev).contiguous())
+    osg_d = tuple(t.to(dev).contiguous() for t in osg)
+    sigma, rgb = ops.query_points(cl, osg_d, points=torch.from_numpy(g["points"])[None].to(dev).contiguous())
+    assert _rel(sigma[0], g["sigma"]) < 1e-5 and _rel(rgb[0], g["rgb"]) < 1e-5
+    G = int(g["grid_size"])
+    sigma, rgb = ops.query_points(cl, osg_d, grid_size=G)
+    assert _rel(sigma[0], g["grid_sigma"]) < 1e-5 and _rel(rgb[0], g["grid_rgb"]) < 1e-5
+    # two objects, a lattice that is not a multiple of the warp size, non-default aabb: against the oracle
+    planes2 = torch.stack([planes, planes.flip(0) * 0.5])
+    cl2 = ops.planes_to_channels_last(planes2.to(dev).contiguous())
+    lo, hi = (-0.3, -0.45, -0.2), (0.45, 0.1, 0.4)
+    sigma, rgb = ops.query_points(cl2, osg_d, grid_size=7, aabb_min=lo, aabb_max=hi)
+    pts = orender.grid_points(lo, hi, 7)
+    for i in range(2):
+        r_rgb, r_sigma = orender.run_model_points(planes2[i], osg, pts, 0.9)
+        assert _rel(sigma[i], r_sigma) < 1e-5 and _rel(rgb[i], r_rgb) < 1e-5
+    # full-size property: the 192^3 mesh-extraction lattice of one 128x128 object runs and is finite
+    big = ops.planes_to_channels_last((torch.randn(1, 3, 32, 128, 128) * 2).to(dev))
+    sigma, rgb = ops.query_points(big, osg_d, grid_size=192)
+    assert sigma.shape == (1, 192 ** 3, 1) and torch.isfinite(sigma).all() and torch.isfinite(rgb).all()
+    assert float(rgb.min()) >= -0.001 - 1e-6 and float(rgb.max()) <= 1.001 + 1e-6
+
+
+def test_decoder_grid_entry_points(dev, golden):
+    """RodinSR...ditDecoder.triplane_decode_grid / forward_points (vit_triplane.py:2009-2120 mirrors)."""
+    from ln3diff_b200.utils import build_ae_decoder
+    from oracle import fixtures as fx
+    from oracle import render as orender
+    m = build_ae_decoder(fx.DECODER_ARCH, image_size=32).to(dev)
+    planes = torch.randn(2, 96, 16, 16, generator=torch.Generator().manual_seed(3)) * 3
+    out = m.triplane_decode_grid({"latent_after_vit": planes.to(dev)}, 6)
+    assert out["sigma"].shape == (2, 6, 6, 6, 1) and out["rgb"].shape == (2, 6, 6, 6, 3)
+    osg = tuple(t.cpu() for t in m.triplane_decoder.decoder.raw_parameters())
+    pts = orender.grid_points([-0.45] * 3, [0.45] * 3, 6)
+    for i in range(2):
+        r_rgb, r_sigma = orender.run_model_points(planes[i].reshape(3, 32, 16, 16), osg, pts, 0.9)
+        assert _rel(out["sigma"][i].reshape(-1, 1), r_sigma) < 1e-5 and _rel(out["rgb"][i].reshape(-1, 3), r_rgb) < 1e-5
+    fp = m.forward_points(planes.to(dev), pts[None].repeat(2, 1, 1).to(dev))
+    assert _rel(fp["sigma"], out["sigma"].reshape(2, -1, 1)) < 1e-6
+    aabb = torch.tensor([[[-0.45] * 3, [0.45] * 3], [[-0.2] * 3, [0.3] * 3]])
+    out2 = m.triplane_decode_grid({"latent_after_vit": planes.to(dev)}, 5, aabb=aabb)
+    r_rgb, r_sigma = orender.run_model_points(planes[1].reshape(3, 32, 16, 16), osg, orender.grid_points([-0.2] * 3, [0.3] * 3, 5), 0.9)
+    assert _rel(out2["sigma"][1].reshape(-1, 1), r_sigma) < 1e-5

@@ -21,6 +21,30 @@ __device__ __forceinline__ float exp2_poly(float x) {
   return __uint_as_float(__float_as_uint(q) + (__float_as_uint(t) << 23));
 }
 
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) { uint64_t d; asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi)); return d; }
+__device__ __forceinline__ void upk2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) { uint64_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) { uint64_t d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ uint64_t add2_rm(uint64_t a, uint64_t b) { uint64_t d; asm("add.rm.ftz.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+// two exponentials on the FMA pipe (see exp2_poly), packed arithmetic
+__device__ __forceinline__ void exp2_poly2(uint64_t x2, float& e0, float& e1) {
+  float x0, x1;
+  upk2(x2, x0, x1);
+  x2 = pk2(fmaxf(x0, -126.f), fmaxf(x1, -126.f));
+  const uint64_t magic = pk2(12582912.f, 12582912.f), nmagic = pk2(-12582912.f, -12582912.f);
+  const uint64_t t2 = add2_rm(x2, magic);
+  const uint64_t f2 = fma2(add2(t2, nmagic), pk2(-1.f, -1.f), x2);
+  uint64_t q2 = fma2(f2, pk2(0.077119089663028717041015625f, 0.077119089663028717041015625f),
+                     pk2(0.227564394474029541015625f, 0.227564394474029541015625f));
+  q2 = fma2(f2, q2, pk2(0.695146143436431884765625f, 0.695146143436431884765625f));
+  q2 = fma2(f2, q2, pk2(1.f, 1.f));
+  float q0, q1, t0, t1;
+  upk2(q2, q0, q1);
+  upk2(t2, t0, t1);
+  e0 = __uint_as_float(__float_as_uint(q0) + (__float_as_uint(t0) << 23));
+  e1 = __uint_as_float(__float_as_uint(q1) + (__float_as_uint(t1) << 23));
+}
+
 template <int POLY, int MODE>
 __global__ void __launch_bounds__(320, 1) k(const float* in, float* out, int iters, long long* cyc, float scale) {
   extern __shared__ uint8_t smem[];
@@ -50,6 +74,33 @@ __global__ void __launch_bounds__(320, 1) k(const float* in, float* out, int ite
                      "r"(pack_bf16x2(e[2], e[3])), "r"(pack_bf16x2(e[4], e[5])), "r"(pack_bf16x2(e[6], e[7])) : "memory");
       }
     }
+    if (MODE == 1) {
+      const uint64_t sc2 = pk2(scale, scale), nm2 = pk2(-m_ref, -m_ref);
+      uint64_t rs2 = pk2(0.f, 0.f);
+#pragma unroll
+      for (int c = 0; c < 128; c += 8) {
+        float e[8];
+#pragma unroll
+        for (int i = 0; i < 8; i += 2) {
+          const uint64_t x2 = fma2(pk2(__uint_as_float(s[c + i]), __uint_as_float(s[c + i + 1])), sc2, nm2);
+          if (i < POLY) {
+            exp2_poly2(x2, e[i], e[i + 1]);
+          } else {
+            float x0, x1;
+            upk2(x2, x0, x1);
+            e[i] = fast_exp2(x0);
+            e[i + 1] = fast_exp2(x1);
+          }
+        }
+        rs2 = add2(rs2, add2(add2(pk2(e[0], e[1]), pk2(e[2], e[3])), add2(pk2(e[4], e[5]), pk2(e[6], e[7]))));
+        const uint32_t addr = p_row + (c >> 6) * 16384 + ((((c & 63) >> 3) ^ swz) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pack_bf16x2(e[0], e[1])),
+                     "r"(pack_bf16x2(e[2], e[3])), "r"(pack_bf16x2(e[4], e[5])), "r"(pack_bf16x2(e[6], e[7])) : "memory");
+      }
+      float r0, r1;
+      upk2(rs2, r0, r1);
+      rs = r0 + r1;
+    }
     l_run += rs;
     m_ref += 1e-6f * rs;   // loop-carried dependence so iterations cannot be merged
 #pragma unroll
@@ -60,19 +111,19 @@ __global__ void __launch_bounds__(320, 1) k(const float* in, float* out, int ite
   if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
 }
 
-template <int POLY>
+template <int POLY, int MODE>
 void run(int warps, const float* in, float* out, long long* cyc) {
   const int iters = 200;
-  cudaFuncSetAttribute(k<POLY, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536 * 2);
+  cudaFuncSetAttribute(k<POLY, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536 * 2);
   for (int rep = 0; rep < 2; ++rep) {
-    k<POLY, 0><<<148, warps * 32, 65536 * 2>>>(in, out, iters, cyc, 0.18f);
+    k<POLY, MODE><<<148, warps * 32, 65536 * 2>>>(in, out, iters, cyc, 0.18f);
     cudaDeviceSynchronize();
   }
   long long h[148];
   cudaMemcpy(h, cyc, sizeof(h), cudaMemcpyDeviceToHost);
   double c = 0;
   for (int i = 0; i < 148; ++i) c += h[i];
-  printf("poly=%d warps/SM=%d: %.0f cycles per 128-element block per warp\n", POLY, warps, c / 148 / iters);
+  printf("mode=%d poly=%d warps/SM=%d: %.0f cycles per 128-element block per warp\n", MODE, POLY, warps, c / 148 / iters);
 }
 
 int main() {
@@ -83,10 +134,11 @@ int main() {
   cudaMalloc(&out, 148 * 1024 * 4);
   cudaMalloc(&cyc, 148 * 8);
   for (int warps : {4, 8}) {
-    run<0>(warps, in, out, cyc);
-    run<2>(warps, in, out, cyc);
-    run<3>(warps, in, out, cyc);
-    run<4>(warps, in, out, cyc);
+    run<0, 0>(warps, in, out, cyc);
+    run<0, 1>(warps, in, out, cyc);
+    run<2, 1>(warps, in, out, cyc);
+    run<4, 1>(warps, in, out, cyc);
+    run<6, 1>(warps, in, out, cyc);
   }
   printf("%s\n", cudaGetErrorString(cudaGetLastError()));
   return 0;
