@@ -294,7 +294,7 @@ def run_ours(args):
         gemm_ms = sum(t for _, t in big)
         gemm_fl = sum(f for f, _ in big)
         achieved = gemm_fl / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
-        roofline = {"kernel": "ln3::gemm_bf16_kernel<256> (tcgen05 128x256x64, fused epilogues)",
+        roofline = {"kernel": "ln3::gemm2_bf16_kernel (tcgen05 cta_group::2, 256x256x64 per CTA pair, fused epilogues)",
                     "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                     "frac": achieved / peak_tf, "peak_source": peak_src,
                     "traffic": 54.65e6,  # dram read+write of the captured qkv launch (profiles/r1_ncu_gemm_pair_v0.txt)

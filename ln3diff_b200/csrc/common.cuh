@@ -248,6 +248,12 @@ __device__ __forceinline__ uint32_t mapa_u32(const void* smem_ptr, uint32_t rank
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// Same without the release fence.  .release.cluster compiles to MEMBAR.ALL.GPU + ERRBAR, i.e. it waits for
+// every global store the warp has in flight (an epilogue's whole output) -- 9 % of the GEMM's stall
+// samples.  Use it where only tcgen05 traffic must be ordered (tcgen05.fence::before_thread_sync does that).
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 // TMA load of one CTA of a pair; completion bytes are credited to the barrier at `mbar_cluster_addr`
 // (the leader CTA's full barrier).
 __device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* m, uint32_t mbar_cluster_addr,

@@ -380,7 +380,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
 // runtime switch compiled to an indirect branch + constant loads that stalled the warp ~15 %).
 template <int ACT, int OUT, bool HN>
 __device__ __forceinline__ void epilogue_cols(const GemmParams& p, uint32_t t_row, int m, int n_tile0,
-                                              int c_begin, int c_end) {
+                                              int c_begin, int c_end, const float* bias_s) {
   constexpr int CW = HN ? 64 : 32;
   const bool row_ok = m < p.M;
   uint32_t v[CW], vn[CW];
@@ -398,10 +398,10 @@ __device__ __forceinline__ void epilogue_cols(const GemmParams& p, uint32_t t_ro
     float f[CW];
 #pragma unroll
     for (int i = 0; i < CW; ++i) f[i] = __uint_as_float(v[i]);
-    if (p.bias != nullptr) {
-#pragma unroll
+    if (p.bias != nullptr) {  // this tile's bias, staged in smem by the caller (a global load here stalls
+#pragma unroll             // the chunk for an L2 round trip: 10 % of the kernel's stall samples)
       for (int i = 0; i < CW; i += 4) {
-        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + i));
+        const float4 b = *reinterpret_cast<const float4*>(bias_s + c + i);
         f[i] += b.x; f[i + 1] += b.y; f[i + 2] += b.z; f[i + 3] += b.w;
       }
     }
@@ -511,7 +511,7 @@ __device__ __forceinline__ void epilogue_cols(const GemmParams& p, uint32_t t_ro
 //   tmem_empty : epilogue warps of both CTAs arrive on the leader's barrier (remote mbarrier arrive)
 static constexpr int kStages2 = 6;
 static constexpr int kStageBytes2 = (BM * BK + 128 * BK) * 2;  // A 128x64 + W half 128x64 = 32 KB
-static constexpr int kSmemBytes2 = kStages2 * kStageBytes2 + 1024 + 256;
+static constexpr int kSmemBytes2 = kStages2 * kStageBytes2 + 1024 + 256 + 2 * 256 * 4;  // + bias[2][256]
 static constexpr int kGemmThreads2 = 320;  // TMA warp, MMA warp, 8 epilogue warps (2 per TMEM lane quarter)
 
 template <int ACT, int OUT, bool HN>
@@ -531,6 +531,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   uint64_t* tmem_full = bars + 2 * kStages2;  // [2]         one per CTA, fed by multicast commits
   uint64_t* tmem_empty = tmem_full + 2;       // [2]         leader's copy: 16 arrivals (8 warps x 2 CTAs)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* bias_s = reinterpret_cast<float*>(smem + kStages2 * kStageBytes2 + 256);  // [2 acc stages][BN]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -641,14 +642,18 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     for (int t = pair; t < num_tiles; t += num_pairs) {
       int tm, tn;
       tile_coords(t, tm, tn);
+      // stage the tile's 256 bias values (one per epilogue thread) while the mainloop is still running;
+      // two buffers + one barrier per tile: nobody can be two tiles ahead of the slowest warp
+      if (p.bias != nullptr) bias_s[acc * BN + (threadIdx.x - 64)] = __ldg(p.bias + tn * BN + (threadIdx.x - 64));
+      named_bar_sync(1, 256);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const int m = tm * 2 * BM + static_cast<int>(rank) * BM + quarter * 32 + lane;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
-      epilogue_cols<ACT, OUT, HN>(p, t_row, m, tn * BN, half * (BN / 2), (half + 1) * (BN / 2));
+      epilogue_cols<ACT, OUT, HN>(p, t_row, m, tn * BN, half * (BN / 2), (half + 1) * (BN / 2), bias_s + acc * BN);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(mapa_u32(&tmem_empty[acc], 0));
+      if (lane == 0) mbar_arrive_cluster_relaxed(mapa_u32(&tmem_empty[acc], 0));
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1;
