@@ -320,19 +320,25 @@ def run_ours(args):
             nf = torch.rand(n_obj * V, M, 64, device=dev)
             pcl = ops.planes_to_channels_last(planes)
             o, d = ops.generate_rays(cams, res)
-            for _ in range(2):
-                ops.render_views(pcl, o, d, nc, nf, osg, views_per_obj=V)
-            torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(3):
-                ops.render_views(pcl, o, d, nc, nf, osg, views_per_obj=V)
-            e1.record()
-            torch.cuda.synchronize()
-            rms = e0.elapsed_time(e1) / 3
+
+            def time_render(tf32):
+                for _ in range(2):
+                    ops.render_views(pcl, o, d, nc, nf, osg, views_per_obj=V, mlp_tf32=tf32)
+                torch.cuda.synchronize()
+                e0.record()
+                for _ in range(3):
+                    ops.render_views(pcl, o, d, nc, nf, osg, views_per_obj=V, mlp_tf32=tf32)
+                e1.record()
+                torch.cuda.synchronize()
+                return e0.elapsed_time(e1) / 3
+
+            rms, rms32 = time_render(True), time_render(False)
             views = {"value": n_obj * V / (rms / 1e3), "unit": "views/s", "res": res, "views": n_obj * V,
                      "samples_per_ray": "64+64", "ms": rms,
-                     "fp32_tflops": 0.70e6 * M * n_obj * V / (rms / 1e3) / 1e12,
+                     "mlp": "TF32 tensor-core OSG MLP (product default; pixels within 1e-4 rel-L2 of fp32)",
+                     "exact_fp32_mlp_views_per_s": n_obj * V / (rms32 / 1e3),
+                     "flops_per_s_T": 0.70e6 * M * n_obj * V / (rms / 1e3) / 1e12,
                      "data": "synthetic planes 5*randn, explicit noise (SURVEY.md 8d config 3 render-only)"}
         except Exception as e:  # noqa
             views = {"error": repr(e)}
@@ -355,6 +361,23 @@ def run_ours(args):
             dms = e0.elapsed_time(e1) / 3
             vae = {"value": B / (dms / 1e3), "unit": "latents/s", "batch": B, "ms": dms,
                    "what": "latent (12,32,32) -> tri-plane (3,128,128,32): PatchEmbedTriplane + DiT2-L/2 + SD conv decoder"}
+            # BASELINE configs[2]: 64 denoised latents -> decode -> 16 views each at 128x128, through the
+            # public pipeline call (device RNG for the sampler noise), 8 latents per call
+            from ln3diff_b200 import pipeline as _pl
+            from ln3diff_b200.utils import orbit_cameras as _oc
+            cams16 = _oc(16).to(dev)
+            lat64 = torch.randn(64, 12, 32, 32, device=dev)
+            _pl.decode_and_render(dec, lat64[:8], cams16, 128)
+            torch.cuda.synchronize()
+            e0.record()
+            for i0 in range(0, 64, 8):
+                _pl.decode_and_render(dec, lat64[i0:i0 + 8], cams16, 128)
+            e1.record()
+            torch.cuda.synchronize()
+            c2ms = e0.elapsed_time(e1)
+            vae["configs2_decode_render"] = {"value": 64 * 16 / (c2ms / 1e3), "unit": "views/s", "latents": 64,
+                                             "views_per_latent": 16, "res": 128, "ms": c2ms,
+                                             "what": "VAE decode + fused ray march, 64 latents x 16 views (BASELINE configs[2])"}
             del dec
         except Exception as e:  # noqa
             vae = {"error": repr(e)}

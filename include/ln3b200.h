@@ -122,6 +122,9 @@ int ln3_fmha_fwd(const ln3_fmha_args* args, void* stream);
  */
 enum { LN3_NORM_NONE = 0, LN3_NORM_LAYER = 1, LN3_NORM_RMS = 2 };
 
+/* OSG decoder arithmetic of the renderer / point queries */
+enum { LN3_MLP_FP32 = 0, LN3_MLP_TF32 = 1 };
+
 typedef struct ln3_norm_modulate_args {
   const float* x;     /* [rows, ldx]; updated in place when `resid` is given */
   void* out;          /* bf16 [rows, ldo] (NULL allowed with `resid`) */
@@ -264,6 +267,7 @@ typedef struct ln3_render_args {
   float* dbg_zfine;
   int V, M, H, W, C, S, S_importance, hidden_dim, decoder_output_dim;
   int group_size, views_per_obj, white_back;
+  int mlp_precision; /* LN3_MLP_FP32 (exact, SIMT) or LN3_MLP_TF32 (mma.sync tensor cores, fp32 accumulate) */
   double box_warp, bbox_min, bbox_max;
 } ln3_render_args;
 
@@ -290,6 +294,7 @@ typedef struct ln3_query_points_args {
   float* rgb;
   long long P;
   int n_obj, C, H, W, hidden_dim, decoder_output_dim, grid_size;
+  int mlp_precision; /* LN3_MLP_FP32 or LN3_MLP_TF32 */
   float aabb_min_x, aabb_min_y, aabb_min_z, aabb_max_x, aabb_max_y, aabb_max_z;
   double box_warp;
 } ln3_query_points_args;

@@ -95,6 +95,7 @@ class RenderArgs(C.Structure):
         ("S", C.c_int), ("S_importance", C.c_int), ("hidden_dim", C.c_int),
         ("decoder_output_dim", C.c_int),
         ("group_size", C.c_int), ("views_per_obj", C.c_int), ("white_back", C.c_int),
+        ("mlp_precision", C.c_int),
         ("box_warp", C.c_double), ("bbox_min", C.c_double), ("bbox_max", C.c_double),
     ]
 
@@ -105,7 +106,7 @@ class QueryPointsArgs(C.Structure):
         ("w2", C.c_void_p), ("b2", C.c_void_p), ("sigma", C.c_void_p), ("rgb", C.c_void_p),
         ("P", C.c_longlong),
         ("n_obj", C.c_int), ("C", C.c_int), ("H", C.c_int), ("W", C.c_int), ("hidden_dim", C.c_int),
-        ("decoder_output_dim", C.c_int), ("grid_size", C.c_int),
+        ("decoder_output_dim", C.c_int), ("grid_size", C.c_int), ("mlp_precision", C.c_int),
         ("aabb_min_x", C.c_float), ("aabb_min_y", C.c_float), ("aabb_min_z", C.c_float),
         ("aabb_max_x", C.c_float), ("aabb_max_y", C.c_float), ("aabb_max_z", C.c_float),
         ("box_warp", C.c_double),
@@ -122,6 +123,7 @@ class ConvArgs(C.Structure):
 
 
 NORM_NONE, NORM_LAYER, NORM_RMS = 0, 1, 2
+MLP_FP32, MLP_TF32 = 0, 1
 
 
 def lib() -> C.CDLL:

@@ -382,17 +382,29 @@ template <int ACT, int OUT, bool HN>
 __device__ __forceinline__ void epilogue_cols(const GemmParams& p, uint32_t t_row, int m, int n_tile0,
                                               int c_begin, int c_end, const float* bias_s) {
   constexpr int CW = HN ? 64 : 32;
+  // Plain epilogues software-pipeline the TMEM loads (chunk c+1 in flight while c is stored).  The
+  // activation epilogues run with 16 warps and a 96-register budget instead: no prefetch registers,
+  // the other three warps of the scheduler cover the tcgen05.ld latency.
+  constexpr bool PREFETCH = ACT == LN3_ACT_NONE;
   const bool row_ok = m < p.M;
-  uint32_t v[CW], vn[CW];
-  tmem_ld_32x32(t_row + c_begin, v);
-  if constexpr (HN) tmem_ld_32x32(t_row + c_begin + 32, v + 32);
-  tmem_ld_wait();
+  uint32_t v[CW], vn[PREFETCH ? CW : 1];
+  if constexpr (PREFETCH) {
+    tmem_ld_32x32(t_row + c_begin, v);
+    if constexpr (HN) tmem_ld_32x32(t_row + c_begin + 32, v + 32);
+    tmem_ld_wait();
+  }
 #pragma unroll 1
   for (int c = c_begin; c < c_end; c += CW) {
     const bool more = c + CW < c_end;
-    if (more) {
-      tmem_ld_32x32(t_row + c + CW, vn);
-      if constexpr (HN) tmem_ld_32x32(t_row + c + CW + 32, vn + 32);
+    if constexpr (PREFETCH) {
+      if (more) {
+        tmem_ld_32x32(t_row + c + CW, vn);
+        if constexpr (HN) tmem_ld_32x32(t_row + c + CW + 32, vn + 32);
+      }
+    } else {
+      tmem_ld_32x32(t_row + c, v);
+      if constexpr (HN) tmem_ld_32x32(t_row + c + 32, v + 32);
+      tmem_ld_wait();
     }
     const int n0 = n_tile0 + c;
     float f[CW];
@@ -491,10 +503,12 @@ __device__ __forceinline__ void epilogue_cols(const GemmParams& p, uint32_t t_ro
         }
       }
     }
-    if (more) {
-      tmem_ld_wait();
+    if constexpr (PREFETCH) {
+      if (more) {
+        tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < CW; ++i) v[i] = vn[i];
+        for (int i = 0; i < CW; ++i) v[i] = vn[i];
+      }
     }
   }
 }
@@ -512,13 +526,20 @@ __device__ __forceinline__ void epilogue_cols(const GemmParams& p, uint32_t t_ro
 static constexpr int kStages2 = 6;
 static constexpr int kStageBytes2 = (BM * BK + 128 * BK) * 2;  // A 128x64 + W half 128x64 = 32 KB
 static constexpr int kSmemBytes2 = kStages2 * kStageBytes2 + 1024 + 256 + 2 * 256 * 4;  // + bias[2][256]
-static constexpr int kGemmThreads2 = 320;  // TMA warp, MMA warp, 8 epilogue warps (2 per TMEM lane quarter)
+// Threads: TMA warp, MMA warp, EW epilogue warps (EW / 4 per TMEM lane quarter, each a column slice).
+// EW = 8 for plain epilogues; EW = 16 for activation epilogues, whose per-element dependency chains
+// (MUFU rcp/ex2 + Horner) leave a warp latency-bound: 4 warps per scheduler hide what 2 cannot.
+template <int EW>
+constexpr int gemm2_threads() { return 64 + 32 * EW; }
+template <int ACT>
+constexpr int gemm2_epi_warps() { return ACT == LN3_ACT_NONE ? 8 : 16; }
 
 template <int ACT, int OUT, bool HN>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads2, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gemm2_threads<gemm2_epi_warps<ACT>()>(), 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const GemmParams p) {
   constexpr int BN = 256;
+  constexpr int EW = gemm2_epi_warps<ACT>();
   constexpr int kABytes = BM * BK * 2, kBBytes = 128 * BK * 2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -529,7 +550,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   uint64_t* full_bar = bars;                  // [kStages2]  (the leader's copy is the live one)
   uint64_t* empty_bar = bars + kStages2;      // [kStages2]  one per CTA, fed by multicast commits
   uint64_t* tmem_full = bars + 2 * kStages2;  // [2]         one per CTA, fed by multicast commits
-  uint64_t* tmem_empty = tmem_full + 2;       // [2]         leader's copy: 16 arrivals (8 warps x 2 CTAs)
+  uint64_t* tmem_empty = tmem_full + 2;       // [2]         leader's copy: EW warps x 2 CTAs arrivals
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   float* bias_s = reinterpret_cast<float*>(smem + kStages2 * kStageBytes2 + 256);  // [2 acc stages][BN]
 
@@ -553,7 +574,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 16);
+      mbar_init(&tmem_empty[i], 2 * EW);
     }
     fence_barrier_init();
   }
@@ -636,7 +657,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     }
   } else {
     const int quarter = warp & 3;
-    const int half = (warp - 2) >> 2;  // which half of the tile's columns
+    const int slice = (warp - 2) >> 2;  // which slice of the tile's columns
+    constexpr int kSliceCols = BN / (EW / 4);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = pair; t < num_tiles; t += num_pairs) {
@@ -644,13 +666,14 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       tile_coords(t, tm, tn);
       // stage the tile's 256 bias values (one per epilogue thread) while the mainloop is still running;
       // two buffers + one barrier per tile: nobody can be two tiles ahead of the slowest warp
-      if (p.bias != nullptr) bias_s[acc * BN + (threadIdx.x - 64)] = __ldg(p.bias + tn * BN + (threadIdx.x - 64));
-      named_bar_sync(1, 256);
+      if (p.bias != nullptr && threadIdx.x < 64 + BN)
+        bias_s[acc * BN + (threadIdx.x - 64)] = __ldg(p.bias + tn * BN + (threadIdx.x - 64));
+      named_bar_sync(1, 32 * EW);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const int m = tm * 2 * BM + static_cast<int>(rank) * BM + quarter * 32 + lane;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
-      epilogue_cols<ACT, OUT, HN>(p, t_row, m, tn * BN, half * (BN / 2), (half + 1) * (BN / 2), bias_s + acc * BN);
+      epilogue_cols<ACT, OUT, HN>(p, t_row, m, tn * BN, slice * kSliceCols, (slice + 1) * kSliceCols, bias_s + acc * BN);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster_relaxed(mapa_u32(&tmem_empty[acc], 0));
@@ -681,7 +704,7 @@ static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const Gemm
   const int tiles = ((p.M + 2 * BM - 1) / (2 * BM)) * (p.N / 256);
   int pairs = num_sms / 2;
   if (tiles < pairs) pairs = tiles;
-  gemm2_bf16_kernel<ACT, OUT, HN><<<2 * pairs, kGemmThreads2, kSmemBytes2, stream>>>(ta, tb, p);
+  gemm2_bf16_kernel<ACT, OUT, HN><<<2 * pairs, gemm2_threads<gemm2_epi_warps<ACT>()>(), kSmemBytes2, stream>>>(ta, tb, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(LN3_ECUDA, "gemm2 launch: %s", cudaGetErrorString(e));
   count_launch();

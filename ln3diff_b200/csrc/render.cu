@@ -109,6 +109,7 @@ struct RenderParams {
   float coord_scale;  // 2 / box_warp (rounded to fp32 like the reference's scalar multiply)
   float bbox_min, bbox_max;
   int white_back;
+  int mlp_tf32;   // 1: OSG MLP on the tensor cores (TF32 operands, fp32 accumulate); 0: exact fp32 SIMT
   int no_filter;  // 1: raw decoder output for every point (ImportanceRenderer._run_model), no in-box filter
   // optional debug outputs (tests): in-box masks / importance indices / sort permutation
   unsigned char* dbg_inbox;  // [V*M][128]
@@ -120,7 +121,7 @@ struct RenderParams {
 struct WarpSmem {
   int tap_off[32][12];
   float tap_w[32][12];
-  float feat[32][33];
+  float feat[32][36];   // stride 36: A-fragment reads (row g, col t) hit 32 distinct banks; rows 16-B aligned
   float cdf[64];
   float bins[64];
   float sz[128];   // merged samples: depth, sigma, r, g, b
@@ -135,8 +136,49 @@ struct BlockSmem {
   float b1[kHid];
   float w2[4][kHid];   // pre-scaled by 1/8
   float b2[4];
+  // TF32 tensor-core path: the same weights as mma.m16n8k8 B fragments (tf32-rounded), one float2 per lane
+  float2 w1f[8][4][32];  // [n-tile of 8 hidden units][k-step of 8 features][lane] = (b0, b1)
+  float2 w2f[8][32];     // [k-step = layer-1 n-tile][lane]; hidden units in layer-1 accumulator order
   WarpSmem warp[kWarpsPerBlock];
 };
+
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+// D (16x8, fp32) += A (16x8, tf32, row) * B (8x8, tf32, col).  Lane = 4g + t holds
+//   A: a0 (g, t)  a1 (g+8, t)  a2 (g, t+4)  a3 (g+8, t+4);   B: b0 (k=t, n=g)  b1 (k=t+4, n=g)
+//   D: d0 (g, 2t)  d1 (g, 2t+1)  d2 (g+8, 2t)  d3 (g+8, 2t+1)
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// Fill the weight copies of a block (fp32 rows for the SIMT path, tf32 B fragments for the mma path).
+__device__ __forceinline__ void load_osg_weights(BlockSmem& bs, const float* w1, const float* b1, const float* w2,
+                                                 const float* b2) {
+  for (int i = threadIdx.x; i < kHid * kC; i += blockDim.x)
+    (&bs.w1[0][0])[i] = __fmul_rn(w1[i], 0.17677669529663687f);  // weight_gain = 1/sqrt(32)
+  for (int i = threadIdx.x; i < 4 * kHid; i += blockDim.x) (&bs.w2[0][0])[i] = __fmul_rn(w2[i], 0.125f);
+  if (threadIdx.x < kHid) bs.b1[threadIdx.x] = b1[threadIdx.x];
+  if (threadIdx.x < 4) bs.b2[threadIdx.x] = b2[threadIdx.x];
+  for (int i = threadIdx.x; i < 8 * 4 * 32; i += blockDim.x) {
+    const int ln = i & 31, ks = (i >> 5) & 3, nt = i >> 7, g = ln >> 2, t = ln & 3;
+    const float* row = w1 + (8 * nt + g) * kC + 8 * ks;  // B[k][n] = W1[n][k]
+    bs.w1f[nt][ks][ln] = make_float2(__uint_as_float(to_tf32(__fmul_rn(row[t], 0.17677669529663687f))),
+                                     __uint_as_float(to_tf32(__fmul_rn(row[t + 4], 0.17677669529663687f))));
+  }
+  for (int i = threadIdx.x; i < 8 * 32; i += blockDim.x) {
+    const int ln = i & 31, nt = i >> 5, g = ln >> 2, t = ln & 3;
+    // layer-2 k index t <-> hidden unit 8nt + 2t, k index t+4 <-> hidden unit 8nt + 2t + 1 (the order in
+    // which a lane holds the layer-1 accumulators), outputs n = g < 4 (sigma, r, g, b), zero padding above
+    const float v0 = g < 4 ? __fmul_rn(w2[g * kHid + 8 * nt + 2 * t], 0.125f) : 0.f;
+    const float v1 = g < 4 ? __fmul_rn(w2[g * kHid + 8 * nt + 2 * t + 1], 0.125f) : 0.f;
+    bs.w2f[nt][ln] = make_float2(__uint_as_float(to_tf32(v0)), __uint_as_float(to_tf32(v1)));
+  }
+}
 
 __device__ __forceinline__ float softplus_t(float x) {  // torch.nn.Softplus(beta=1, threshold=20)
   return x > 20.f ? x : log1pf(expf(x));
@@ -199,7 +241,11 @@ __device__ __forceinline__ void plane_taps(float gx, float gy, int H, int W, int
 
 // Evaluate the implicit model on 32 samples (one per lane): returns sigma / rgb for this lane's
 // sample with the reference's out-of-box filter applied.
-__device__ __forceinline__ void eval_batch(const RenderParams& p, const BlockSmem& bs, WarpSmem& ws,
+// Not inlined: four copies of this body put the kernel at 164 KB of SASS and "no instruction" (i-cache
+// miss) became the top stall once the MLP moved to the tensor cores; the precision is a template
+// parameter so that only one MLP body is in the instruction stream.
+template <bool TF32>
+__device__ __noinline__ void eval_batch(const RenderParams& p, const BlockSmem& bs, WarpSmem& ws,
                                            const float* __restrict__ planes_obj, int lane,
                                            float px, float py, float pz, bool& inbox, float& sigma,
                                            float& cr, float& cg, float& cb) {
@@ -244,11 +290,71 @@ __device__ __forceinline__ void eval_batch(const RenderParams& p, const BlockSme
     }
   }
   __syncwarp();
-  // phase C: lane = sample; 32 -> 64 (softplus) -> 4
+  float y0, y1, y2, y3;
+  if constexpr (TF32) {
+    // phase C on the tensor cores: [32 samples x 32] x [32 x 64] -> softplus -> [32 x 64] x [64 x 8(4 used)]
+    // as mma.m16n8k8 TF32 (fp32 accumulate): 64 + 16 MMAs instead of 2304 FFMA + 768 LDS per lane.
+    const int g = lane >> 2, t = lane & 3;
+    uint32_t a[2][4][4];  // [m-tile][k-step][fragment]
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        a[mt][ks][0] = to_tf32(ws.feat[16 * mt + g][8 * ks + t]);
+        a[mt][ks][1] = to_tf32(ws.feat[16 * mt + g + 8][8 * ks + t]);
+        a[mt][ks][2] = to_tf32(ws.feat[16 * mt + g][8 * ks + t + 4]);
+        a[mt][ks][3] = to_tf32(ws.feat[16 * mt + g + 8][8 * ks + t + 4]);
+      }
+    float o[2][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      o[mt][0] = o[mt][2] = t < 2 ? bs.b2[2 * t] : 0.f;
+      o[mt][1] = o[mt][3] = t < 2 ? bs.b2[2 * t + 1] : 0.f;
+    }
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      float h[2][4];
+      const float bb0 = bs.b1[8 * nt + 2 * t], bb1 = bs.b1[8 * nt + 2 * t + 1];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) h[mt][0] = h[mt][2] = bb0, h[mt][1] = h[mt][3] = bb1;
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const float2 b = bs.w1f[nt][ks][lane];
+        mma_tf32(h[0], a[0][ks], __float_as_uint(b.x), __float_as_uint(b.y));
+        mma_tf32(h[1], a[1][ks], __float_as_uint(b.x), __float_as_uint(b.y));
+      }
+      // the layer-1 accumulator fragment IS the layer-2 A fragment for k-step nt (hidden units permuted
+      // consistently in w2f): a0 = d0, a1 = d2, a2 = d1, a3 = d3
+      const float2 b2f = bs.w2f[nt][lane];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const uint32_t a2[4] = {to_tf32(softplus_fast(h[mt][0])), to_tf32(softplus_fast(h[mt][2])),
+                                to_tf32(softplus_fast(h[mt][1])), to_tf32(softplus_fast(h[mt][3]))};
+        mma_tf32(o[mt], a2, __float_as_uint(b2f.x), __float_as_uint(b2f.y));
+      }
+    }
+    // back to lane = sample through the (now idle) feature buffer: y[sample][4]
+    __syncwarp();
+    float* ybuf = &ws.feat[0][0];
+    if (t < 2) {
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        *reinterpret_cast<float2*>(ybuf + (16 * mt + g) * 4 + 2 * t) = make_float2(o[mt][0], o[mt][1]);
+        *reinterpret_cast<float2*>(ybuf + (16 * mt + g + 8) * 4 + 2 * t) = make_float2(o[mt][2], o[mt][3]);
+      }
+    }
+    __syncwarp();
+    const float4 yv = *reinterpret_cast<const float4*>(ybuf + lane * 4);
+    y0 = yv.x, y1 = yv.y, y2 = yv.z, y3 = yv.w;
+  } else {
+  // phase C (exact fp32 SIMT): lane = sample; 32 -> 64 (softplus) -> 4
   float x[kC];
 #pragma unroll
-  for (int c = 0; c < kC; ++c) x[c] = ws.feat[lane][c];
-  float y0 = bs.b2[0], y1 = bs.b2[1], y2 = bs.b2[2], y3 = bs.b2[3];
+  for (int c = 0; c < kC; c += 4) {
+    const float4 v = *reinterpret_cast<const float4*>(&ws.feat[lane][c]);
+    x[c] = v.x, x[c + 1] = v.y, x[c + 2] = v.z, x[c + 3] = v.w;
+  }
+  y0 = bs.b2[0], y1 = bs.b2[1], y2 = bs.b2[2], y3 = bs.b2[3];
 #pragma unroll 4
   for (int j = 0; j < kHid; ++j) {
     float acc = bs.b1[j];
@@ -266,6 +372,7 @@ __device__ __forceinline__ void eval_batch(const RenderParams& p, const BlockSme
     y2 = fmaf(h, bs.w2[2][j], y2);
     y3 = fmaf(h, bs.w2[3][j], y3);
   }
+  }
   __syncwarp();
   if (inbox || p.no_filter) {
     sigma = y0;
@@ -278,16 +385,13 @@ __device__ __forceinline__ void eval_batch(const RenderParams& p, const BlockSme
   }
 }
 
+template <bool TF32>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, 2)
 render_rays_kernel(const RenderParams p) {
   extern __shared__ uint8_t smem_raw[];
   BlockSmem& bs = *reinterpret_cast<BlockSmem*>(smem_raw);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int i = threadIdx.x; i < kHid * kC; i += blockDim.x)
-    (&bs.w1[0][0])[i] = __fmul_rn(p.w1[i], 0.17677669529663687f);  // weight_gain = 1/sqrt(32)
-  for (int i = threadIdx.x; i < 4 * kHid; i += blockDim.x) (&bs.w2[0][0])[i] = __fmul_rn(p.w2[i], 0.125f);
-  if (threadIdx.x < kHid) bs.b1[threadIdx.x] = p.b1[threadIdx.x];
-  if (threadIdx.x < 4) bs.b2[threadIdx.x] = p.b2[threadIdx.x];
+  load_osg_weights(bs, p.w1, p.b1, p.w2, p.b2);
   __syncthreads();
   WarpSmem& ws = bs.warp[warp];
 
@@ -327,7 +431,7 @@ render_rays_kernel(const RenderParams p) {
       const float py = __fadd_rn(oy, __fmul_rn(zc[b], dy));
       const float pz = __fadd_rn(oz, __fmul_rn(zc[b], dz));
       bool inbox;
-      eval_batch(p, bs, ws, planes_obj, lane, px, py, pz, inbox, sc[b], rc[b], gc[b], bc[b]);
+      eval_batch<TF32>(p, bs, ws, planes_obj, lane, px, py, pz, inbox, sc[b], rc[b], gc[b], bc[b]);
       if (p.dbg_inbox) p.dbg_inbox[ray * 128 + b * 32 + lane] = inbox;
     }
     // ---- coarse ray march -> weights (ray_marcher.py:26-47); interval i = samples (i, i+1)
@@ -428,7 +532,7 @@ render_rays_kernel(const RenderParams p) {
       const float py = __fadd_rn(oy, __fmul_rn(zf[b], dy));
       const float pz = __fadd_rn(oz, __fmul_rn(zf[b], dz));
       bool inbox;
-      eval_batch(p, bs, ws, planes_obj, lane, px, py, pz, inbox, sf[b], rf[b], gf[b], bf[b]);
+      eval_batch<TF32>(p, bs, ws, planes_obj, lane, px, py, pz, inbox, sf[b], rf[b], gf[b], bf[b]);
       if (p.dbg_inbox) p.dbg_inbox[ray * 128 + 64 + b * 32 + lane] = inbox;
     }
     // ---- unify: stable rank sort of the 128 (coarse ++ fine) depths (renderer.py:422-435)
@@ -441,12 +545,25 @@ render_rays_kernel(const RenderParams p) {
       __syncwarp();
       int rank[4] = {0, 0, 0, 0};
       const float mine[4] = {zc[0], zc[1], zf[0], zf[1]};
-      for (int k = 0; k < 128; ++k) {
-        const float zk = stage[k];
+      // rank = #(z_k < mine) + #(z_k == mine with k < my index).  My index is q*32 + lane, so against a
+      // whole 32-block kb the tie-break is a compile-time choice (kb < q: "<=", kb > q: "<") and only the
+      // own block needs the lane-dependent form; candidates come four per LDS.128.
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int idx = q * 32 + lane;
-          rank[q] += (zk < mine[q]) || (zk == mine[q] && k < idx);
+      for (int kb = 0; kb < 4; ++kb) {
+#pragma unroll 2
+        for (int kk = 0; kk < 32; kk += 4) {
+          const float4 z4 = *reinterpret_cast<const float4*>(stage + kb * 32 + kk);
+          const float zs[4] = {z4.x, z4.y, z4.z, z4.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float zk = zs[e];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              if (kb < q) rank[q] += zk <= mine[q];
+              else if (kb > q) rank[q] += zk < mine[q];
+              else rank[q] += (zk < mine[q]) || (zk == mine[q] && kk + e < lane);
+            }
+          }
         }
       }
       const float sv[4] = {sc[0], sc[1], sf[0], sf[1]};
@@ -574,20 +691,27 @@ int render_views(const ln3_render_args* a, cudaStream_t stream) {
   p.bbox_min = static_cast<float>(a->bbox_min); p.bbox_max = static_cast<float>(a->bbox_max);
   p.white_back = a->white_back;
   p.no_filter = 0;
+  p.mlp_tf32 = a->mlp_precision == LN3_MLP_TF32;
   p.dbg_inbox = a->dbg_inbox; p.dbg_inds = a->dbg_inds; p.dbg_order = a->dbg_order;
   p.dbg_zfine = a->dbg_zfine;
 
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(render_rays_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(render_rays_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(sizeof(BlockSmem)));
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(render_rays_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               static_cast<int>(sizeof(BlockSmem)));
     if (e != cudaSuccess) return set_error(LN3_ECUDA, "render: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
   const int sms = device_sm_count();
   long long blocks = (rays + kWarpsPerBlock - 1) / kWarpsPerBlock;
   if (blocks > 2LL * sms) blocks = 2LL * sms;  // persistent: 2 CTAs per SM, grid-stride over rays
-  render_rays_kernel<<<static_cast<unsigned>(blocks), kWarpsPerBlock * 32, sizeof(BlockSmem), stream>>>(p);
+  if (p.mlp_tf32)
+    render_rays_kernel<true><<<static_cast<unsigned>(blocks), kWarpsPerBlock * 32, sizeof(BlockSmem), stream>>>(p);
+  else
+    render_rays_kernel<false><<<static_cast<unsigned>(blocks), kWarpsPerBlock * 32, sizeof(BlockSmem), stream>>>(p);
   render_finalize_kernel<<<static_cast<unsigned>((rays + 255) / 256), 256, 0, stream>>>(
       a->depth, keys, a->V, a->M, a->group_size);
   cudaError_t e = cudaGetLastError();
@@ -616,16 +740,13 @@ __device__ __forceinline__ float linspace_at(float lo, float hi, float step, int
                    : __fsub_rn(hi, __fmul_rn(step, static_cast<float>(n - i - 1)));
 }
 
+template <bool TF32>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, 2)
 query_points_kernel(const RenderParams p, const QueryParams q) {
   extern __shared__ uint8_t smem_raw[];
   BlockSmem& bs = *reinterpret_cast<BlockSmem*>(smem_raw);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int i = threadIdx.x; i < kHid * kC; i += blockDim.x)
-    (&bs.w1[0][0])[i] = __fmul_rn(p.w1[i], 0.17677669529663687f);
-  for (int i = threadIdx.x; i < 4 * kHid; i += blockDim.x) (&bs.w2[0][0])[i] = __fmul_rn(p.w2[i], 0.125f);
-  if (threadIdx.x < kHid) bs.b1[threadIdx.x] = p.b1[threadIdx.x];
-  if (threadIdx.x < 4) bs.b2[threadIdx.x] = p.b2[threadIdx.x];
+  load_osg_weights(bs, p.w1, p.b1, p.w2, p.b2);
   __syncthreads();
   WarpSmem& ws = bs.warp[warp];
   const long long chunks_per_obj = (q.P + 31) / 32;
@@ -650,7 +771,7 @@ query_points_kernel(const RenderParams p, const QueryParams q) {
     const float* planes_obj = p.planes + static_cast<long long>(obj) * 3 * p.H * p.W * kC;
     bool inbox;
     float sg, cr, cg, cb;
-    eval_batch(p, bs, ws, planes_obj, lane, px, py, pz, inbox, sg, cr, cg, cb);
+    eval_batch<TF32>(p, bs, ws, planes_obj, lane, px, py, pz, inbox, sg, cr, cg, cb);
     if (live) {
       const long long o = static_cast<long long>(obj) * q.P + i;
       q.sigma[o] = sg;
@@ -695,10 +816,14 @@ int query_points(const ln3_query_points_args* a, cudaStream_t stream) {
   p.coord_scale = static_cast<float>(2.0 / a->box_warp);
   p.bbox_min = 0.f; p.bbox_max = 0.f;
   p.no_filter = 1;
+  p.mlp_tf32 = a->mlp_precision == LN3_MLP_TF32;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(query_points_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(query_points_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(sizeof(BlockSmem)));
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(query_points_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               static_cast<int>(sizeof(BlockSmem)));
     if (e != cudaSuccess) return set_error(LN3_ECUDA, "query_points: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
@@ -706,7 +831,10 @@ int query_points(const ln3_query_points_args* a, cudaStream_t stream) {
   long long blocks = (chunks + kWarpsPerBlock - 1) / kWarpsPerBlock;
   const int sms = device_sm_count();
   if (blocks > 2LL * sms) blocks = 2LL * sms;
-  query_points_kernel<<<static_cast<unsigned>(blocks), kWarpsPerBlock * 32, sizeof(BlockSmem), stream>>>(p, q);
+  if (p.mlp_tf32)
+    query_points_kernel<true><<<static_cast<unsigned>(blocks), kWarpsPerBlock * 32, sizeof(BlockSmem), stream>>>(p, q);
+  else
+    query_points_kernel<false><<<static_cast<unsigned>(blocks), kWarpsPerBlock * 32, sizeof(BlockSmem), stream>>>(p, q);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(LN3_ECUDA, "query_points launch: %s", cudaGetErrorString(e));
   count_launch();

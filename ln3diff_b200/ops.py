@@ -308,9 +308,10 @@ def render_views(planes_cl: torch.Tensor, ray_o: torch.Tensor, ray_d: torch.Tens
                  noise_coarse: torch.Tensor, noise_fine: torch.Tensor, osg: tuple, *,
                  view_obj: torch.Tensor | None = None, views_per_obj: int = 0, group_size: int = 1,
                  box_warp: float = 0.9, bbox_min: float = -0.45, bbox_max: float = 0.45,
-                 white_back: bool = True, debug: bool = False):
+                 white_back: bool = True, debug: bool = False, mlp_tf32: bool = False):
     """Fused ImportanceRenderer.forward for V views.  Returns dict(rgb (V,3,M), depth (V,1,M),
-    weights (V,1,M)) (+ debug index tensors)."""
+    weights (V,1,M)) (+ debug index tensors).  mlp_tf32: evaluate the OSG MLP on the tensor cores (TF32
+    operands, fp32 accumulate; pixel error ~1e-4 rel-L2) instead of exact fp32."""
     for nm, t_ in (("planes_cl", planes_cl), ("ray_o", ray_o), ("ray_d", ray_d),
                    ("noise_coarse", noise_coarse), ("noise_fine", noise_fine)):
         _cuda(t_, nm, torch.float32)
@@ -354,12 +355,14 @@ def render_views(planes_cl: torch.Tensor, ray_o: torch.Tensor, ray_d: torch.Tens
     a.S, a.S_importance, a.hidden_dim, a.decoder_output_dim = 64, 64, 64, 3
     a.group_size, a.views_per_obj, a.white_back = group_size, views_per_obj, int(white_back)
     a.box_warp, a.bbox_min, a.bbox_max = box_warp, bbox_min, bbox_max
+    a.mlp_precision = _lib.MLP_TF32 if mlp_tf32 else _lib.MLP_FP32
     _lib.check(_lib.lib().ln3_render_views(C.byref(a), _lib.current_stream()), "ln3_render_views")
     return out
 
 
 def query_points(planes_cl: torch.Tensor, osg: tuple, *, points: torch.Tensor | None = None,
-                 grid_size: int = 0, aabb_min=(-0.45,) * 3, aabb_max=(0.45,) * 3, box_warp: float = 0.9):
+                 grid_size: int = 0, aabb_min=(-0.45,) * 3, aabb_max=(0.45,) * 3, box_warp: float = 0.9,
+                 mlp_tf32: bool = False):
     """ImportanceRenderer._run_model at arbitrary points: planes_cl (N,3,H,W,32) channels-last,
     points (N,P,3) fp32 or None for the reference's linspace grid of grid_size^3 points over the aabb.
     Returns sigma (N,P,1) (raw density logit) and rgb (N,P,3)."""
@@ -390,6 +393,7 @@ def query_points(planes_cl: torch.Tensor, osg: tuple, *, points: torch.Tensor | 
     a.w1, a.b1, a.w2, a.b2 = w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr()
     a.n_obj, a.C, a.H, a.W = N, 32, planes_cl.shape[2], planes_cl.shape[3]
     a.hidden_dim, a.decoder_output_dim, a.box_warp = 64, 3, box_warp
+    a.mlp_precision = _lib.MLP_TF32 if mlp_tf32 else _lib.MLP_FP32
     _lib.check(_lib.lib().ln3_query_points(C.byref(a), _lib.current_stream()), "ln3_query_points")
     return sigma, rgb
 

@@ -80,7 +80,7 @@ def sample_t23d(model, randn: torch.Tensor, c: dict, uc: dict, num_steps: int = 
 
 @torch.no_grad()
 def decode_and_render(decoder, latents: torch.Tensor, cameras: torch.Tensor, resolution: int = 128,
-                      scaling_divider: float = 0.96806, noise: tuple | None = None):
+                      scaling_divider: float = 0.96806, noise: tuple | None = None, mlp_tf32: bool = True):
     """`TrainLoopDiffusionWithRec.render_video_given_triplane` (nsr/train_util_diffusion.py:176-382)
     without the host round trips: latents (B,12,32,32) -> tri-planes (decoded ONCE; the reference
     decodes twice, :204-206 and :268-270) -> every camera of `cameras` (V,25) for every latent in
@@ -101,7 +101,8 @@ def decode_and_render(decoder, latents: torch.Tensor, cameras: torch.Tensor, res
     out = ops.render_views(planes_cl, ray_o, ray_d, noise[0].contiguous(), noise[1].contiguous(),
                            decoder.triplane_decoder.decoder.raw_parameters(), views_per_obj=V, group_size=1,
                            box_warp=kw.get("box_warp", 0.9), bbox_min=kw.get("sampler_bbox_min", -0.45),
-                           bbox_max=kw.get("sampler_bbox_max", 0.45), white_back=kw.get("white_back", True))
+                           bbox_max=kw.get("sampler_bbox_max", 0.45), white_back=kw.get("white_back", True),
+                           mlp_tf32=mlp_tf32)
     H = W = resolution
     w = out["weights"].view(B, V, 1, H, W)
     return dict(image_raw=out["rgb"].view(B, V, 3, H, W), image_depth=out["depth"].view(B, V, 1, H, W),

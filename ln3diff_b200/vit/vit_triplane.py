@@ -229,10 +229,12 @@ class RodinSR_256_fusionv6_ConvQuant_liteSR_dinoInit3DAttn_SD_B_3L_C_withrollout
         osg = self.triplane_decoder.decoder.raw_parameters()
         if uniform:
             sigma, rgb = ops.query_points(planes_cl, osg, grid_size=grid_size, aabb_min=boxes[0][0],
-                                          aabb_max=boxes[0][1], box_warp=kw["box_warp"])
+                                          aabb_max=boxes[0][1], box_warp=kw["box_warp"],
+                                          mlp_tf32=kw.get("osg_mlp_tf32", True))
         else:
             parts = [ops.query_points(planes_cl[i:i + 1], osg, grid_size=grid_size, aabb_min=boxes[i][0],
-                                      aabb_max=boxes[i][1], box_warp=kw["box_warp"]) for i in range(N)]
+                                      aabb_max=boxes[i][1], box_warp=kw["box_warp"],
+                                      mlp_tf32=kw.get("osg_mlp_tf32", True)) for i in range(N)]
             sigma, rgb = torch.cat([p_[0] for p_ in parts]), torch.cat([p_[1] for p_ in parts])
         G = grid_size
         return {"rgb": rgb.reshape(N, G, G, G, -1), "sigma": sigma.reshape(N, G, G, G, -1)}

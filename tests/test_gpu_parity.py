@@ -524,6 +524,7 @@ def test_decoder_grid_entry_points(dev, golden):
     from oracle import fixtures as fx
     from oracle import render as orender
     m = build_ae_decoder(fx.DECODER_ARCH, image_size=32).to(dev)
+    m.rendering_kwargs["osg_mlp_tf32"] = False          # exact fp32 MLP for the 1e-5 comparisons below
     planes = torch.randn(2, 96, 16, 16, generator=torch.Generator().manual_seed(3)) * 3
     out = m.triplane_decode_grid({"latent_after_vit": planes.to(dev)}, 6)
     assert out["sigma"].shape == (2, 6, 6, 6, 1) and out["rgb"].shape == (2, 6, 6, 6, 3)
@@ -538,3 +539,27 @@ def test_decoder_grid_entry_points(dev, golden):
     out2 = m.triplane_decode_grid({"latent_after_vit": planes.to(dev)}, 5, aabb=aabb)
     r_rgb, r_sigma = orender.run_model_points(planes[1].reshape(3, 32, 16, 16), osg, orender.grid_points([-0.2] * 3, [0.3] * 3, 5), 0.9)
     assert _rel(out2["sigma"][1].reshape(-1, 1), r_sigma) < 1e-5
+
+
+def test_render_tf32_mlp_within_north_star_tolerance(dev, golden):
+    """The tensor-core (TF32 operands, fp32 accumulate) OSG MLP path: pixels within the north-star 1e-3
+    rel-L2 of the REFERENCE's renderer; ray bookkeeping (in-box masks) unchanged from the exact path."""
+    from ln3diff_b200 import ops
+    from oracle import fixtures as fx
+    g = golden("render.npz")
+    planes, osg, nc, nf = fx.render_inputs(24)
+    o = torch.stack([torch.from_numpy(g[f"ray_o_{v}"]) for v in range(2)])
+    d = torch.stack([torch.from_numpy(g[f"ray_d_{v}"]) for v in range(2)])
+    r = _render_cuda(dev, planes, osg, o, d, nc, nf, mlp_tf32=True, debug=True)
+    rx = _render_cuda(dev, planes, osg, o, d, nc, nf, mlp_tf32=False, debug=True)
+    for v in range(2):
+        assert _rel(r["rgb"][v].t(), g[f"rgb_{v}"]) < 1e-3
+        assert _rel(r["depth"][v].t(), g[f"depth_{v}"]) < 1e-3
+        assert _rel(r["weights"][v].t(), g[f"weights_{v}"]) < 1e-3
+    assert torch.equal(r["inbox"][:, :64], rx["inbox"][:, :64])       # coarse in-box masks: independent of the MLP
+    gp = golden("points.npz")
+    cl = ops.planes_to_channels_last(fx.render_inputs(8)[0][None].to(dev).contiguous())
+    sigma, rgb = ops.query_points(cl, tuple(t.to(dev) for t in osg), points=torch.from_numpy(gp["points"])[None].to(dev),
+                                  mlp_tf32=True)
+    assert _rel(sigma[0], gp["sigma"]) < 1e-3 and _rel(rgb[0], gp["rgb"]) < 1e-3
+    print("tf32 rel-L2: rgb", _rel(r["rgb"][0].t(), g["rgb_0"]), "sigma(points)", _rel(sigma[0], gp["sigma"]))

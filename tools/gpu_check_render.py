@@ -96,7 +96,7 @@ def check(res, V, seed):
     print(tag, c, flush=True)
 
 
-def bench(res, V, n_obj):
+def bench(res, V, n_obj, tf32=False):
     planes, osg = make_scene(5, n_obj)
     cams = test_cameras(V).repeat(n_obj, 1).to(dev)
     VV = V * n_obj
@@ -107,17 +107,17 @@ def bench(res, V, n_obj):
     o, d = ops.generate_rays(cams, res)
     osg_d = tuple(t.to(dev) for t in osg)
     for _ in range(2):
-        ops.render_views(pcl, o, d, nc, nf, osg_d, views_per_obj=V)
+        ops.render_views(pcl, o, d, nc, nf, osg_d, views_per_obj=V, mlp_tf32=tf32)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
     e0.record()
     n = 3
     for _ in range(n):
-        ops.render_views(pcl, o, d, nc, nf, osg_d, views_per_obj=V)
+        ops.render_views(pcl, o, d, nc, nf, osg_d, views_per_obj=V, mlp_tf32=tf32)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / n
-    r = {"res": res, "views": VV, "ms": ms, "views_per_s": VV / ms * 1e3, "ms_per_view": ms / VV,
+    r = {"tf32": tf32, "res": res, "views": VV, "ms": ms, "views_per_s": VV / ms * 1e3, "ms_per_view": ms / VV,
          "gflops_per_s": 0.70e-3 * M * VV / ms * 1e3}
     print("bench", r, flush=True)
     res_out.setdefault("bench", []).append(r)
@@ -128,6 +128,7 @@ try:
     check(64, 3, 2)
     check(128, 1, 3)
     bench(128, 16, 4)
+    bench(128, 16, 4, tf32=True)
     bench(256, 8, 2)
     res_out["ok"] = all(c.get("ok", False) for c in res_out["cases"].values())
 except Exception as e:  # noqa

@@ -23,6 +23,6 @@ nc, nf = torch.rand(V, M, 64, device=dev), torch.rand(V, M, 64, device=dev)
 pcl = ops.planes_to_channels_last(planes)
 o, d = ops.generate_rays(orbit_cameras(V).to(dev), res)
 for _ in range(n):
-    ops.render_views(pcl, o, d, nc, nf, osg, views_per_obj=V)
+    ops.render_views(pcl, o, d, nc, nf, osg, views_per_obj=V, mlp_tf32=len(sys.argv) > 4 and sys.argv[4] == "tf32")
 torch.cuda.synchronize()
 print("done")
