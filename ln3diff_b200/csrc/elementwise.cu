@@ -5,6 +5,8 @@
 //   final_layer        LN + modulate + Linear(D -> 4*Cout) + unpatchify -> fp32 latent layout
 //   sampler_update     x' = a x + w0 m0 + w1 m1 + s noise (all sampler engines, one launch/step)
 // Reference call sites are cited per kernel in include/ln3b200.h.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "ln3_internal.h"
 
@@ -121,6 +123,121 @@ norm_modulate_kernel(const ln3_norm_modulate_args a) {
   }  // row loop
 }
 
+// 256-bit variant for D % 256 == 0 with 32-byte aligned rows (every DiT / DiT2 call): a lane owns NV8
+// chunks of 8 consecutive columns, so the fp32 row moves as LDG.256 / STG.256 (L1 no-allocate: each byte
+// is touched once) and the bf16 rows as 128-bit accesses -- half the memory instructions of the float4
+// version for the same bytes.  Same arithmetic, same order of operations per element.
+template <int NV8>
+__global__ void __launch_bounds__(256, 3)
+norm_modulate_wide_kernel(const ln3_norm_modulate_args a) {
+  const int lane = threadIdx.x & 31;
+  for (int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < a.rows;
+       row += gridDim.x * (blockDim.x >> 5)) {
+    float* x = const_cast<float*>(a.x) + static_cast<long long>(row) * a.ldx;
+    float v[NV8][8];
+#pragma unroll
+    for (int i = 0; i < NV8; ++i) ldg256_na(x + (i * 32 + lane) * 8, v[i]);
+    if (a.resid != nullptr) {
+      const __nv_bfloat16* rr = reinterpret_cast<const __nv_bfloat16*>(a.resid) + static_cast<long long>(row) * a.resid_ld;
+      const float* gg = a.resid_gate ? a.resid_gate + static_cast<long long>(row / a.resid_gate_rows) * a.resid_gate_ld : nullptr;
+#pragma unroll
+      for (int i = 0; i < NV8; ++i) {
+        const int c = (i * 32 + lane) * 8;
+        const uint4 rb = *reinterpret_cast<const uint4*>(rr + c);
+        const uint32_t rw[4] = {rb.x, rb.y, rb.z, rb.w};
+        float g[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
+        if (gg != nullptr) {
+          const float4 g0 = __ldg(reinterpret_cast<const float4*>(gg + c));
+          const float4 g1 = __ldg(reinterpret_cast<const float4*>(gg + c + 4));
+          g[0] = g0.x, g[1] = g0.y, g[2] = g0.z, g[3] = g0.w, g[4] = g1.x, g[5] = g1.y, g[6] = g1.z, g[7] = g1.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const __nv_bfloat162 r2 = *reinterpret_cast<const __nv_bfloat162*>(&rw[j]);
+          v[i][2 * j] = fmaf(g[2 * j], __low2float(r2), v[i][2 * j]);
+          v[i][2 * j + 1] = fmaf(g[2 * j + 1], __high2float(r2), v[i][2 * j + 1]);
+        }
+        stg256_f32(x + c, v[i]);
+      }
+      if (a.out == nullptr) continue;
+    }
+    float mean = 0.f, rstd = 1.f;
+    if (a.norm == LN3_NORM_LAYER) {
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV8; ++i)  // same pairing as the float4 kernel: ((a+b)+(c+d)) per 4 columns
+        s += ((v[i][0] + v[i][1]) + (v[i][2] + v[i][3])) + ((v[i][4] + v[i][5]) + (v[i][6] + v[i][7]));
+      mean = warp_sum(s) / static_cast<float>(a.D);
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float dlt = v[i][j] - mean;
+          q = fmaf(dlt, dlt, q);
+        }
+      rstd = rsqrtf(warp_sum(q) / static_cast<float>(a.D) + a.eps);
+    } else if (a.norm == LN3_NORM_RMS) {
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) q = fmaf(v[i][j], v[i][j], q);
+      rstd = rsqrtf(warp_sum(q) / static_cast<float>(a.D) + a.eps);
+    }
+    const float* sh = nullptr;
+    const float* sc = nullptr;
+    if (a.shift != nullptr) {
+      const long long g = row / a.mod_rows;
+      sh = a.shift + g * a.mod_ld;
+      sc = a.scale + g * a.mod_ld;
+    }
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(a.out) + static_cast<long long>(row) * a.ldo;
+#pragma unroll
+    for (int i = 0; i < NV8; ++i) {
+      const int c = (i * 32 + lane) * 8;
+      float y[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) y[j] = (v[i][j] - mean) * rstd;
+      auto ld8 = [&](const float* p8, float* d8) {
+        const float4 p0 = __ldg(reinterpret_cast<const float4*>(p8));
+        const float4 p1 = __ldg(reinterpret_cast<const float4*>(p8 + 4));
+        d8[0] = p0.x, d8[1] = p0.y, d8[2] = p0.z, d8[3] = p0.w, d8[4] = p1.x, d8[5] = p1.y, d8[6] = p1.z, d8[7] = p1.w;
+      };
+      if (a.weight != nullptr) {
+        float w[8];
+        ld8(a.weight + c, w);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) y[j] *= w[j];
+      }
+      if (sh != nullptr) {
+        float s1[8], s0[8];
+        ld8(sc + c, s1);
+        ld8(sh + c, s0);
+        if (a.scale_tab != nullptr) {
+          float t1[8], t0[8];
+          ld8(a.scale_tab + c, t1);
+          ld8(a.shift_tab + c, t0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) s1[j] += t1[j], s0[j] += t0[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) y[j] = fmaf(y[j], 1.f + s1[j], s0[j]);
+      }
+      if (a.act != LN3_ACT_NONE) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) y[j] = apply_act(y[j], a.act);
+      }
+      uint4 pk;
+      pk.x = pack_bf16x2(y[0], y[1]);
+      pk.y = pack_bf16x2(y[2], y[3]);
+      pk.z = pack_bf16x2(y[4], y[5]);
+      pk.w = pack_bf16x2(y[6], y[7]);
+      *reinterpret_cast<uint4*>(o + c) = pk;
+    }
+  }
+}
+
 int norm_modulate(const ln3_norm_modulate_args* a, cudaStream_t stream) {
   if (a->rows <= 0) return LN3_OK;
   if (a->D % 128 != 0 || a->D > 2048 || a->D <= 0)
@@ -143,6 +260,26 @@ int norm_modulate(const ln3_norm_modulate_args* a, cudaStream_t stream) {
   const int blocks_needed = (a->rows + warps - 1) / warps;
   const int wave = device_sm_count() * 4;  // 4 x 256-thread blocks resident per SM (<= 64 regs/thread)
   dim3 grid(blocks_needed < wave ? blocks_needed : wave), block(warps * 32);
+  static const bool wide_enabled = !(getenv("LN3_NORM_WIDE") && atoi(getenv("LN3_NORM_WIDE")) == 0);
+  const bool wide = wide_enabled && a->D % 256 == 0 && a->D <= 1536 && a->ldx % 8 == 0 && a->ldo % 8 == 0 &&
+                    (reinterpret_cast<uintptr_t>(a->x) & 31) == 0 && (a->out == nullptr || (reinterpret_cast<uintptr_t>(a->out) & 15) == 0) &&
+                    (a->resid == nullptr || (a->resid_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(a->resid) & 15) == 0));
+  if (wide) {
+    const int wave3 = device_sm_count() * 3;  // 3 resident blocks per SM at <= 80 registers
+    grid = dim3(blocks_needed < wave3 ? blocks_needed : wave3);
+    switch (a->D / 256) {
+      case 1: norm_modulate_wide_kernel<1><<<grid, block, 0, stream>>>(*a); break;
+      case 2: norm_modulate_wide_kernel<2><<<grid, block, 0, stream>>>(*a); break;
+      case 3: norm_modulate_wide_kernel<3><<<grid, block, 0, stream>>>(*a); break;
+      case 4: norm_modulate_wide_kernel<4><<<grid, block, 0, stream>>>(*a); break;
+      case 5: norm_modulate_wide_kernel<5><<<grid, block, 0, stream>>>(*a); break;
+      default: norm_modulate_wide_kernel<6><<<grid, block, 0, stream>>>(*a); break;
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error(LN3_ECUDA, "norm_modulate launch: %s", cudaGetErrorString(e));
+    count_launch();
+    return LN3_OK;
+  }
   switch (a->D / 128) {
 #define LN3_NM_CASE(n) \
   case n: norm_modulate_kernel<n><<<grid, block, 0, stream>>>(*a); break;
