@@ -4,6 +4,8 @@
 #include <cstdio>
 #include <cstring>
 
+#include <cstdlib>
+
 #include "ln3_internal.h"
 
 namespace ln3 {
@@ -20,6 +22,11 @@ int set_error(int code, const char* fmt, ...) {
 }
 
 void count_launch(int n) { g_launches.fetch_add(static_cast<unsigned long long>(n)); }
+
+bool pdl_enabled() {
+  static const bool on = getenv("LN3_PDL") && atoi(getenv("LN3_PDL")) != 0;  // opt-in: measured no gain inside CUDA graphs
+  return on;
+}
 
 int device_sm_count() {
   static int sms = 0;

@@ -151,6 +151,8 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_launch_dependents();
+  pdl_wait();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 8) {
@@ -491,15 +493,16 @@ int fmha_fwd(const ln3_fmha_args* a, cudaStream_t stream) {
   if (nitems >= (1 << 20)) return set_error(LN3_EUNSUPPORTED, "fmha: more than 2^20 (batch, head, 256-row) work items");
   const int sms = device_sm_count();
   const int grid = static_cast<int>(nitems < sms ? nitems : sms);
+  cudaError_t le = cudaSuccess;
   switch (variant) {
 #define LN3_FMHA_CASE(P, G) \
-  case (P) * 2 + (G): fmha_fwd_kernel<P, (G) != 0><<<grid, kFmhaThreads, kFmhaSmem, stream>>>(tq, tk, tv, tk2, tv2, to, p); break;
+  case (P) * 2 + (G): le = launch_pdl(fmha_fwd_kernel<P, (G) != 0>, dim3(grid), dim3(kFmhaThreads), kFmhaSmem, stream, tq, tk, tv, tk2, tv2, to, p); break;
     LN3_FMHA_CASE(0, 0) LN3_FMHA_CASE(0, 1) LN3_FMHA_CASE(2, 0) LN3_FMHA_CASE(2, 1)
     LN3_FMHA_CASE(3, 0) LN3_FMHA_CASE(3, 1) LN3_FMHA_CASE(4, 0) LN3_FMHA_CASE(4, 1)
 #undef LN3_FMHA_CASE
     default: return set_error(LN3_EINVAL, "fmha: bad variant");
   }
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = le != cudaSuccess ? le : cudaGetLastError();
   if (e != cudaSuccess) return set_error(LN3_ECUDA, "fmha launch: %s", cudaGetErrorString(e));
   count_launch();
   return LN3_OK;

@@ -172,6 +172,12 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t* v)
       "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
       : "memory");
 }
+// Programmatic dependent launch: the kernel may start while its stream predecessor is still running;
+// pdl_wait() returns once every prerequisite grid has completed and its memory is visible (a no-op for a
+// normal launch), pdl_launch_dependents() lets the NEXT kernel's CTAs be scheduled as ours retire.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // One lane of the (converged) warp.  Code that feeds tcgen05.mma should run warp-uniformly and guard
 // only the issue itself with this: inside an `if (lane == 0)` region ptxas cannot prove descriptors
 // uniform and wraps every UTCHMMA in an ELECT / R2UR.BROADCAST waterfall (~100 cycles per MMA).

@@ -30,6 +30,8 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 template <int NV>
 __global__ void __launch_bounds__(256)
 norm_modulate_kernel(const ln3_norm_modulate_args a) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   // grid-stride over rows: the host sizes the grid to one resident wave, so there is no partial last wave
   for (int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < a.rows;
@@ -130,6 +132,8 @@ norm_modulate_kernel(const ln3_norm_modulate_args a) {
 template <int NV8>
 __global__ void __launch_bounds__(256, 3)
 norm_modulate_wide_kernel(const ln3_norm_modulate_args a) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   for (int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < a.rows;
        row += gridDim.x * (blockDim.x >> 5)) {
@@ -265,17 +269,18 @@ int norm_modulate(const ln3_norm_modulate_args* a, cudaStream_t stream) {
                     (reinterpret_cast<uintptr_t>(a->x) & 31) == 0 && (a->out == nullptr || (reinterpret_cast<uintptr_t>(a->out) & 15) == 0) &&
                     (a->resid == nullptr || (a->resid_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(a->resid) & 15) == 0));
   if (wide) {
+    cudaError_t le = cudaSuccess;
     const int wave3 = device_sm_count() * 3;  // 3 resident blocks per SM at <= 80 registers
     grid = dim3(blocks_needed < wave3 ? blocks_needed : wave3);
     switch (a->D / 256) {
-      case 1: norm_modulate_wide_kernel<1><<<grid, block, 0, stream>>>(*a); break;
-      case 2: norm_modulate_wide_kernel<2><<<grid, block, 0, stream>>>(*a); break;
-      case 3: norm_modulate_wide_kernel<3><<<grid, block, 0, stream>>>(*a); break;
-      case 4: norm_modulate_wide_kernel<4><<<grid, block, 0, stream>>>(*a); break;
-      case 5: norm_modulate_wide_kernel<5><<<grid, block, 0, stream>>>(*a); break;
-      default: norm_modulate_wide_kernel<6><<<grid, block, 0, stream>>>(*a); break;
+      case 1: le = launch_pdl(norm_modulate_wide_kernel<1>, grid, block, 0, stream, *a); break;
+      case 2: le = launch_pdl(norm_modulate_wide_kernel<2>, grid, block, 0, stream, *a); break;
+      case 3: le = launch_pdl(norm_modulate_wide_kernel<3>, grid, block, 0, stream, *a); break;
+      case 4: le = launch_pdl(norm_modulate_wide_kernel<4>, grid, block, 0, stream, *a); break;
+      case 5: le = launch_pdl(norm_modulate_wide_kernel<5>, grid, block, 0, stream, *a); break;
+      default: le = launch_pdl(norm_modulate_wide_kernel<6>, grid, block, 0, stream, *a); break;
     }
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = le != cudaSuccess ? le : cudaGetLastError();
     if (e != cudaSuccess) return set_error(LN3_ECUDA, "norm_modulate launch: %s", cudaGetErrorString(e));
     count_launch();
     return LN3_OK;

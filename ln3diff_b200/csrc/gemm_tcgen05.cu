@@ -248,6 +248,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_launch_dependents();
+  pdl_wait();  // everything above (barriers, TMEM, descriptor prefetch) overlapped the previous kernel
   const uint32_t tmem_base = *tmem_slot;
 
   // Tile order: consecutive CTAs walk M first inside a group of N panels so that the
@@ -365,8 +367,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
   }
   const int tiles = ((p.M + BM - 1) / BM) * (p.N / BN);
   const int grid = tiles < num_sms ? tiles : num_sms;
-  gemm_bf16_kernel<BN, HN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = launch_pdl(gemm_bf16_kernel<BN, HN>, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, stream, ta, tb, p);
   if (e != cudaSuccess) return set_error(LN3_ECUDA, "gemm launch: %s", cudaGetErrorString(e));
   count_launch();
   return LN3_OK;
@@ -585,6 +586,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   tc_fence_before();
   cluster_sync_all();  // barriers of both CTAs initialised before any remote signal
   tc_fence_after();
+  pdl_launch_dependents();
+  pdl_wait();
   const uint32_t tmem_base = *tmem_slot;
 
   auto tile_coords = [&](int t, int& tm, int& tn) {
@@ -704,8 +707,8 @@ static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const Gemm
   const int tiles = ((p.M + 2 * BM - 1) / (2 * BM)) * (p.N / 256);
   int pairs = num_sms / 2;
   if (tiles < pairs) pairs = tiles;
-  gemm2_bf16_kernel<ACT, OUT, HN><<<2 * pairs, gemm2_threads<gemm2_epi_warps<ACT>()>(), kSmemBytes2, stream>>>(ta, tb, p);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = launch_pdl(gemm2_bf16_kernel<ACT, OUT, HN>, dim3(2 * pairs), dim3(gemm2_threads<gemm2_epi_warps<ACT>()>()),
+                             kSmemBytes2, stream, ta, tb, p);
   if (e != cudaSuccess) return set_error(LN3_ECUDA, "gemm2 launch: %s", cudaGetErrorString(e));
   count_launch();
   return LN3_OK;
