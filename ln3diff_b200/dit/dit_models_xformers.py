@@ -145,6 +145,24 @@ class TextCondDiTBlock(DiTBlock):
         self.cross_attn = MemoryEfficientCrossAttention(query_dim=hidden_size, heads=num_heads)
 
 
+class PixelArtTextCondDiTBlock(nn.Module):
+    """reference dit_models_xformers.py:326-369 -- parameters only: RMSNorm pre-norms (eps 1e-5), plain
+    attention, un-gated cross-attention on the block's own RMS-normed text tokens (attention_y_norm over
+    context_dim), shared adaLN + per-block scale_shift_table (adaLN_modulation is None)."""
+
+    def __init__(self, hidden_size, num_heads, mlp_ratio=4, context_dim=None, **block_kwargs):
+        super().__init__()
+        self.hidden_size, self.num_heads = hidden_size, num_heads
+        self.norm1 = _RMSNormParam(hidden_size, eps=1e-5)
+        self.norm2 = _RMSNormParam(hidden_size, eps=1e-5)
+        self.attn = Attention(hidden_size, num_heads=num_heads, qkv_bias=True)
+        self.mlp = _FusedMLP(hidden_size, int(mlp_ratio))
+        self.cross_attn = MemoryEfficientCrossAttention(query_dim=hidden_size, context_dim=context_dim, heads=num_heads)
+        self.scale_shift_table = nn.Parameter(torch.randn(6, hidden_size) / hidden_size ** 0.5)
+        self.adaLN_modulation = None
+        self.attention_y_norm = _RMSNormParam(context_dim, eps=1e-5)
+
+
 class FinalLayer(nn.Module):
     """reference dit_models_xformers.py:655-678."""
 

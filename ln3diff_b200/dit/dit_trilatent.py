@@ -14,8 +14,8 @@ import torch
 import torch.nn as nn
 
 from .. import _lib, ops
-from .._lib import NORM_LAYER, NORM_NONE
-from .dit_models_xformers import (CaptionEmbedder, DiTBlock, FinalLayer, T2IFinalLayer,
+from .._lib import NORM_LAYER, NORM_NONE, NORM_RMS
+from .dit_models_xformers import (CaptionEmbedder, DiTBlock, FinalLayer, PixelArtTextCondDiTBlock, T2IFinalLayer,
                                   TextCondDiTBlock, TimestepEmbedder, _PatchEmbed,
                                   get_2d_sincos_pos_embed)
 
@@ -291,6 +291,201 @@ class DiT_TriLatent(nn.Module):
         return torch.cat([half, half], dim=0)
 
 
+class DiT_TriLatent_PixelArt(nn.Module):
+    """reference dit/dit_trilatent.py:146-246: the PixArt-style T23D denoiser -- one shared adaLN
+    (`adaLN_modulation` on t_emb + cap_embedder(pooled CLIP)) plus per-block `scale_shift_table`,
+    `PixelArtTextCondDiTBlock` blocks, `T2IFinalLayer`.  context = {'vector': (B, context_dim) pooled
+    CLIP, 'crossattn': (B, 77, context_dim) CLIP tokens}.
+
+    Step-invariant work is cached per prompt batch: the pooled-CLIP embedding and every block's
+    cross-attention K/V (each block RMS-normalises the tokens with its own `attention_y_norm` first; the
+    reference redoes both in every block of every step, dit_models_xformers.py:364)."""
+
+    _ln3_fused_in_scale = False
+
+    def __init__(self, input_size=32, patch_size=2, in_channels=4, hidden_size=1152, depth=28, num_heads=16,
+                 mlp_ratio=4, class_dropout_prob=0.1, num_classes=1000, learn_sigma=True, mixing_logit_init=-3,
+                 mixed_prediction=True, context_dim=False, roll_out=False, vit_blk=None, final_layer_blk=T2IFinalLayer):
+        super().__init__()
+        assert roll_out, "DiT_TriLatent requires roll_out=True (dit_trilatent.py:49)"
+        if patch_size != 2 or hidden_size // num_heads != 64:
+            raise NotImplementedError("libln3b200 implements patch_size=2, head_dim=64")
+        if final_layer_blk is not T2IFinalLayer:
+            raise NotImplementedError("the PixelArt T23D registry entries use T2IFinalLayer (dit_trilatent.py:301-316)")
+        assert num_classes == 0 and context_dim
+        self.plane_n, self.depth, self.mlp_ratio = 3, depth, mlp_ratio
+        self.learn_sigma, self.in_channels = learn_sigma, in_channels
+        self.out_channels = in_channels * 2 if learn_sigma else in_channels
+        self.patch_size, self.num_heads, self.embed_dim = patch_size, num_heads, hidden_size
+        self.input_size, self.roll_out, self.context_dim = input_size, roll_out, context_dim
+        self.x_embedder = _PatchEmbed(input_size, patch_size, in_channels, hidden_size, bias=True)
+        self.t_embedder = TimestepEmbedder(hidden_size)
+        self.y_embedder = None
+        self.pos_embed = nn.Parameter(torch.zeros(1, 3 * self.x_embedder.num_patches, hidden_size), requires_grad=False)
+        # the reference ignores the caller's vit_blk here (dit_trilatent.py:167-171)
+        self.blocks = nn.ModuleList([PixelArtTextCondDiTBlock(hidden_size=hidden_size, num_heads=num_heads,
+                                                              mlp_ratio=mlp_ratio, context_dim=context_dim)
+                                     for _ in range(depth)])
+        self.final_layer = T2IFinalLayer(hidden_size, patch_size, self.out_channels)
+        self.adaLN_modulation = nn.Sequential(nn.SiLU(), nn.Linear(hidden_size, 6 * hidden_size, bias=True))
+        self.cap_embedder = nn.Sequential(nn.LayerNorm(context_dim), nn.Linear(context_dim, hidden_size))
+        self.initialize_weights()
+        self._prep = None
+        self._ctx_cache = None
+
+    def initialize_weights(self):
+        def _basic_init(m):
+            if isinstance(m, nn.Linear):
+                nn.init.xavier_uniform_(m.weight)
+                if m.bias is not None:
+                    nn.init.constant_(m.bias, 0)
+        self.apply(_basic_init)
+        w = self.x_embedder.proj.weight.data
+        nn.init.xavier_uniform_(w.view([w.shape[0], -1]))
+        nn.init.constant_(self.x_embedder.proj.bias, 0)
+        nn.init.normal_(self.t_embedder.mlp[0].weight, std=0.02)
+        nn.init.normal_(self.t_embedder.mlp[2].weight, std=0.02)
+        nn.init.constant_(self.final_layer.linear.weight, 0)
+        nn.init.constant_(self.final_layer.linear.bias, 0)
+        nn.init.constant_(self.cap_embedder[-1].weight, 0)
+        nn.init.constant_(self.cap_embedder[-1].bias, 0)
+        p = int(self.x_embedder.num_patches ** 0.5)
+        D = self.pos_embed.shape[-1]
+        pe = get_2d_sincos_pos_embed(D, (3, p * p)).reshape(3 * p * p, D)
+        self.pos_embed.data.copy_(torch.from_numpy(pe).float().unsqueeze(0))
+
+    def _apply(self, fn, *a, **kw):
+        self._prep = None
+        self._ctx_cache = None
+        return super()._apply(fn, *a, **kw)
+
+    def load_state_dict(self, *a, **kw):
+        self._prep = None
+        self._ctx_cache = None
+        return super().load_state_dict(*a, **kw)
+
+    @torch.no_grad()
+    def prepare(self):
+        dev = self.pos_embed.device
+        if dev.type != "cuda":
+            raise RuntimeError("ln3diff_b200 DiT runs on CUDA only (no CPU fallback)")
+        bf = lambda w: w.detach().to(dev, torch.bfloat16).contiguous()
+        f32 = lambda w: w.detach().to(dev, torch.float32).contiguous()
+        P = dict(t0_w=bf(self.t_embedder.mlp[0].weight), t0_b=f32(self.t_embedder.mlp[0].bias),
+                 t2_w=bf(self.t_embedder.mlp[2].weight), t2_b=f32(self.t_embedder.mlp[2].bias),
+                 ada_w=bf(self.adaLN_modulation[1].weight), ada_b=f32(self.adaLN_modulation[1].bias),
+                 cap_ln_w=f32(self.cap_embedder[0].weight), cap_ln_b=f32(self.cap_embedder[0].bias),
+                 cap_w=bf(self.cap_embedder[1].weight), cap_b=f32(self.cap_embedder[1].bias),
+                 pe_w=f32(self.x_embedder.proj.weight), pe_b=f32(self.x_embedder.proj.bias), pos=f32(self.pos_embed),
+                 fin_w=f32(self.final_layer.linear.weight), fin_b=f32(self.final_layer.linear.bias),
+                 fin_tab=f32(self.final_layer.scale_shift_table),
+                 tables=f32(torch.stack([b.scale_shift_table.detach().reshape(-1) for b in self.blocks], 0)))
+        P["blocks"] = [dict(
+            n1_w=f32(b.norm1.weight), n2_w=f32(b.norm2.weight), yn_w=f32(b.attention_y_norm.weight),
+            qkv_w=bf(b.attn.qkv.weight), qkv_b=f32(b.attn.qkv.bias),
+            proj_w=bf(b.attn.proj.weight), proj_b=f32(b.attn.proj.bias),
+            cq_w=bf(b.cross_attn.to_q.weight),
+            ckv_w=bf(torch.cat([b.cross_attn.to_k.weight.detach(), b.cross_attn.to_v.weight.detach()], 0)),
+            co_w=bf(b.cross_attn.to_out[0].weight), co_b=f32(b.cross_attn.to_out[0].bias),
+            fc1_w=bf(b.mlp.mlp[0].weight), fc1_b=f32(b.mlp.mlp[1].bias),
+            fc2_w=bf(b.mlp.mlp[2].weight), fc2_b=f32(b.mlp.mlp[3].bias)) for b in self.blocks]
+        self._prep = P
+        self._ws = {}
+        return P
+
+    @torch.no_grad()
+    def _context(self, context):
+        vec, ca = context["vector"], context["crossattn"]
+        key = (vec.data_ptr(), vec._version, ca.data_ptr(), ca._version, tuple(ca.shape))
+        if self._ctx_cache is not None and self._ctx_cache[0] == key:
+            return self._ctx_cache[1]
+        P, D = self._prep, self.embed_dim
+        B, Lc, Cc = ca.shape
+        vec = vec.float().contiguous()
+        # cap_embedder: LayerNorm(affine, eps 1e-5) -> Linear.  LN(x)*w + b == LN(x)*(1 + (w-1)) + b
+        vn = ops.norm_modulate(vec, norm=NORM_LAYER, eps=1e-5, shift=P["cap_ln_b"][None], scale=(P["cap_ln_w"] - 1)[None],
+                               mod_rows=B)
+        cls = ops.gemm(vn, P["cap_w"], P["cap_b"], out_kind=ops.OUT_F32)            # (B, D) fp32
+        ca2 = ca.float().reshape(B * Lc, Cc).contiguous()
+        ckv = torch.empty(self.depth, B, Lc, 2 * D, device=ca.device, dtype=torch.bfloat16)
+        for l, W in enumerate(P["blocks"]):
+            y = ops.norm_modulate(ca2, norm=NORM_RMS, weight=W["yn_w"], eps=1e-5)
+            ops.gemm(y, W["ckv_w"], out=ckv[l].view(B * Lc, 2 * D))
+        out = dict(cls=cls, ckv=ckv)
+        self._ctx_cache = (key, out)
+        return out
+
+    def _workspace(self, B):
+        ws = self._ws.get(B)
+        if ws is None:
+            dev = self.pos_embed.device
+            D, T = self.embed_dim, self.pos_embed.shape[1]
+            M = B * T
+            e = lambda *s, dt=torch.bfloat16: torch.empty(*s, device=dev, dtype=dt)
+            ws = dict(tfeat=e(B, 256), th=e(B, D), t=e(B, D, dt=torch.float32), st=e(B, D),
+                      t0=e(B, 6 * D, dt=torch.float32), mod=e(self.depth, B, 6 * D, dt=torch.float32),
+                      x=e(B, T, D, dt=torch.float32), xb=e(M, D), a=e(M, D), v=e(M, D), qkv=e(M, 3 * D), att=e(M, D), q=e(M, D),
+                      h=e(M, int(self.mlp_ratio) * D))
+            self._ws[B] = ws
+        return ws
+
+    @torch.no_grad()
+    def forward(self, x, timesteps=None, context=None, y=None, get_attr="", **kwargs):
+        if get_attr != "":
+            return getattr(self, get_attr)
+        assert context is not None and isinstance(context, dict), "PixelArt T23D needs {'vector','crossattn'}"
+        if not x.is_cuda:
+            raise RuntimeError("ln3diff_b200 DiT runs on CUDA only (no CPU fallback)")
+        if self._prep is None:
+            self.prepare()
+        P, cx = self._prep, self._context(context)
+        B = x.shape[0]
+        D, H, T = self.embed_dim, self.num_heads, self.pos_embed.shape[1]
+        M = B * T
+        ws = self._workspace(B)
+        t = timesteps.to(device=x.device, dtype=torch.float32).contiguous()
+        ops.timestep_embedding(t, out=ws["tfeat"])
+        ops.gemm(ws["tfeat"], P["t0_w"], P["t0_b"], act=ops.ACT_SILU, out=ws["th"])
+        ws["t"].copy_(cx["cls"])                                                       # t = t_emb + clip_cls
+        ops.gemm(ws["th"], P["t2_w"], P["t2_b"], out_kind=ops.OUT_RESID_F32, out=ws["t"])
+        ops.norm_modulate(ws["t"], norm=NORM_NONE, act=ops.ACT_SILU, out=ws["st"])
+        ops.gemm(ws["st"], P["ada_w"], P["ada_b"], out_kind=ops.OUT_F32, out=ws["t0"])  # shared adaLN (B, 6D)
+        torch.add(P["tables"][:, None, :], ws["t0"][None], out=ws["mod"])              # + per-block tables
+        xs = ops.patch_embed(x.float().contiguous(), P["pe_w"], P["pe_b"], P["pos"], out=ws["x"])
+        x2 = xs.view(M, D)
+        qkv3, att3, q3 = ws["qkv"].view(B, T, 3 * D), ws["att"].view(B, T, D), ws["q"].view(B, T, D)
+        val, pend_gate = ws["v"], None   # deferred residuals (see DiT_TriLatent._forward_impl)
+        for l, W in enumerate(P["blocks"]):
+            mod = ws["mod"][l]
+            sl = lambda j: mod[:, j * D:(j + 1) * D]
+            ops.norm_modulate(x2, norm=NORM_RMS, weight=W["n1_w"], eps=1e-5, shift=sl(0), scale=sl(1), mod_rows=T, out=ws["a"],
+                              resid=val if l > 0 else None, resid_gate=pend_gate, resid_gate_rows=T)
+            ops.gemm(ws["a"], W["qkv_w"], W["qkv_b"], out=ws["qkv"])
+            ops.fmha(qkv3[:, :, :D], qkv3[:, :, D:2 * D], qkv3[:, :, 2 * D:], H, out=att3)
+            ops.gemm(ws["att"], W["proj_w"], W["proj_b"], out=val)
+            ops.norm_modulate(x2, norm=NORM_NONE, out=ws["xb"], resid=val, resid_gate=sl(2), resid_gate_rows=T)
+            ops.gemm(ws["xb"], W["cq_w"], out=ws["q"])
+            ckv = cx["ckv"][l]
+            ops.fmha(q3, ckv[:, :, :D], ckv[:, :, D:], H, out=att3)
+            ops.gemm(ws["att"], W["co_w"], W["co_b"], out=val)
+            ops.norm_modulate(x2, norm=NORM_RMS, weight=W["n2_w"], eps=1e-5, shift=sl(3), scale=sl(4), mod_rows=T, out=ws["a"],
+                              resid=val)
+            ops.gemm(ws["a"], W["fc1_w"], W["fc1_b"], act=ops.ACT_GELU_ERF, out=ws["h"])
+            ops.gemm(ws["h"], W["fc2_w"], W["fc2_b"], out=val)
+            pend_gate = sl(5)
+        ops.norm_modulate(x2, norm=NORM_NONE, resid=val, resid_gate=pend_gate, resid_gate_rows=T, want_out=False)
+        return ops.final_layer(xs, ws["t"], ws["t"], P["fin_w"], P["fin_b"], self.input_size,
+                               shift_tab=P["fin_tab"][0].contiguous(), scale_tab=P["fin_tab"][1].contiguous())
+
+    @torch.no_grad()
+    def forward_with_cfg(self, x, t, context, cfg_scale):
+        """reference dit_trilatent.py:249-262 (cond first, uncond second; returns cat([half, half]))."""
+        eps = self.forward(x, t, context)
+        cond_eps, uncond_eps = torch.split(eps, len(eps) // 2, dim=0)
+        half = uncond_eps + cfg_scale * (cond_eps - uncond_eps)
+        return torch.cat([half, half], dim=0)
+
+
 def DiT_XL_2(**kwargs):
     return DiT_TriLatent(depth=28, hidden_size=1152, patch_size=2, num_heads=16, **kwargs)
 
@@ -307,18 +502,22 @@ def DiT_B_1(**kwargs):
     return DiT_TriLatent(depth=12, hidden_size=768, patch_size=1, num_heads=12, **kwargs)
 
 
-# reference dit/dit_trilatent.py:320-327 (PixelArt variants: not built yet -> explicit error)
-def _unbuilt(name):
-    def f(**kwargs):
-        raise NotImplementedError(f"{name}: PixelArt T23D variant is not implemented in ln3diff_b200 yet")
-    return f
+def DiT_B_Pixelart_2(**kwargs):
+    return DiT_TriLatent_PixelArt(depth=12, hidden_size=768, patch_size=2, num_heads=12,
+                                  final_layer_blk=T2IFinalLayer, **kwargs)
 
 
+def DiT_L_Pixelart_2(**kwargs):
+    return DiT_TriLatent_PixelArt(depth=24, hidden_size=1024, patch_size=2, num_heads=16,
+                                  final_layer_blk=T2IFinalLayer, **kwargs)
+
+
+# reference dit/dit_trilatent.py:320-327
 DiT_models = {
     "DiT-XL/2": DiT_XL_2,
     "DiT-L/2": DiT_L_2,
-    "DiT-PixelArt-L/2": _unbuilt("DiT-PixelArt-L/2"),
-    "DiT-PixelArt-B/2": _unbuilt("DiT-PixelArt-B/2"),
+    "DiT-PixelArt-L/2": DiT_L_Pixelart_2,
+    "DiT-PixelArt-B/2": DiT_B_Pixelart_2,
     "DiT-B/2": DiT_B_2,
     "DiT-B/1": DiT_B_1,
 }

@@ -223,3 +223,35 @@ def dit_i23d_pixart_forward(sd: dict, arch: str, x: torch.Tensor, timesteps: tor
     h = layer_norm(h) * (1 + scale) + shift
     h = F.linear(h, sd["final_layer.linear.weight"], sd["final_layer.linear.bias"])
     return unpatchify_rollout(h, sd["final_layer.linear.weight"].shape[0] // 4).contiguous()
+
+
+def dit_t23d_pixart_forward(sd: dict, arch: str, x: torch.Tensor, timesteps: torch.Tensor,
+                            context: dict) -> torch.Tensor:
+    """DiT_TriLatent_PixelArt (dit/dit_trilatent.py:146-246) with PixelArtTextCondDiTBlock
+    (dit/dit_models_xformers.py:326-369) and T2IFinalLayer (:61-84), fp32.
+    arch in {'DiT-PixelArt-L/2', 'DiT-PixelArt-B/2'}; context = {'vector': (B, Cc), 'crossattn': (B, L, Cc)}."""
+    cfg = DIT_SIZES[arch.replace("-PixelArt", "")]
+    heads, depth = cfg["heads"], cfg["depth"]
+    sd = {k: v.float() for k, v in sd.items()}
+    x = x.float()
+    B = x.shape[0]
+    vec, ca = context["vector"].float(), context["crossattn"].float()
+    cls = F.linear(F.layer_norm(vec, (vec.shape[-1],), sd["cap_embedder.0.weight"], sd["cap_embedder.0.bias"], 1e-5),
+                   sd["cap_embedder.1.weight"], sd["cap_embedder.1.bias"])
+    t = timestep_embedding(timesteps.float())
+    t = F.linear(F.silu(F.linear(t, sd["t_embedder.mlp.0.weight"], sd["t_embedder.mlp.0.bias"])),
+                 sd["t_embedder.mlp.2.weight"], sd["t_embedder.mlp.2.bias"]) + cls
+    t0 = F.linear(F.silu(t), sd["adaLN_modulation.1.weight"], sd["adaLN_modulation.1.bias"])
+    h = patch_embed_rollout(sd, x) + sd["pos_embed"]
+    for i in range(depth):
+        p = f"blocks.{i}."
+        mod = sd[p + "scale_shift_table"][None] + t0.reshape(B, 6, -1)
+        sh_a, sc_a, g_a, sh_m, sc_m, g_m = mod.chunk(6, dim=1)
+        h = h + g_a * self_attention(sd, p + "attn.", rms_norm(h, sd[p + "norm1.weight"], 1e-5) * (1 + sc_a) + sh_a, heads)
+        h = h + cross_attention(sd, p + "cross_attn.", h, rms_norm(ca, sd[p + "attention_y_norm.weight"], 1e-5), heads)
+        h = h + g_m * fused_mlp(sd, p + "mlp.", rms_norm(h, sd[p + "norm2.weight"], 1e-5) * (1 + sc_m) + sh_m)
+    shift, scale = (sd["final_layer.scale_shift_table"][None] + t[:, None]).chunk(2, dim=1)
+    h = layer_norm(h) * (1 + scale) + shift
+    h = F.linear(h, sd["final_layer.linear.weight"], sd["final_layer.linear.bias"])
+    return unpatchify_rollout(h, sd["final_layer.linear.weight"].shape[0] // 4).contiguous()
+

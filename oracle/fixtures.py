@@ -92,3 +92,15 @@ def i23d_state_dict(shapes: dict, pos_embed: torch.Tensor) -> dict:
                 or k == "cap_embedder.0.weight" or k.endswith("attention_y_norm.weight")):
             sd[k] = 1 + sd[k]
     return sd
+
+
+T23D_PIXART_ARCH = "DiT-PixelArt-B/2"
+
+
+def t23d_pixart_inputs():
+    g = torch.Generator().manual_seed(17)
+    x = torch.randn(2, 12, 32, 32, generator=g)
+    t = torch.tensor([12.0, 871.0])
+    ctx = {"vector": torch.randn(2, 768, generator=g), "crossattn": torch.randn(2, 77, 768, generator=g)}
+    return x, t, ctx
+

@@ -563,3 +563,21 @@ def test_render_tf32_mlp_within_north_star_tolerance(dev, golden):
                                   mlp_tf32=True)
     assert _rel(sigma[0], gp["sigma"]) < 1e-3 and _rel(rgb[0], gp["rgb"]) < 1e-3
     print("tf32 rel-L2: rgb", _rel(r["rgb"][0].t(), g["rgb_0"]), "sigma(points)", _rel(sigma[0], gp["sigma"]))
+
+
+def test_dit_t23d_pixart_forward_matches_reference_golden(dev, golden):
+    """DiT_models['DiT-PixelArt-B/2'] (shared adaLN + tables, per-block RMS-normed text K/V) vs the reference."""
+    from ln3diff_b200.dit.dit_trilatent import DiT_models
+    from oracle import fixtures as fx
+    g = golden("dit_t23d_pixart.npz")
+    m = DiT_models[fx.T23D_PIXART_ARCH](input_size=32, num_classes=0, learn_sigma=False, in_channels=4,
+                                        context_dim=768, roll_out=True)
+    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    m.load_state_dict(fx.i23d_state_dict(shapes, m.state_dict()["pos_embed"]))
+    m = m.to(dev)
+    x, t, ctx = fx.t23d_pixart_inputs()
+    cd = {k: v.to(dev) for k, v in ctx.items()}
+    out = m(x.to(dev), t.to(dev), cd)
+    assert out.dtype == torch.float32 and out.shape == (2, 12, 32, 32)
+    assert _rel(out, g["out"]) < 2e-2
+    assert _rel(m.forward_with_cfg(x.to(dev), t.to(dev), cd, 6.5), g["out_cfg"]) < 3e-2

@@ -133,3 +133,21 @@ def test_point_queries_match_reference(golden):
     # about a fifth of the random points fall outside the planes' support (zeros padding): both sides agree
     outside = (torch.from_numpy(g["points"]).abs() > 0.45).any(-1)
     assert 0.1 < outside.float().mean() < 0.7
+
+
+def test_dit_t23d_pixart_forward_matches_reference(golden):
+    """oracle.dit.dit_t23d_pixart_forward vs the reference's DiT_TriLatent_PixelArt (dit_t23d_pixart.npz)."""
+    from ln3diff_b200.dit.dit_trilatent import DiT_models
+    g = golden("dit_t23d_pixart.npz")
+    m = DiT_models[fx.T23D_PIXART_ARCH](input_size=32, num_classes=0, learn_sigma=False, in_channels=4,
+                                        context_dim=768, roll_out=True)
+    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    assert shapes["blocks.0.attention_y_norm.weight"] == (768,) and "clip_text_proj.y_proj.fc1.weight" not in shapes
+    sd = fx.i23d_state_dict(shapes, m.state_dict()["pos_embed"])
+    x, t, ctx = fx.t23d_pixart_inputs()
+    with torch.no_grad():
+        y = odit.dit_t23d_pixart_forward(sd, fx.T23D_PIXART_ARCH, x, t, ctx)
+    assert _rel(y, g["out"]) < 2e-6
+    c, u = y.chunk(2)
+    half = u + 6.5 * (c - u)
+    assert _rel(torch.cat([half, half]), g["out_cfg"]) < 2e-6
