@@ -49,7 +49,9 @@ def workload_config(n_gpus):
             "arch": ARCH, "denoise_steps": DENOISE_STEPS, "cfg_scale": CFG_SCALE,
             "prompts_per_gpu": PROMPTS_PER_GPU, "global_batch": PROMPTS_PER_GPU * n_gpus,
             "parallelism": f"prompt-sharded x{n_gpus} (replicated weights, no data-path collective)",
-            "l2": "inputs larger than L2: 1.1 GB of bf16 weights stream through every forward"}
+            "l2": "inputs larger than L2: 1.1 GB of bf16 weights stream through every forward",
+              "uncond_cross_attention": "closed form for the zero-embedding CFG half (identical context tokens -> "
+                                        "uniform softmax -> to_out(v_row)); LN3_UNCOND_CLOSED_FORM=0 disables"}
 
 
 # ------------------------------------------------------------------ CPU reference arm / baseline
@@ -382,6 +384,35 @@ def run_ours(args):
         except Exception as e:  # noqa
             vae = {"error": repr(e)}
 
+        # ---- BASELINE configs[3] on this rank's shard: I23D flow matching, 50-point Euler ODE + CFG 4.0,
+        #      DiT-PixArt-L/2 with DINO/CLIP tokens, 8 images per GPU (16 samples per forward)
+        i23d = None
+        try:
+            from ln3diff_b200.transport import Sampler, create_transport
+            from ln3diff_b200.utils import build_i23d
+            mi = build_i23d("DiT-PixArt-L/2", device=dev)
+            gi = torch.Generator(device=dev).manual_seed(7)
+            zi = torch.randn(B, 12, 32, 32, device=dev, generator=gi)
+            ci = {"vector": torch.randn(B, 768, device=dev, generator=gi),
+                  "crossattn": torch.randn(B, 256, 2048, device=dev, generator=gi)}
+            cti = {k: torch.cat([v, torch.zeros_like(v)]) for k, v in ci.items()}
+            fn = Sampler(create_transport(snr_type="lognorm")).sample_ode(sampling_method="euler", num_steps=50)
+            run = lambda: fn(torch.cat([zi, zi]), mi.forward_with_cfg, context=cti, cfg_scale=4.0)
+            run()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            run()
+            e1.record()
+            torch.cuda.synchronize()
+            ims = e0.elapsed_time(e1)
+            i23d = {"value": B / (ims / 1e3), "unit": "latents/s", "images_per_gpu": B, "ode_points": 50, "cfg_scale": 4.0,
+                    "ms": ims, "what": "BASELINE configs[3] shard: DiT-PixArt-L/2 sample_ode('euler', 50) + forward_with_cfg "
+                                       "(49 network evaluations of 16 samples), through the transport mirror (no CUDA graph)"}
+            del mi
+        except Exception as e:  # noqa
+            i23d = {"error": repr(e)}
+
         # ---- mesh-extraction lattice: 192^3 point queries (triplane_decode_grid) on one object
         grid = None
         try:
@@ -419,7 +450,7 @@ def run_ours(args):
                         "h2d_bytes_per_step": randn_h.numel() * 4 + ctx_h.numel() * 4,
                         "d2h_bytes_per_step": out_h.numel() * 4},
                 "gpu_launches": int(launches), "clocks": clk, "roofline": roofline,
-                "model_tflops": model_tf, "rendered_views": views, "vae_decode": vae, "point_queries": grid, "cpu_baseline": cpu}
+                "model_tflops": model_tf, "rendered_views": views, "vae_decode": vae, "i23d_flow": i23d, "point_queries": grid, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

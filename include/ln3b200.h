@@ -149,6 +149,15 @@ typedef struct ln3_norm_modulate_args {
   const float* resid_gate; /* fp32 [groups, resid_gate_ld] or NULL */
   long long resid_ld, resid_gate_ld;
   int resid_gate_rows;
+  /* optional: rows outside [resid_row_begin, resid_row_end) take their residual from a per-group row
+   *   resid_bcast[(r / resid_bcast_rows), :]   (bf16, row pitch resid_bcast_ld)
+   * instead of resid[r,:] -- the cross-attention output of samples whose context tokens are all
+   * identical (the zero-embedding unconditional half of classifier-free guidance,
+   * sgm/modules/diffusionmodules/guiders.py:33-44 with force_uc_zero_embeddings): softmax over identical
+   * keys is uniform, so the attention output is the one value row for every query.  NULL -> unused. */
+  const void* resid_bcast;
+  long long resid_bcast_ld;
+  int resid_bcast_rows, resid_row_begin, resid_row_end;
 } ln3_norm_modulate_args;
 
 int ln3_norm_modulate(const ln3_norm_modulate_args* args, void* stream);

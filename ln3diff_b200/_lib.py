@@ -54,6 +54,8 @@ class NormModulateArgs(C.Structure):
         ("mod_rows", C.c_int), ("norm", C.c_int), ("act", C.c_int), ("eps", C.c_float),
         ("resid", C.c_void_p), ("resid_gate", C.c_void_p), ("resid_ld", C.c_longlong),
         ("resid_gate_ld", C.c_longlong), ("resid_gate_rows", C.c_int),
+        ("resid_bcast", C.c_void_p), ("resid_bcast_ld", C.c_longlong), ("resid_bcast_rows", C.c_int),
+        ("resid_row_begin", C.c_int), ("resid_row_end", C.c_int),
     ]
 
 

@@ -43,6 +43,8 @@ norm_modulate_kernel(const ln3_norm_modulate_args a) {
   if (a.resid != nullptr) {
     // fused residual update: x += gate * resid (bf16), written back in place
     const __nv_bfloat16* rr = reinterpret_cast<const __nv_bfloat16*>(a.resid) + static_cast<long long>(row) * a.resid_ld;
+    if (a.resid_bcast != nullptr && (row < a.resid_row_begin || row >= a.resid_row_end))
+      rr = reinterpret_cast<const __nv_bfloat16*>(a.resid_bcast) + static_cast<long long>(row / a.resid_bcast_rows) * a.resid_bcast_ld;
     const float* gg = a.resid_gate ? a.resid_gate + static_cast<long long>(row / a.resid_gate_rows) * a.resid_gate_ld : nullptr;
     float* xw = const_cast<float*>(x);
 #pragma unroll
@@ -143,6 +145,8 @@ norm_modulate_wide_kernel(const ln3_norm_modulate_args a) {
     for (int i = 0; i < NV8; ++i) ldg256_na(x + (i * 32 + lane) * 8, v[i]);
     if (a.resid != nullptr) {
       const __nv_bfloat16* rr = reinterpret_cast<const __nv_bfloat16*>(a.resid) + static_cast<long long>(row) * a.resid_ld;
+      if (a.resid_bcast != nullptr && (row < a.resid_row_begin || row >= a.resid_row_end))
+        rr = reinterpret_cast<const __nv_bfloat16*>(a.resid_bcast) + static_cast<long long>(row / a.resid_bcast_rows) * a.resid_bcast_ld;
       const float* gg = a.resid_gate ? a.resid_gate + static_cast<long long>(row / a.resid_gate_rows) * a.resid_gate_ld : nullptr;
 #pragma unroll
       for (int i = 0; i < NV8; ++i) {
@@ -259,6 +263,12 @@ int norm_modulate(const ln3_norm_modulate_args* a, cudaStream_t stream) {
     if (a->resid_ld % 4) return set_error(LN3_EINVAL, "norm_modulate: resid_ld must be a multiple of 4");
     if (a->resid_gate != nullptr && (a->resid_gate_rows <= 0 || a->resid_gate_ld % 4))
       return set_error(LN3_EINVAL, "norm_modulate: bad resid_gate_rows / resid_gate_ld");
+    if (a->resid_bcast != nullptr &&
+        (a->resid_bcast_rows <= 0 || a->resid_bcast_ld % 8 || (reinterpret_cast<uintptr_t>(a->resid_bcast) & 15) ||
+         a->resid_row_begin < 0 || a->resid_row_end < a->resid_row_begin || a->resid_row_end > a->rows))
+      return set_error(LN3_EINVAL, "norm_modulate: bad resid_bcast arguments");
+  } else if (a->resid_bcast != nullptr) {
+    return set_error(LN3_EINVAL, "norm_modulate: resid_bcast needs resid");
   }
   const int warps = 8;
   const int blocks_needed = (a->rows + warps - 1) / warps;

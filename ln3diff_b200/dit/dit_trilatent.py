@@ -20,6 +20,12 @@ from .dit_models_xformers import (CaptionEmbedder, DiTBlock, FinalLayer, PixelAr
                                   get_2d_sincos_pos_embed)
 
 
+def _closed_form_uncond() -> bool:
+    """LN3_UNCOND_CLOSED_FORM=0 forces full cross-attention for identical-token samples (A/B, tests)."""
+    import os
+    return os.environ.get("LN3_UNCOND_CLOSED_FORM", "1") != "0"
+
+
 class DiT_TriLatent(nn.Module):
     """reference dit/dit_trilatent.py:22-143 (+ base dit_models_xformers.py:681-819)."""
 
@@ -164,7 +170,14 @@ class DiT_TriLatent(nn.Module):
     def _context_kv(self, context):
         """clip_text_proj + every layer's to_k/to_v on the context.  The reference recomputes
         these every step (dit_trilatent.py:107, ldm/modules/attention.py:281-283) although the
-        context is step-invariant; cached here keyed on the tensor identity/version."""
+        context is step-invariant; cached here keyed on the tensor identity/version.
+
+        Also detects samples whose context tokens are all identical -- the zero-embedding unconditional
+        half of classifier-free guidance (force_uc_zero_embeddings; every token becomes the same
+        clip_text_proj(0) row).  For those, softmax(q k^T) is uniform whatever q is, so the cross-attention
+        output of every query is `to_out(v_row)`: one (D,) row per layer and sample, computed here once.
+        `rows` is the contiguous block of samples that still needs real attention (the identical-token
+        samples must form a prefix and/or suffix of the batch, as both CFG layouts of the reference do)."""
         key = (context.data_ptr(), context._version, tuple(context.shape))
         if self._ctx_cache is not None and self._ctx_cache[0] == key:
             return self._ctx_cache[1]
@@ -176,8 +189,23 @@ class DiT_TriLatent(nn.Module):
         c2 = ops.gemm(c1, P["c2_w"], P["c2_b"])
         kv = ops.gemm(c2, P["kv_w"])  # (B*Lc, depth*2*D)
         kv = kv.view(B, Lc, self.depth, 2, self.embed_dim)
-        self._ctx_cache = (key, kv)
-        return kv
+        out = dict(kv=kv, rows=(0, B), oconst=None)
+        if _closed_form_uncond() and Lc > 1:
+            c2v = c2.view(B, Lc, -1)
+            same = (c2v == c2v[:, :1]).all(dim=2).all(dim=1).tolist()     # one host sync per prompt batch
+            g0 = 0
+            while g0 < B and same[g0]:
+                g0 += 1
+            g1 = B
+            while g1 > g0 and same[g1 - 1]:
+                g1 -= 1
+            if (g0 > 0 or g1 < B) and not any(same[g0:g1]):
+                oc = torch.empty(self.depth, B, self.embed_dim, device=context.device, dtype=torch.bfloat16)
+                for l, W in enumerate(P["blocks"]):
+                    ops.gemm(kv[:, 0, l, 1].contiguous(), W["o_w"], W["o_b"], out=oc[l])
+                out = dict(kv=kv, rows=(g0, g1), oconst=oc)
+        self._ctx_cache = (key, out)
+        return out
 
     # ------------------------------------------------------------------ forward
     @torch.no_grad()
@@ -194,17 +222,19 @@ class DiT_TriLatent(nn.Module):
             raise RuntimeError("ln3diff_b200 DiT runs on CUDA only (no CPU fallback)")
         if self._prep is None:
             self.prepare()
-        kv = self._context_kv(context)
+        cx = self._context_kv(context)
         t = timesteps.to(device=x.device, dtype=torch.float32).contiguous()
-        return self._forward_impl(x.float().contiguous(), t, kv, in_scale)
+        return self._forward_impl(x.float().contiguous(), t, cx, in_scale)
 
-    def _forward_impl(self, x, t, kv, in_scale):
+    def _forward_impl(self, x, t, cx, in_scale):
         """The fixed launch sequence of one forward (capturable in a CUDA graph: no host syncs, all
         intermediates in the per-batch workspace)."""
         P = self._prep
         B = x.shape[0]
         D, H, T = self.embed_dim, self.num_heads, self.pos_embed.shape[1]
         M = B * T
+        kv, (g0, g1), oconst = cx["kv"], cx["rows"], cx["oconst"]
+        r0, r1 = g0 * T, g1 * T        # token rows that need real cross-attention
         ws = self._workspace(B)
         ops.timestep_embedding(t, out=ws["tfeat"])
         ops.gemm(ws["tfeat"], P["t0_w"], P["t0_b"], act=ops.ACT_SILU, out=ws["th"])
@@ -230,11 +260,14 @@ class DiT_TriLatent(nn.Module):
             ops.gemm(ws["att"], W["proj_w"], W["proj_b"], out=val)
             # x += gate_msa * attn ; xb = bf16(x): the un-normalised query input of the cross-attention
             ops.norm_modulate(x2, norm=NORM_NONE, out=ws["xb"], resid=val, resid_gate=sl(2), resid_gate_rows=T)
-            ops.gemm(ws["xb"], W["q_w"], out=ws["q"])
-            ops.fmha(q3, kv[:, :, l, 0], kv[:, :, l, 1], H, out=att3)
-            ops.gemm(ws["att"], W["o_w"], W["o_b"], out=val)
-            # x += cross_attn (no gate) ; a = modulate(LN(x))
-            ops.norm_modulate(x2, norm=NORM_LAYER, shift=sl(3), scale=sl(4), mod_rows=T, out=ws["a"], resid=val)
+            if r1 > r0:
+                ops.gemm(ws["xb"][r0:r1], W["q_w"], out=ws["q"][r0:r1])
+                ops.fmha(q3[g0:g1], kv[g0:g1, :, l, 0], kv[g0:g1, :, l, 1], H, out=att3[g0:g1])
+                ops.gemm(ws["att"][r0:r1], W["o_w"], W["o_b"], out=val[r0:r1])
+            # x += cross_attn (no gate) ; a = modulate(LN(x)).  Identical-token samples take the closed form.
+            ops.norm_modulate(x2, norm=NORM_LAYER, shift=sl(3), scale=sl(4), mod_rows=T, out=ws["a"], resid=val,
+                              resid_bcast=oconst[l] if oconst is not None else None, resid_bcast_rows=T,
+                              resid_rows=(r0, r1) if oconst is not None else None)
             ops.gemm(ws["a"], W["fc1_w"], W["fc1_b"], act=ops.ACT_GELU_ERF, out=ws["h"])
             ops.gemm(ws["h"], W["fc2_w"], W["fc2_b"], out=val)
             pend_gate = sl(5)
@@ -260,7 +293,8 @@ class DiT_TriLatent(nn.Module):
             pass
 
         g = _G()
-        g.kv = kv  # keep the cached K/V alive: the graph holds raw pointers into it
+        g.kv = kv  # keep the cached K/V (+ closed-form rows) alive: the graph holds raw pointers into them
+        g.cross_attention_rows = kv["rows"]
         g.x = torch.zeros(B, 3 * self.in_channels, self.input_size, self.input_size, device=dev)
         g.t = torch.zeros(B, device=dev)
         g.in_scale = torch.ones(B, device=dev)

@@ -120,11 +120,14 @@ def norm_modulate(x: torch.Tensor, *, norm: int, shift: torch.Tensor | None = No
                   weight: torch.Tensor | None = None, eps: float = 1e-6, act: int = ACT_NONE,
                   out: torch.Tensor | None = None, resid: torch.Tensor | None = None,
                   resid_gate: torch.Tensor | None = None, resid_gate_rows: int = 1,
-                  want_out: bool = True) -> torch.Tensor | None:
+                  want_out: bool = True, resid_bcast: torch.Tensor | None = None, resid_bcast_rows: int = 1,
+                  resid_rows: tuple | None = None) -> torch.Tensor | None:
     """bf16( norm(x) * (1 + scale[g]) + shift[g] ), x fp32 (rows, D); shift/scale 2-D fp32 views
     (groups, D) with unit inner stride and equal row stride; row r uses group r // mod_rows.
     With `resid` (bf16 (rows, D)) the residual update x += resid_gate[r // resid_gate_rows] * resid is
-    applied first, IN PLACE on x; want_out=False then skips the normalised output."""
+    applied first, IN PLACE on x; want_out=False then skips the normalised output.  With `resid_bcast`
+    ((groups, D) bf16) rows outside resid_rows=(begin, end) use resid_bcast[r // resid_bcast_rows] as
+    their residual row instead of resid[r]."""
     _cuda(x, "x", torch.float32)
     _req(x.dim() == 2 and x.stride(1) == 1, "x must be (rows, D) with unit inner stride")
     rows, D = x.shape
@@ -147,6 +150,14 @@ def norm_modulate(x: torch.Tensor, *, norm: int, shift: torch.Tensor | None = No
             _req(resid_gate.dim() == 2 and resid_gate.shape[1] == D and resid_gate.stride(1) == 1
                  and resid_gate.shape[0] * resid_gate_rows >= rows, "resid_gate must be a (groups, D) view")
             a.resid_gate, a.resid_gate_ld, a.resid_gate_rows = resid_gate.data_ptr(), resid_gate.stride(0), resid_gate_rows
+    if resid_bcast is not None:
+        _req(resid is not None and resid_rows is not None, "resid_bcast needs resid and resid_rows=(begin, end)")
+        _cuda(resid_bcast, "resid_bcast", torch.bfloat16)
+        _req(resid_bcast.dim() == 2 and resid_bcast.shape[1] == D and resid_bcast.stride(1) == 1
+             and resid_bcast.shape[0] * resid_bcast_rows >= rows, "resid_bcast must be a (groups, D) bf16 view")
+        _req(0 <= resid_rows[0] <= resid_rows[1] <= rows, "resid_rows out of range")
+        a.resid_bcast, a.resid_bcast_ld, a.resid_bcast_rows = resid_bcast.data_ptr(), resid_bcast.stride(0), resid_bcast_rows
+        a.resid_row_begin, a.resid_row_end = resid_rows
     a.x, a.rows, a.D = x.data_ptr(), rows, D
     a.ldx = x.stride(0)
     if shift is not None:

@@ -581,3 +581,28 @@ def test_dit_t23d_pixart_forward_matches_reference_golden(dev, golden):
     assert out.dtype == torch.float32 and out.shape == (2, 12, 32, 32)
     assert _rel(out, g["out"]) < 2e-2
     assert _rel(m.forward_with_cfg(x.to(dev), t.to(dev), cd, 6.5), g["out_cfg"]) < 3e-2
+
+
+def test_closed_form_uncond_cross_attention(dev, monkeypatch):
+    """Samples whose context tokens are all identical (the zero-embedding CFG half) skip the cross-attention
+    q GEMM / FMHA / out GEMM: softmax over identical keys is uniform, the output is to_out(v_row).  The
+    closed form must agree with the full computation to bf16 rounding, for both CFG batch layouts."""
+    from ln3diff_b200.utils import build_t23d
+    m = build_t23d("DiT-B/2").to(dev)
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn(4, 12, 32, 32, generator=g).to(dev)
+    t = torch.tensor([3.0, 500.0, 3.0, 500.0]).to(dev)
+    c = torch.randn(2, 77, 768, generator=g)
+    for ctx, rows in ((torch.cat([torch.zeros_like(c), c]), (2, 4)), (torch.cat([c, torch.zeros_like(c)]), (0, 2)),
+                      (torch.cat([c, c]), (0, 4))):
+        ctx = ctx.to(dev)
+        monkeypatch.setenv("LN3_UNCOND_CLOSED_FORM", "1")
+        m._ctx_cache = None
+        fast = m(x, t, ctx).clone()
+        assert m._ctx_cache[1]["rows"] == rows
+        monkeypatch.setenv("LN3_UNCOND_CLOSED_FORM", "0")
+        m._ctx_cache = None
+        full = m(x, t, ctx).clone()
+        assert m._ctx_cache[1]["rows"] == (0, 4) and m._ctx_cache[1]["oconst"] is None
+        assert _rel(fast, full) < 3e-3
+    m._ctx_cache = None
