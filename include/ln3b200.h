@@ -76,7 +76,15 @@ typedef struct ln3_gemm_args {
   int head_norm_nsec;
   int head_norm_sec_cols;
   float head_norm_eps;
+  /* optional scratch for the stream-K tail of the CTA-pair kernel: ln3_gemm_workspace_bytes() bytes of
+   * device memory, 256-byte aligned, ZEROED ONCE by the caller (the kernel leaves it zeroed), never shared
+   * by GEMMs that may run concurrently.  With T output tiles on P CTA pairs the last T % P tiles are split
+   * along K over all pairs instead of leaving P - T % P pairs idle for a whole tile.  NULL -> plain tiles. */
+  void* workspace;
+  size_t workspace_bytes;
 } ln3_gemm_args;
+
+size_t ln3_gemm_workspace_bytes(void);
 
 int ln3_gemm_bf16(const ln3_gemm_args* args, void* stream);
 

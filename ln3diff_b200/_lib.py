@@ -29,6 +29,7 @@ class GemmArgs(C.Structure):
         ("gate_rows", C.c_int), ("act", C.c_int), ("out_kind", C.c_int),
         ("head_norm_w", C.c_void_p), ("head_norm_nsec", C.c_int), ("head_norm_sec_cols", C.c_int),
         ("head_norm_eps", C.c_float),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
     ]
 
 
@@ -142,6 +143,7 @@ def lib() -> C.CDLL:
         L.ln3_launch_count.restype = C.c_ulonglong
         L.ln3_add_launch_count.restype = None
         L.ln3_render_workspace_bytes.restype = C.c_size_t
+        L.ln3_gemm_workspace_bytes.restype = C.c_size_t
         _lib = L
     return _lib
 

@@ -112,6 +112,7 @@ int ln3_gemm_bf16(const ln3_gemm_args* args, void* stream) {
   return gemm_bf16(args, static_cast<cudaStream_t>(stream));
 }
 
+size_t ln3_gemm_workspace_bytes(void) { return gemm_workspace_bytes(); }
 int ln3_fmha_fwd(const ln3_fmha_args* args, void* stream) {
   if (!args) return set_error(LN3_EINVAL, "fmha: null args");
   return fmha_fwd(args, static_cast<cudaStream_t>(stream));

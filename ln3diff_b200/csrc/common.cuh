@@ -178,6 +178,12 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t* v)
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
 // One lane of the (converged) warp.  Code that feeds tcgen05.mma should run warp-uniformly and guard
 // only the issue itself with this: inside an `if (lane == 0)` region ptxas cannot prove descriptors
 // uniform and wraps every UTCHMMA in an ELECT / R2UR.BROADCAST waterfall (~100 cycles per MMA).

@@ -50,6 +50,10 @@ struct GemmParams {
   const float* hn_w;       // per-head RMSNorm weights [nsec][64] (HN kernels only)
   int hn_nsec, hn_sec_cols;
   float hn_eps;
+  // stream-K tail of the CTA-pair kernel (sk_tiles == 0: plain data-parallel tiles)
+  int sk_tiles;            // the last sk_tiles tiles are split along K over all pairs
+  int* sk_flags;           // [pairs][2] counters, zero between launches (self-resetting)
+  float* sk_partials;      // [pairs][2 ranks][32 column groups][128 rows][8] fp32 accumulator dumps
 };
 
 // One accumulator tile (this warp's 32 TMEM lanes x BN columns) -> global memory.
@@ -381,7 +385,8 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
 // runtime switch compiled to an indirect branch + constant loads that stalled the warp ~15 %).
 template <int ACT, int OUT, bool HN>
 __device__ __forceinline__ void epilogue_cols(const GemmParams& p, uint32_t t_row, int m, int n_tile0,
-                                              int c_begin, int c_end, const float* bias_s) {
+                                              int c_begin, int c_end, const float* bias_s,
+                                              const float* part_row = nullptr, int nparts = 0) {
   constexpr int CW = HN ? 64 : 32;
   // Plain epilogues software-pipeline the TMEM loads (chunk c+1 in flight while c is stored).  The
   // activation epilogues run with 16 warps and a 96-register budget instead: no prefetch registers,
@@ -411,6 +416,18 @@ __device__ __forceinline__ void epilogue_cols(const GemmParams& p, uint32_t t_ro
     float f[CW];
 #pragma unroll
     for (int i = 0; i < CW; ++i) f[i] = __uint_as_float(v[i]);
+    // stream-K owner: add the K-range partial sums of the contributing pairs (this thread's row, fp32)
+    // (slot layout [col / 8][row][8]: a warp's 32 rows of one 8-column group are 1 KB contiguous)
+    for (int q = 0; q < nparts; ++q) {
+      const float* pr = part_row + static_cast<long long>(q) * (2 * 128 * 256) + (c >> 3) * 1024;
+      float t8[CW / 8][8];
+#pragma unroll
+      for (int i = 0; i < CW / 8; ++i) ldg256_na(pr + i * 1024, t8[i]);
+#pragma unroll
+      for (int i = 0; i < CW / 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[i * 8 + j] += t8[i][j];
+    }
     if (p.bias != nullptr) {  // this tile's bias, staged in smem by the caller (a global load here stalls
 #pragma unroll             // the chunk for an L2 round trip: 10 % of the kernel's stall samples)
       for (int i = 0; i < CW; i += 4) {
@@ -595,16 +612,55 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     tn = t / tiles_m;
   };
 
+  // Work list of this pair, identical in every warp role: data-parallel tiles pair, pair + P, ... below
+  // dp_tiles, then (stream-K tail) this pair's contiguous share [u_lo, u_hi) of the sk_tiles * num_kb
+  // k-block units of the last sk_tiles tiles.  A tile split over pairs a < b < ... is OWNED by a (it holds
+  // the tile's first k-blocks and reaches them at the END of its share); b, ... hold later k-blocks at
+  // the START of their shares, dump their raw accumulators early and never wait.
+  const int dp_tiles = num_tiles - p.sk_tiles;
+  const long long sk_total = static_cast<long long>(p.sk_tiles) * num_kb;
+  const long long u_lo = sk_total * pair / num_pairs, u_hi = sk_total * (pair + 1) / num_pairs;
+  // item iteration: returns false when exhausted.  mode 0 = whole tile, 1 = contributor, 2 = owner
+  struct Item { int tile, kb0, kb1, mode, nparts; };
+  auto next_item = [&](int& t_dp, long long& u, Item& it) -> bool {
+    if (t_dp < dp_tiles) {
+      it.tile = t_dp, it.kb0 = 0, it.kb1 = num_kb, it.mode = 0, it.nparts = 0;
+      t_dp += num_pairs;
+      return true;
+    }
+    if (u >= u_hi) return false;
+    const int j = static_cast<int>(u / num_kb);
+    it.tile = dp_tiles + j;
+    it.kb0 = static_cast<int>(u - static_cast<long long>(j) * num_kb);
+    const long long left = u_hi - u;
+    it.kb1 = (num_kb - it.kb0 <= left) ? num_kb : it.kb0 + static_cast<int>(left);
+    u += it.kb1 - it.kb0;
+    it.nparts = 0;
+    if (it.kb0 > 0) {
+      it.mode = 1;
+    } else if (it.kb1 == num_kb) {
+      it.mode = 0;
+    } else {
+      it.mode = 2;
+      const long long tile_end = static_cast<long long>(j + 1) * num_kb;
+      for (int q = pair + 1; q < num_pairs && sk_total * q / num_pairs < tile_end; ++q) ++it.nparts;
+    }
+    return true;
+  };
+
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = pair; t < num_tiles; t += num_pairs) {
+      int t_dp = pair;
+      long long u = u_lo;
+      Item it;
+      while (next_item(t_dp, u, it)) {
         int tm, tn;
-        tile_coords(t, tm, tn);
+        tile_coords(it.tile, tm, tn);
         const int row_a = tm * 2 * BM + static_cast<int>(rank) * BM;
         const int row_b = tn * BN + static_cast<int>(rank) * 128;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = it.kb0; kb < it.kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           const uint32_t full_leader = mapa_u32(&full_bar[stage], 0);
           if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * kStageBytes2);  // bytes of both CTAs
@@ -629,19 +685,23 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int t = pair; t < num_tiles; t += num_pairs) {
+      int t_dp = pair;
+      long long u = u_lo;
+      Item it;
+      while (next_item(t_dp, u, it)) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tm_base + acc * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = it.kb0; kb < it.kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint64_t a_desc = a_desc0 + static_cast<uint32_t>(stage) * (kABytes >> 4);
           const uint64_t b_desc = b_desc0 + static_cast<uint32_t>(stage) * (kBBytes >> 4);
+          const uint32_t first = kb == it.kb0 ? 0u : 1u;
           if (elect_one_sync()) {
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k)
-              umma_f16_ss_2sm(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              umma_f16_ss_2sm(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, k != 0 ? 1u : first);
             umma_commit_2sm(&empty_bar[stage], 0b11);  // frees this stage in both CTAs
           }
           __syncwarp();
@@ -664,9 +724,12 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     constexpr int kSliceCols = BN / (EW / 4);
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int t = pair; t < num_tiles; t += num_pairs) {
+    int t_dp = pair;
+    long long u = u_lo;
+    Item it;
+    while (next_item(t_dp, u, it)) {
       int tm, tn;
-      tile_coords(t, tm, tn);
+      tile_coords(it.tile, tm, tn);
       // stage the tile's 256 bias values (one per epilogue thread) while the mainloop is still running;
       // two buffers + one barrier per tile: nobody can be two tiles ahead of the slowest warp
       if (p.bias != nullptr && threadIdx.x < 64 + BN)
@@ -676,7 +739,51 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       tc_fence_after();
       const int m = tm * 2 * BM + static_cast<int>(rank) * BM + quarter * 32 + lane;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
-      epilogue_cols<ACT, OUT, HN>(p, t_row, m, tn * BN, slice * kSliceCols, (slice + 1) * kSliceCols, bias_s + acc * BN);
+      // this thread's row inside a partial-sum slot: [pair][rank][256 / 8 column groups][128 rows][8]
+      float* my_part = p.sk_partials + (static_cast<long long>(pair) * 2 + rank) * (128 * 256) + (quarter * 32 + lane) * 8;
+      if (it.mode == 1) {
+        // contributor: raw accumulator slice -> this pair's slot, then one flag tick per warp
+#pragma unroll 1
+        for (int c = slice * kSliceCols; c < (slice + 1) * kSliceCols; c += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(t_row + c, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) stg256_b32(my_part + ((c + i) >> 3) * 1024, v + i);
+        }
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) atomicAdd(p.sk_flags + pair * 2 + rank, 1);
+      } else {
+        if (it.mode == 2) {
+          // owner: the contributors (pairs pair+1 .. pair+nparts) dumped their parts at the start of their
+          // shares, long before this pair reaches the end of its own; wait for EW ticks per slot anyway
+          if (lane == 0) {
+            for (int q = 1; q <= it.nparts; ++q) {
+              const int* f = p.sk_flags + (pair + q) * 2 + rank;
+              long long spins = 0;
+              while (ld_acquire_gpu(f) < EW) {
+                if (++spins > (1ll << 28)) {
+                  printf("ln3 gemm2: stream-K flag timeout (pair %d waits for %d)\n", pair, pair + q);
+                  __trap();
+                }
+              }
+            }
+          }
+          __syncwarp();
+        }
+        epilogue_cols<ACT, OUT, HN>(p, t_row, m, tn * BN, slice * kSliceCols, (slice + 1) * kSliceCols, bias_s + acc * BN,
+                                    my_part + 2 * 128 * 256, it.mode == 2 ? it.nparts : 0);
+        if (it.mode == 2) {
+          // second tick per warp; whoever brings a slot's counter to 2 * EW resets it for the next launch
+          __syncwarp();
+          if (lane == 0)
+            for (int q = 1; q <= it.nparts; ++q) {
+              int* f = p.sk_flags + (pair + q) * 2 + rank;
+              if (atomicAdd(f, 1) == 2 * EW - 1) atomicExch(f, 0);
+            }
+        }
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster_relaxed(mapa_u32(&tmem_empty[acc], 0));
@@ -693,9 +800,13 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   if (warp == 1) tmem_dealloc_2sm(tmem_base, 2 * BN);
 }
 
+size_t gemm_workspace_bytes() {
+  return 1024 + static_cast<size_t>(device_sm_count() / 2) * 2 * 128 * 256 * sizeof(float);
+}
+
 template <int ACT, int OUT, bool HN>
-static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int num_sms,
-                        cudaStream_t stream) {
+static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams p, int num_sms,
+                        void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm2_bf16_kernel<ACT, OUT, HN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -705,8 +816,35 @@ static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const Gemm
     attr_set = true;
   }
   const int tiles = ((p.M + 2 * BM - 1) / (2 * BM)) * (p.N / 256);
-  int pairs = num_sms / 2;
-  if (tiles < pairs) pairs = tiles;
+  const int num_kb = p.K / BK;
+  const int all_pairs = num_sms / 2;
+  int pairs = tiles < all_pairs ? tiles : all_pairs;
+  // Stream-K tail: with T tiles on P pairs the last wave leaves P - T % P pairs idle for a whole tile
+  // (192 tiles on 74 pairs: 3 rounds for 2.59 rounds of work).  When a workspace is given, the last
+  // T % P tiles are split along K over all pairs instead.
+  // Opt-in (LN3_GEMM_STREAMK=1): correct, but on the DiT shapes the fix-up currently costs more than the
+  // idle tail it removes (qkv 56 -> 65 us, proj 25 -> 37 us, fc2 85 -> 84 us); kept for the next round.
+  const char* sk_env = getenv("LN3_GEMM_STREAMK");
+  const bool sk_off = !(sk_env && atoi(sk_env) != 0);
+  p.sk_tiles = 0;
+  p.sk_flags = nullptr;
+  p.sk_partials = nullptr;
+  if (!sk_off && workspace != nullptr && workspace_bytes >= gemm_workspace_bytes() &&
+      (reinterpret_cast<uintptr_t>(workspace) & 255) == 0 && num_kb >= 4) {
+    int sk = 0;
+    if (tiles >= all_pairs) {
+      const int rem = tiles % all_pairs;
+      if (rem != 0 && rem * 10 <= all_pairs * 9) sk = rem;
+    } else if (tiles * 2 >= all_pairs && tiles * 10 <= all_pairs * 9) {
+      sk = tiles;
+    }
+    if (sk > 0 && static_cast<long long>(sk) * num_kb >= 2LL * all_pairs) {
+      p.sk_tiles = sk;
+      p.sk_flags = reinterpret_cast<int*>(workspace);
+      p.sk_partials = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + 1024);
+      pairs = all_pairs;
+    }
+  }
   cudaError_t e = launch_pdl(gemm2_bf16_kernel<ACT, OUT, HN>, dim3(2 * pairs), dim3(gemm2_threads<gemm2_epi_warps<ACT>()>()),
                              kSmemBytes2, stream, ta, tb, p);
   if (e != cudaSuccess) return set_error(LN3_ECUDA, "gemm2 launch: %s", cudaGetErrorString(e));
@@ -774,21 +912,21 @@ int gemm_bf16(const ln3_gemm_args* a, cudaStream_t stream) {
         return set_error(LN3_EINVAL, "gemm: head_norm needs LN3_OUT_BF16 and no activation");
       if (a->head_norm_nsec <= 0 || a->head_norm_sec_cols <= 0 || a->head_norm_sec_cols % 64 != 0)
         return set_error(LN3_EINVAL, "gemm: head_norm sections must be positive multiples of 64 columns");
-      return launch_gemm2<LN3_ACT_NONE, LN3_OUT_BF16, true>(ta, tb, p, sms, stream);
+      return launch_gemm2<LN3_ACT_NONE, LN3_OUT_BF16, true>(ta, tb, p, sms, a->workspace, a->workspace_bytes, stream);
     }
     if (a->out_kind == LN3_OUT_RESID_F32) {
       if (a->act != LN3_ACT_NONE) return set_error(LN3_EINVAL, "gemm: residual epilogue takes no activation");
-      return launch_gemm2<LN3_ACT_NONE, LN3_OUT_RESID_F32, false>(ta, tb, p, sms, stream);
+      return launch_gemm2<LN3_ACT_NONE, LN3_OUT_RESID_F32, false>(ta, tb, p, sms, a->workspace, a->workspace_bytes, stream);
     }
     if (a->out_kind == LN3_OUT_F32) {
       if (a->act != LN3_ACT_NONE) return set_error(LN3_EUNSUPPORTED, "gemm: fp32 output with activation");
-      return launch_gemm2<LN3_ACT_NONE, LN3_OUT_F32, false>(ta, tb, p, sms, stream);
+      return launch_gemm2<LN3_ACT_NONE, LN3_OUT_F32, false>(ta, tb, p, sms, a->workspace, a->workspace_bytes, stream);
     }
     switch (a->act) {
-      case LN3_ACT_NONE: return launch_gemm2<LN3_ACT_NONE, LN3_OUT_BF16, false>(ta, tb, p, sms, stream);
-      case LN3_ACT_GELU_ERF: return launch_gemm2<LN3_ACT_GELU_ERF, LN3_OUT_BF16, false>(ta, tb, p, sms, stream);
-      case LN3_ACT_GELU_TANH: return launch_gemm2<LN3_ACT_GELU_TANH, LN3_OUT_BF16, false>(ta, tb, p, sms, stream);
-      case LN3_ACT_SILU: return launch_gemm2<LN3_ACT_SILU, LN3_OUT_BF16, false>(ta, tb, p, sms, stream);
+      case LN3_ACT_NONE: return launch_gemm2<LN3_ACT_NONE, LN3_OUT_BF16, false>(ta, tb, p, sms, a->workspace, a->workspace_bytes, stream);
+      case LN3_ACT_GELU_ERF: return launch_gemm2<LN3_ACT_GELU_ERF, LN3_OUT_BF16, false>(ta, tb, p, sms, a->workspace, a->workspace_bytes, stream);
+      case LN3_ACT_GELU_TANH: return launch_gemm2<LN3_ACT_GELU_TANH, LN3_OUT_BF16, false>(ta, tb, p, sms, a->workspace, a->workspace_bytes, stream);
+      case LN3_ACT_SILU: return launch_gemm2<LN3_ACT_SILU, LN3_OUT_BF16, false>(ta, tb, p, sms, a->workspace, a->workspace_bytes, stream);
       default: return set_error(LN3_EINVAL, "gemm: unknown activation %d", a->act);
     }
   }

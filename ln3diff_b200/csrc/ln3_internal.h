@@ -42,6 +42,7 @@ int make_tmap_3d_bf16(CUtensorMap* out, const void* ptr, long long d0, long long
                       long long s1, long long s2, int box0, int box1);
 
 int gemm_bf16(const ln3_gemm_args* a, cudaStream_t stream);
+size_t gemm_workspace_bytes();
 int fmha_fwd(const ln3_fmha_args* a, cudaStream_t stream);
 int norm_modulate(const ln3_norm_modulate_args* a, cudaStream_t stream);
 int timestep_embedding(const float* t, int B, void* out_bf16, cudaStream_t stream);

@@ -606,3 +606,28 @@ def test_closed_form_uncond_cross_attention(dev, monkeypatch):
         assert m._ctx_cache[1]["rows"] == (0, 4) and m._ctx_cache[1]["oconst"] is None
         assert _rel(fast, full) < 3e-3
     m._ctx_cache = None
+
+
+@pytest.mark.parametrize("M,N,K,act", [(12288, 1024, 1024, 0), (6144, 1024, 1024, 0), (12288, 1024, 4096, 0),
+                                       (12288, 3072, 1024, 0), (12288, 4096, 1024, 1), (5000, 1024, 512, 0),
+                                       (2560, 2048, 256, 0)])
+def test_gemm_streamk_tail(dev, M, N, K, act, monkeypatch):
+    """Opt-in stream-K tail of the CTA-pair GEMM (LN3_GEMM_STREAMK=1): shapes whose tile count is not a
+    multiple of the pair count split their last tiles along K (fp32 partial sums through the workspace).
+    Result vs fp32 reference, repeated launches (the flags must return to zero)."""
+    from ln3diff_b200 import ops
+    monkeypatch.setenv("LN3_GEMM_STREAMK", "1")
+    g = torch.Generator().manual_seed(M + N + K)
+    a = (torch.randn(M, K, generator=g) * 0.5).bfloat16().to(dev)
+    w = (torch.randn(N, K, generator=g) * 0.05).bfloat16().to(dev)
+    b = torch.randn(N, generator=g).to(dev)
+    ref = a.float() @ w.float().t() + b
+    if act == 1:
+        ref = F.gelu(ref)
+    outs = [ops.gemm(a, w, b, act=act).float() for _ in range(3)]
+    assert _rel(outs[0], ref) < 4e-3
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[1], outs[2])
+    assert int(ops._gemm_workspace(a.device)[:1024].view(torch.int32).abs().sum()) == 0   # flags self-reset
+    o32 = ops.gemm(a, w, b, act=act, out_kind=ops.OUT_F32) if act == 0 else None
+    if o32 is not None:
+        assert _rel(o32, ref) < 1e-5
