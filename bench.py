@@ -299,7 +299,7 @@ def run_ours(args):
         roofline = {"kernel": "ln3::gemm2_bf16_kernel (tcgen05 cta_group::2, 256x256x64 per CTA pair, fused epilogues)",
                     "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                     "frac": achieved / peak_tf, "peak_source": peak_src,
-                    "traffic": 54.65e6,  # dram read+write of the captured qkv launch (profiles/r1_ncu_gemm_pair_v0.txt)
+                    "traffic": 69.57e6,  # dram read+write of the captured qkv launch (profiles/r1_ncu_gemm_pair_v1.txt)
                     "launches_measured": len(big), "avg_launch_us": 1e3 * gemm_ms / max(len(big), 1),
                     "flops_per_launch_avg": gemm_fl / max(len(big), 1),
                     "note": "events add launch gaps; gemm share of the forward in profiles/"}
