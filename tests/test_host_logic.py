@@ -123,3 +123,45 @@ def test_orbit_cameras_are_valid_rigid_transforms():
     R = cams[:, :16].reshape(5, 4, 4)[:, :3, :3]
     assert torch.allclose(R @ R.transpose(1, 2), torch.eye(3).expand(5, 3, 3), atol=1e-5)
     assert torch.allclose(torch.linalg.det(R), torch.ones(5), atol=1e-5)
+
+
+def test_overlay_routes_reference_import_names(tmp_path):
+    """ln3diff_b200.overlay: the reference's import names of the mirrored modules resolve to this package,
+    everything else keeps resolving to the (here: fake) reference checkout on sys.path."""
+    import importlib
+    import sys
+    from ln3diff_b200 import overlay
+    for pkg in ("dit", "sgm/modules/diffusionmodules", "nsr/volumetric_rendering", "guided_diffusion"):
+        d = tmp_path
+        for part in pkg.split("/"):
+            d = d / part
+            d.mkdir(exist_ok=True)
+            (d / "__init__.py").write_text("")
+    (tmp_path / "dit" / "norm.py").write_text("WHO = 'reference'\n")
+    (tmp_path / "dit" / "dit_trilatent.py").write_text("WHO = 'reference'\n")
+    (tmp_path / "nsr" / "train_util_diffusion.py").write_text("WHO = 'reference'\n")
+    saved = {k: sys.modules.pop(k) for k in list(sys.modules) if k.split(".")[0] in ("dit", "sgm", "nsr", "guided_diffusion", "transport")}
+    sys.path.insert(0, str(tmp_path))
+    overlay.install()
+    try:
+        import ln3diff_b200.dit.dit_trilatent as mirror
+        assert importlib.import_module("dit.dit_trilatent") is mirror                 # mirrored name -> this package
+        assert importlib.import_module("dit.dit_trilatent").DiT_models is mirror.DiT_models
+        assert importlib.import_module("dit.norm").WHO == "reference"                 # not mirrored -> reference file
+        assert importlib.import_module("nsr.train_util_diffusion").WHO == "reference"
+        s = importlib.import_module("sgm.modules.diffusionmodules.sampling")
+        assert s.__name__ == "ln3diff_b200.sgm.modules.diffusionmodules.sampling" and hasattr(s, "EulerEDMSampler")
+        r = importlib.import_module("nsr.volumetric_rendering.renderer")
+        assert r.ImportanceRenderer.__module__.startswith("ln3diff_b200.")
+        t = importlib.import_module("transport")
+        assert hasattr(t, "create_transport") and importlib.import_module("transport.transport").__name__.startswith("ln3diff_b200.")
+        from guided_diffusion.respace import SpacedDiffusion                          # noqa: F401  (from-import form)
+        assert SpacedDiffusion.__module__.startswith("ln3diff_b200.")
+    finally:
+        overlay.uninstall()
+        sys.path.remove(str(tmp_path))
+        for k in list(sys.modules):
+            if k.split(".")[0] in ("dit", "sgm", "nsr", "guided_diffusion", "transport"):
+                del sys.modules[k]
+        sys.modules.update(saved)
+    assert overlay._finder is None
