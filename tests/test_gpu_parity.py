@@ -631,3 +631,33 @@ def test_gemm_streamk_tail(dev, M, N, K, act, monkeypatch):
     o32 = ops.gemm(a, w, b, act=act, out_kind=ops.OUT_F32) if act == 0 else None
     if o32 is not None:
         assert _rel(o32, ref) < 1e-5
+
+
+def test_dit_full_size_properties(dev):
+    """BASELINE configs[1] size (DiT-L/2, 16 samples per forward), where the CPU oracle is too slow: properties
+    that do not depend on a reference output.  (1) samples are independent: permuting the batch permutes the
+    output bit-exactly (every kernel reduces each row in a fixed order); (2) a CUDA-graph replay equals the
+    eager launch sequence bit-exactly; (3) a sample's output does not depend on its batch neighbours; (4) the
+    CFG combination of the fused sampler update equals uc + s (c - uc) on the forward's own outputs."""
+    from ln3diff_b200 import ops
+    from ln3diff_b200.utils import build_t23d
+    m = build_t23d("DiT-L/2", device=dev)
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(16, 12, 32, 32, generator=g).to(dev)
+    t = torch.randint(0, 1000, (16,), generator=g).float().to(dev)
+    ctx = torch.randn(16, 77, 768, generator=g).to(dev)
+    out = m(x, t, ctx).clone()
+    assert torch.isfinite(out).all() and out.shape == (16, 12, 32, 32)
+    perm = torch.randperm(16, generator=g).to(dev)
+    assert torch.equal(m(x[perm].contiguous(), t[perm].contiguous(), ctx[perm].contiguous()), out[perm])
+    gr = m.capture_graph(16, ctx)
+    gr.x.copy_(x)
+    gr.t.copy_(t)
+    gr.replay()
+    assert torch.equal(gr.out, out)
+    x2 = x.clone()
+    x2[1:] = torch.randn(15, 12, 32, 32, generator=g).to(dev)           # change every neighbour of sample 0
+    assert torch.equal(m(x2, t, ctx)[0], out[0])
+    coef = torch.tensor([[0.7, 1.0 - 6.5, 6.5, 0.0]] * 8).to(dev)          # x' = 0.7 x + (1-s) uc + s c
+    upd = ops.sampler_affine_update(x[:8].contiguous(), coef, out[:8].contiguous(), out[8:].contiguous())
+    assert _rel(upd, 0.7 * x[:8] + out[:8] + 6.5 * (out[8:] - out[:8])) < 1e-6
