@@ -82,8 +82,16 @@ struct FmhaParams {
 // buffered, so the TMA warp prefetches the next item's Q / K / V while the current item is still in its
 // softmax -- the per-CTA prologue (TMEM allocation, barrier init, first-load latency) is paid once per
 // SM instead of once per item (it was ~30 % of a self-attention item and most of a cross-attention one).
-template <int kPolyPer8, bool PINGPONG>
-__global__ void __launch_bounds__(kFmhaThreads, 1)
+// SPLIT = true: 16 softmax warps instead of 8 -- every 128-row tile is handled by TWO warpgroups, each
+// owning 64 of the 128 score columns of a block (= one 64-column P atom).  Four softmax warps per scheduler
+// instead of two cover each other's MUFU / barrier / TMEM latencies, and a thread holds 64 scores instead
+// of 128 (no spills, room to interleave).  The two halves of a row agree on the block maximum and the final
+// row sum through spare TMEM columns [384, 400) (lane = row, so partner warps address the same lanes).
+template <bool SPLIT>
+constexpr int fmha_threads() { return SPLIT ? 576 : kFmhaThreads; }
+
+template <int kPolyPer8, bool PINGPONG, bool SPLIT = false>
+__global__ void __launch_bounds__(fmha_threads<SPLIT>(), 1)
 fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_k2,
                 const __grid_constant__ CUtensorMap tmap_v2, const __grid_constant__ CUtensorMap tmap_o,
@@ -108,6 +116,9 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
+  constexpr int kSoftWarps = SPLIT ? 16 : 8;
+  constexpr int kTmaWarp = kSoftWarps, kMmaWarp = kSoftWarps + 1;
+  constexpr int kTileThreads = SPLIT ? 256 : 128;  // softmax threads per query tile
   const int nkv1 = (p.Lkv + kKT - 1) / kKT;  // with a second source Lkv is a multiple of 128
   const int nkv = nkv1 + (p.Lkv2 + kKT - 1) / kKT;
   const int nitems = p.B * p.H * p.nq;
@@ -134,8 +145,8 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       mbar_init(&q_full[i], 1);
       mbar_init(&q_empty[i], 1);
       mbar_init(&s_full[i], 1);
-      mbar_init(&s_empty[i], 128);
-      mbar_init(&p_full[i], 128);
+      mbar_init(&s_empty[i], kTileThreads);
+      mbar_init(&p_full[i], kTileThreads);
       mbar_init(&o_full[i], 1);
     }
     for (int i = 0; i < kKVStages; ++i) {
@@ -144,7 +155,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     }
     fence_barrier_init();
   }
-  if (warp == 9) {
+  if (warp == kMmaWarp) {
     tmem_alloc(tmem_slot, kFmhaTmemCols);
     tmem_relinquish();
   }
@@ -155,7 +166,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   pdl_wait();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 8) {
+  if (warp == kTmaWarp) {
     // ------------------------------------------------------------ TMA producer
     if ((tid & 31) == 0) {
       int it = 0, kst = 0, kph = 0;
@@ -182,7 +193,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == kMmaWarp) {
     // ------------------------------------------------------------ MMA issuer
     // The whole warp walks this loop with warp-uniform values (so descriptors live in uniform
     // registers); elect_one_sync() guards only the tcgen05 instructions themselves.
@@ -258,7 +269,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         if (++st == kKVStages) st = 0;
       }
     }
-  } else if (warp < 8) {
+  } else if (!SPLIT && warp < 8) {
     // ------------------------------------------------------------ softmax warpgroups
     const int t = warp >> 2;
     const int row = tid & 127;  // TMEM lane
@@ -420,12 +431,162 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     }
     if (PINGPONG && t == 0) named_bar_sync(1, 256);  // consume warpgroup 1's last hand-over
     if (row == 0 && o_store_pending) tma_store_wait_all();  // smem must outlive the bulk store
+  } else if (SPLIT && warp < 16) {
+    // ------------------------------------------------------------ softmax, two warpgroups per tile
+    const int t = warp >> 3;            // query tile
+    const int h = (warp >> 2) & 1;      // column half of every 128-column score block (= P atom)
+    const int row = (warp & 3) * 32 + (tid & 31);  // TMEM lane
+    const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const uint32_t tS = tmem_base + t * 128 + h * 64 + lane_off;
+    const uint32_t tO = tmem_base + 256 + t * 64 + lane_off;
+    const uint32_t tX = tmem_base + 384 + t * 8 + lane_off;   // exchange: [parity][half] max, [4 + half] sum
+    const uint32_t p_row = smem_u32(sP + (t * 2 + h) * kTileBytes) + row * 128;
+    const uint32_t o_row = smem_u32(sP + t * 2 * kTileBytes) + row * 128;
+    const int swz = row & 7;
+    int g = 0;
+    bool o_store_pending = false;
+    for (int w = blockIdx.x; w < nitems; w += gridDim.x) {
+      int q0, head, batch;
+      item_coords(w, q0, head, batch);
+      float m_ref = -INFINITY, l_run = 0.f;
+      for (int j = 0; j < nkv; ++j, ++g) {
+        const int kv_valid = (j < nkv1) ? p.Lkv - j * kKT : p.Lkv2 - (j - nkv1) * kKT;  // >= 1
+        const int my_valid = kv_valid - h * 64;                                          // of my 64 columns (may be <= 0)
+        mbar_wait(&s_full[t], g & 1);
+        tc_fence_after();
+        uint32_t s[64];
+        tmem_ld_32x32(tS + 0, s);
+        tmem_ld_32x32(tS + 32, s + 32);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(&s_empty[t]);  // the tensor core may overwrite S_t with the next block now
+        if (my_valid < 64) {
+#pragma unroll
+          for (int i = 0; i < 64; ++i)
+            if (i >= my_valid) s[i] = 0xff800000u;  // -inf
+        }
+        float mq[2];
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+          mq[a] = fmax3(__uint_as_float(s[32 * a]), __uint_as_float(s[32 * a + 1]), __uint_as_float(s[32 * a + 2]));
+#pragma unroll
+        for (int i = 3; i < 31; i += 2) {
+#pragma unroll
+          for (int a = 0; a < 2; ++a)
+            mq[a] = fmax3(mq[a], __uint_as_float(s[32 * a + i]), __uint_as_float(s[32 * a + i + 1]));
+        }
+        float mx = fmax3(mq[0], mq[1], fmaxf(__uint_as_float(s[31]), __uint_as_float(s[63])));
+        // the row's block maximum is the max over both halves: swap through TMEM (parity double buffer,
+        // one 256-thread named barrier per block)
+        tmem_st_32x1(tX + (g & 1) * 2 + h, __float_as_uint(mx));
+        tmem_st_wait();
+        tc_fence_before();
+        named_bar_sync(1 + t, 256);
+        tc_fence_after();
+        mx = fmaxf(mx, __uint_as_float(tmem_ld_32x1(tX + (g & 1) * 2 + (1 - h))));
+        tmem_ld_wait();
+        const float m_cand = mx * p.scale_log2;
+        float alpha = 1.f;
+        bool need = false;
+        if (j == 0) {
+          m_ref = m_cand;
+        } else if (m_cand > m_ref + kRescaleThreshold) {
+          need = true;
+          alpha = fast_exp2(m_ref - m_cand);
+          m_ref = m_cand;
+          l_run *= alpha;
+        }
+        if (j == 0 && g > 0) {  // previous item's O tile left the P buffer? (one barrier per item)
+          if (h == 0 && row == 0 && o_store_pending) tma_store_wait_read();
+          named_bar_sync(3 + t, 256);
+        }
+        // my P atom is read by k-steps 4h .. 4h+3 of the previous P_t V: wait for the whole MMA
+        if (g > 0) mbar_wait(&o_full[t], (g - 1) & 1);
+        const int c_end = my_valid >= 64 ? 64 : (my_valid <= 0 ? 0 : (my_valid + 15) & ~15);
+        float rs = 0.f;
+        auto exp_store = [&](auto full_tag) {
+          constexpr bool FULL = decltype(full_tag)::value;
+#pragma unroll
+          for (int c = 0; c < 64; c += 8) {
+            if (!FULL && c >= c_end) break;
+            float e[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float x = fmaf(__uint_as_float(s[c + i]), p.scale_log2, -m_ref);
+              e[i] = (i < kPolyPer8) ? exp2_poly(x) : fast_exp2(x);
+            }
+            rs += ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));
+            const uint32_t addr = p_row + (((c >> 3) ^ swz) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pack_bf16x2(e[0], e[1])),
+                         "r"(pack_bf16x2(e[2], e[3])), "r"(pack_bf16x2(e[4], e[5])),
+                         "r"(pack_bf16x2(e[6], e[7]))
+                         : "memory");
+          }
+        };
+        if (my_valid >= 64) exp_store(std::true_type{});
+        else exp_store(std::false_type{});
+        l_run += rs;
+        if (j > 0 && __any_sync(0xffffffffu, need)) {
+          // both halves took the same decision (same combined maximum); half 0 rescales O_t in place
+          tc_fence_after();
+          if (h == 0) {
+#pragma unroll
+            for (int c = 0; c < kHD; c += 32) {
+              uint32_t v[32];
+              tmem_ld_32x32(tO + c, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+              tmem_st_32x32(tO + c, v);
+            }
+            tmem_st_wait();
+          }
+        }
+        fence_proxy_async_smem();  // P (generic-proxy stores) -> visible to the tensor core
+        tc_fence_before();
+        mbar_arrive(&p_full[t]);
+      }
+      // ---- epilogue: total row sum = both halves, each half normalises and stores 32 of the 64 O columns
+      tmem_st_32x1(tX + 4 + h, __float_as_uint(l_run));
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_wait(&o_full[t], (g - 1) & 1);
+      named_bar_sync(1 + t, 256);
+      tc_fence_after();
+      const float l_tot = l_run + __uint_as_float(tmem_ld_32x1(tX + 4 + (1 - h)));
+      tmem_ld_wait();
+      const float inv = 1.f / l_tot;
+      {
+        uint32_t v[32];
+        tmem_ld_32x32(tO + h * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          const uint32_t addr = o_row + ((((h * 32 + i) >> 3) ^ swz) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr),
+                       "r"(pack_bf16x2(__uint_as_float(v[i]) * inv, __uint_as_float(v[i + 1]) * inv)),
+                       "r"(pack_bf16x2(__uint_as_float(v[i + 2]) * inv, __uint_as_float(v[i + 3]) * inv)),
+                       "r"(pack_bf16x2(__uint_as_float(v[i + 4]) * inv, __uint_as_float(v[i + 5]) * inv)),
+                       "r"(pack_bf16x2(__uint_as_float(v[i + 6]) * inv, __uint_as_float(v[i + 7]) * inv))
+                       : "memory");
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();  // the TMEM reads above precede the next item's first P_t V (accumulate = 0)
+      named_bar_sync(3 + t, 256);
+      if (h == 0 && row == 0) {
+        tma_store_3d(sP + t * 2 * kTileBytes, &tmap_o, head * kHD, q0 + t * kQT, batch);
+        tma_store_commit();
+        o_store_pending = true;
+      }
+    }
+    if (h == 0 && row == 0 && o_store_pending) tma_store_wait_all();  // smem must outlive the bulk store
   }
 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (warp == 9) tmem_dealloc(tmem_base, kFmhaTmemCols);
+  if (warp == kMmaWarp) tmem_dealloc(tmem_base, kFmhaTmemCols);
 }
 
 int fmha_fwd(const ln3_fmha_args* a, cudaStream_t stream) {
@@ -454,8 +615,12 @@ int fmha_fwd(const ln3_fmha_args* a, cudaStream_t stream) {
     set(fmha_fwd_kernel<2, false>); set(fmha_fwd_kernel<2, true>);
     set(fmha_fwd_kernel<3, false>); set(fmha_fwd_kernel<3, true>);
     set(fmha_fwd_kernel<4, false>); set(fmha_fwd_kernel<4, true>);
+    set(fmha_fwd_kernel<0, false, true>); set(fmha_fwd_kernel<2, false, true>);
     if (e != cudaSuccess) return set_error(LN3_ECUDA, "fmha: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    variant = v * 2 + ping;
+    // LN3_FMHA_SPLIT = 1: 16 softmax warps, each tile's score columns split over two warpgroups
+    const char* sp = getenv("LN3_FMHA_SPLIT");
+    const int split = (sp && atoi(sp) != 0) ? 1 : 0;
+    variant = split ? 100 + (v == 2 ? 2 : 0) : v * 2 + ping;
   }
   if (a->k2 != nullptr || a->v2 != nullptr) {
     if (!a->k2 || !a->v2 || a->Lkv2 <= 0) return set_error(LN3_EINVAL, "fmha: k2/v2/Lkv2 must be given together");
@@ -500,6 +665,8 @@ int fmha_fwd(const ln3_fmha_args* a, cudaStream_t stream) {
     LN3_FMHA_CASE(0, 0) LN3_FMHA_CASE(0, 1) LN3_FMHA_CASE(2, 0) LN3_FMHA_CASE(2, 1)
     LN3_FMHA_CASE(3, 0) LN3_FMHA_CASE(3, 1) LN3_FMHA_CASE(4, 0) LN3_FMHA_CASE(4, 1)
 #undef LN3_FMHA_CASE
+    case 100: le = launch_pdl(fmha_fwd_kernel<0, false, true>, dim3(grid), dim3(fmha_threads<true>()), kFmhaSmem, stream, tq, tk, tv, tk2, tv2, to, p); break;
+    case 102: le = launch_pdl(fmha_fwd_kernel<2, false, true>, dim3(grid), dim3(fmha_threads<true>()), kFmhaSmem, stream, tq, tk, tv, tk2, tv2, to, p); break;
     default: return set_error(LN3_EINVAL, "fmha: bad variant");
   }
   cudaError_t e = le != cudaSuccess ? le : cudaGetLastError();

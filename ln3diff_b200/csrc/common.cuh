@@ -172,6 +172,15 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t* v)
       "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
       : "memory");
 }
+// one 32-bit TMEM column (lane = thread's row): scratch exchange between warps that share TMEM lanes
+__device__ __forceinline__ void tmem_st_32x1(uint32_t taddr, uint32_t v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t tmem_ld_32x1(uint32_t taddr) {
+  uint32_t v;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr) : "memory");
+  return v;
+}
 // Programmatic dependent launch: the kernel may start while its stream predecessor is still running;
 // pdl_wait() returns once every prerequisite grid has completed and its memory is visible (a no-op for a
 // normal launch), pdl_launch_dependents() lets the NEXT kernel's CTAs be scheduled as ours retire.
