@@ -18,6 +18,7 @@ import torch.nn as nn
 
 from .. import _lib, ops
 from .._lib import NORM_LAYER, NORM_NONE, NORM_RMS
+from .dit_trilatent import _attention_rows
 from .dit_models_xformers import (Attention, CaptionEmbedder, MemoryEfficientCrossAttention, T2IFinalLayer,
                                   TimestepEmbedder, _FusedMLP, _PatchEmbed, _RMSNormParam,
                                   get_2d_sincos_pos_embed)
@@ -178,7 +179,15 @@ class DiT_I23D_PixelArt(nn.Module):
         for l, W in enumerate(P["blocks"]):
             ops.gemm(clip, W["ckv_w"], out=ckv[l].view(B * Lc, 2 * D), head_norm=W["ck_norm"], head_norm_sec_cols=D)
             ops.gemm(dino, W["kv_w"], W["kv_b"], out=dkv[l].view(B * Lc, 2 * D), head_norm=W["k_norm"], head_norm_sec_cols=D)
-        out = dict(cls=cls, ckv=ckv, dkv=dkv)
+        out = dict(cls=cls, ckv=ckv, dkv=dkv, rows=(0, B), oconst=None)
+        # identical CLIP tokens (the all-zero unconditional half of forward_with_cfg): softmax over identical
+        # keys is uniform -> cross-attention output = to_out(v_row); see DiT_TriLatent._context_kv
+        rows = _attention_rows(ca[..., :1024])
+        if rows is not None:
+            oc = torch.empty(self.depth, B, D, device=dev, dtype=torch.bfloat16)
+            for l, W in enumerate(P["blocks"]):
+                ops.gemm(ckv[l][:, 0, D:].contiguous(), W["co_w"], W["co_b"], out=oc[l])
+            out.update(rows=rows, oconst=oc)
         self._ctx_cache = (key, out)
         return out
 
@@ -222,6 +231,8 @@ class DiT_I23D_PixelArt(nn.Module):
         xs = ops.patch_embed(x.float().contiguous(), P["pe_w"], P["pe_b"], P["pos"], out=ws["x"])
         x2 = xs.view(M, D)
         qkv3, att3, q3 = ws["qkv"].view(B, T, 3 * D), ws["att"].view(B, T, D), ws["q"].view(B, T, D)
+        (g0, g1), oconst = cx["rows"], cx["oconst"]
+        r0, r1 = g0 * T, g1 * T
         val, pend_gate = ws["v"], None   # deferred residuals (see dit_trilatent._forward_impl)
         for l, W in enumerate(P["blocks"]):
             mod = ws["mod"][l]
@@ -234,12 +245,14 @@ class DiT_I23D_PixelArt(nn.Module):
                      k2=dkv[:, :, :D], v2=dkv[:, :, D:])
             ops.gemm(ws["att"], W["proj_w"], W["proj_b"], out=val)
             ops.norm_modulate(x2, norm=NORM_NONE, out=ws["xb"], resid=val, resid_gate=sl(2), resid_gate_rows=T)
-            ops.gemm(ws["xb"], W["cq_w"], out=ws["q"], head_norm=W["cq_norm"], head_norm_sec_cols=D)
-            ckv = cx["ckv"][l]
-            ops.fmha(q3, ckv[:, :, :D], ckv[:, :, D:], H, out=att3)
-            ops.gemm(ws["att"], W["co_w"], W["co_b"], out=val)
+            if r1 > r0:
+                ops.gemm(ws["xb"][r0:r1], W["cq_w"], out=ws["q"][r0:r1], head_norm=W["cq_norm"], head_norm_sec_cols=D)
+                ckv = cx["ckv"][l]
+                ops.fmha(q3[g0:g1], ckv[g0:g1, :, :D], ckv[g0:g1, :, D:], H, out=att3[g0:g1])
+                ops.gemm(ws["att"][r0:r1], W["co_w"], W["co_b"], out=val[r0:r1])
             ops.norm_modulate(x2, norm=NORM_RMS, weight=W["n2_w"], eps=1e-5, shift=sl(3), scale=sl(4), mod_rows=T, out=ws["a"],
-                              resid=val)
+                              resid=val, resid_bcast=oconst[l] if oconst is not None else None, resid_bcast_rows=T,
+                              resid_rows=(r0, r1) if oconst is not None else None)
             ops.gemm(ws["a"], W["fc1_w"], W["fc1_b"], act=ops.ACT_GELU_ERF, out=ws["h"])
             ops.gemm(ws["h"], W["fc2_w"], W["fc2_b"], out=val)
             pend_gate = sl(5)

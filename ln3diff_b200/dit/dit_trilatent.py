@@ -26,6 +26,25 @@ def _closed_form_uncond() -> bool:
     return os.environ.get("LN3_UNCOND_CLOSED_FORM", "1") != "0"
 
 
+def _attention_rows(tokens: torch.Tensor):
+    """tokens (B, L, C) as the cross-attention sees them.  Returns (g0, g1): the contiguous block of samples
+    that needs real attention when the samples whose L tokens are all identical form a prefix and/or suffix
+    of the batch (both CFG layouts of the reference), else None.  One host sync; callers cache per context."""
+    B, L, _ = tokens.shape
+    if not _closed_form_uncond() or L < 2:
+        return None
+    same = (tokens == tokens[:, :1]).all(dim=2).all(dim=1).tolist()
+    g0 = 0
+    while g0 < B and same[g0]:
+        g0 += 1
+    g1 = B
+    while g1 > g0 and same[g1 - 1]:
+        g1 -= 1
+    if (g0 > 0 or g1 < B) and not any(same[g0:g1]):
+        return g0, g1
+    return None
+
+
 class DiT_TriLatent(nn.Module):
     """reference dit/dit_trilatent.py:22-143 (+ base dit_models_xformers.py:681-819)."""
 
@@ -190,20 +209,12 @@ class DiT_TriLatent(nn.Module):
         kv = ops.gemm(c2, P["kv_w"])  # (B*Lc, depth*2*D)
         kv = kv.view(B, Lc, self.depth, 2, self.embed_dim)
         out = dict(kv=kv, rows=(0, B), oconst=None)
-        if _closed_form_uncond() and Lc > 1:
-            c2v = c2.view(B, Lc, -1)
-            same = (c2v == c2v[:, :1]).all(dim=2).all(dim=1).tolist()     # one host sync per prompt batch
-            g0 = 0
-            while g0 < B and same[g0]:
-                g0 += 1
-            g1 = B
-            while g1 > g0 and same[g1 - 1]:
-                g1 -= 1
-            if (g0 > 0 or g1 < B) and not any(same[g0:g1]):
-                oc = torch.empty(self.depth, B, self.embed_dim, device=context.device, dtype=torch.bfloat16)
-                for l, W in enumerate(P["blocks"]):
-                    ops.gemm(kv[:, 0, l, 1].contiguous(), W["o_w"], W["o_b"], out=oc[l])
-                out = dict(kv=kv, rows=(g0, g1), oconst=oc)
+        rows = _attention_rows(c2.view(B, Lc, -1))                        # one host sync per prompt batch
+        if rows is not None:
+            oc = torch.empty(self.depth, B, self.embed_dim, device=context.device, dtype=torch.bfloat16)
+            for l, W in enumerate(P["blocks"]):
+                ops.gemm(kv[:, 0, l, 1].contiguous(), W["o_w"], W["o_b"], out=oc[l])
+            out = dict(kv=kv, rows=rows, oconst=oc)
         self._ctx_cache = (key, out)
         return out
 
@@ -445,7 +456,14 @@ class DiT_TriLatent_PixelArt(nn.Module):
         for l, W in enumerate(P["blocks"]):
             y = ops.norm_modulate(ca2, norm=NORM_RMS, weight=W["yn_w"], eps=1e-5)
             ops.gemm(y, W["ckv_w"], out=ckv[l].view(B * Lc, 2 * D))
-        out = dict(cls=cls, ckv=ckv)
+        out = dict(cls=cls, ckv=ckv, rows=(0, B), oconst=None)
+        # identical text tokens (the zero-embedding CFG half): closed-form cross-attention, see DiT_TriLatent
+        rows = _attention_rows(ca.float())
+        if rows is not None:
+            oc = torch.empty(self.depth, B, D, device=ca.device, dtype=torch.bfloat16)
+            for l, W in enumerate(P["blocks"]):
+                ops.gemm(ckv[l][:, 0, D:].contiguous(), W["co_w"], W["co_b"], out=oc[l])
+            out.update(rows=rows, oconst=oc)
         self._ctx_cache = (key, out)
         return out
 
@@ -488,6 +506,8 @@ class DiT_TriLatent_PixelArt(nn.Module):
         xs = ops.patch_embed(x.float().contiguous(), P["pe_w"], P["pe_b"], P["pos"], out=ws["x"])
         x2 = xs.view(M, D)
         qkv3, att3, q3 = ws["qkv"].view(B, T, 3 * D), ws["att"].view(B, T, D), ws["q"].view(B, T, D)
+        (g0, g1), oconst = cx["rows"], cx["oconst"]
+        r0, r1 = g0 * T, g1 * T
         val, pend_gate = ws["v"], None   # deferred residuals (see DiT_TriLatent._forward_impl)
         for l, W in enumerate(P["blocks"]):
             mod = ws["mod"][l]
@@ -498,12 +518,14 @@ class DiT_TriLatent_PixelArt(nn.Module):
             ops.fmha(qkv3[:, :, :D], qkv3[:, :, D:2 * D], qkv3[:, :, 2 * D:], H, out=att3)
             ops.gemm(ws["att"], W["proj_w"], W["proj_b"], out=val)
             ops.norm_modulate(x2, norm=NORM_NONE, out=ws["xb"], resid=val, resid_gate=sl(2), resid_gate_rows=T)
-            ops.gemm(ws["xb"], W["cq_w"], out=ws["q"])
-            ckv = cx["ckv"][l]
-            ops.fmha(q3, ckv[:, :, :D], ckv[:, :, D:], H, out=att3)
-            ops.gemm(ws["att"], W["co_w"], W["co_b"], out=val)
+            if r1 > r0:
+                ops.gemm(ws["xb"][r0:r1], W["cq_w"], out=ws["q"][r0:r1])
+                ckv = cx["ckv"][l]
+                ops.fmha(q3[g0:g1], ckv[g0:g1, :, :D], ckv[g0:g1, :, D:], H, out=att3[g0:g1])
+                ops.gemm(ws["att"][r0:r1], W["co_w"], W["co_b"], out=val[r0:r1])
             ops.norm_modulate(x2, norm=NORM_RMS, weight=W["n2_w"], eps=1e-5, shift=sl(3), scale=sl(4), mod_rows=T, out=ws["a"],
-                              resid=val)
+                              resid=val, resid_bcast=oconst[l] if oconst is not None else None, resid_bcast_rows=T,
+                              resid_rows=(r0, r1) if oconst is not None else None)
             ops.gemm(ws["a"], W["fc1_w"], W["fc1_b"], act=ops.ACT_GELU_ERF, out=ws["h"])
             ops.gemm(ws["h"], W["fc2_w"], W["fc2_b"], out=val)
             pend_gate = sl(5)

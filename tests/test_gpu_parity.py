@@ -661,3 +661,34 @@ def test_dit_full_size_properties(dev):
     coef = torch.tensor([[0.7, 1.0 - 6.5, 6.5, 0.0]] * 8).to(dev)          # x' = 0.7 x + (1-s) uc + s c
     upd = ops.sampler_affine_update(x[:8].contiguous(), coef, out[:8].contiguous(), out[8:].contiguous())
     assert _rel(upd, 0.7 * x[:8] + out[:8] + 6.5 * (out[8:] - out[:8])) < 1e-6
+
+
+def test_closed_form_uncond_cross_attention_pixart_models(dev, monkeypatch):
+    """Same identity in the PixArt-style denoisers (T23D DiT_TriLatent_PixelArt, I23D DiT_I23D_PixelArt): an
+    all-zero unconditional half has identical (zero) text / CLIP tokens."""
+    from ln3diff_b200.dit.dit_trilatent import DiT_models
+    from ln3diff_b200.utils import build_i23d
+    from oracle import fixtures as fx
+    g = torch.Generator().manual_seed(23)
+    x = torch.randn(4, 12, 32, 32, generator=g).to(dev)
+    mt = DiT_models[fx.T23D_PIXART_ARCH](input_size=32, num_classes=0, learn_sigma=False, in_channels=4,
+                                         context_dim=768, roll_out=True)
+    shapes = {k: tuple(v.shape) for k, v in mt.state_dict().items()}
+    mt.load_state_dict(fx.i23d_state_dict(shapes, mt.state_dict()["pos_embed"]))
+    mi = build_i23d(fx.I23D_ARCH)
+    cases = [(mt.to(dev), torch.tensor([3.0, 500.0, 3.0, 500.0]),
+              {"vector": torch.randn(2, 768, generator=g), "crossattn": torch.randn(2, 77, 768, generator=g)}),
+             (mi.to(dev), torch.tensor([0.1, 0.8, 0.1, 0.8]),
+              {"vector": torch.randn(2, 768, generator=g), "crossattn": torch.randn(2, 256, 2048, generator=g)})]
+    for m, t, c in cases:
+        ctx = {k: torch.cat([v, torch.zeros_like(v)]).to(dev) for k, v in c.items()}     # cond first, uc = 0
+        monkeypatch.setenv("LN3_UNCOND_CLOSED_FORM", "1")
+        m._ctx_cache = None
+        fast = m(x, t.to(dev), ctx).clone()
+        assert m._ctx_cache[1]["rows"] == (0, 2)
+        monkeypatch.setenv("LN3_UNCOND_CLOSED_FORM", "0")
+        m._ctx_cache = None
+        full = m(x, t.to(dev), ctx).clone()
+        assert m._ctx_cache[1]["oconst"] is None
+        assert _rel(fast, full) < 3e-3
+        m._ctx_cache = None
