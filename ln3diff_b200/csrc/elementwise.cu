@@ -387,25 +387,38 @@ patch_embed_k16_kernel(const ln3_patch_embed_args a) {
     }
   }
   __syncthreads();
-  for (int d = threadIdx.x; d < a.D; d += 256) {
-    float w[16];
-    const float4* wp = reinterpret_cast<const float4*>(a.weight + static_cast<long long>(d) * 16);
+  // a thread owns four consecutive output channels: 64 weights in registers, 128-bit pos_embed loads and
+  // token stores (the 4-byte version ran at 0.8 TB/s)
+  for (int d = threadIdx.x * 4; d < a.D; d += 1024) {
+    float w[4][16];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float4 v = __ldg(wp + i);
-      w[4 * i] = v.x, w[4 * i + 1] = v.y, w[4 * i + 2] = v.z, w[4 * i + 3] = v.w;
+    for (int j = 0; j < 4; ++j) {
+      const float4* wp = reinterpret_cast<const float4*>(a.weight + static_cast<long long>(d + j) * 16);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 v = __ldg(wp + i);
+        w[j][4 * i] = v.x, w[j][4 * i + 1] = v.y, w[j][4 * i + 2] = v.z, w[j][4 * i + 3] = v.w;
+      }
     }
-    const float bias = a.bias ? a.bias[d] : 0.f;
-    const int nl0 = tok0 % (3 * L);  // 3L is a multiple of kPeTok for every supported S, so no wrap inside a block
-#pragma unroll
+    float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (a.bias) bias = __ldg(reinterpret_cast<const float4*>(a.bias + d));
+    const int nl0 = tok0 % (3 * L);
+#pragma unroll 4
     for (int t = 0; t < kPeTok; ++t) {
       const int tok = tok0 + t;
-      float acc = bias;
+      float acc[4] = {bias.x, bias.y, bias.z, bias.w};
 #pragma unroll
-      for (int k = 0; k < 16; ++k) acc = fmaf(w[k], xin[t][k], acc);
+      for (int k = 0; k < 16; ++k) {
+        const float xv = xin[t][k];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] = fmaf(w[j][k], xv, acc[j]);
+      }
       if (tok < ntok) {
-        if (a.pos_embed) acc += __ldg(a.pos_embed + static_cast<long long>((nl0 + t) % (3 * L)) * a.D + d);
-        a.tokens[static_cast<long long>(tok) * a.D + d] = acc;
+        if (a.pos_embed) {
+          const float4 pe = __ldg(reinterpret_cast<const float4*>(a.pos_embed + static_cast<long long>((nl0 + t) % (3 * L)) * a.D + d));
+          acc[0] += pe.x, acc[1] += pe.y, acc[2] += pe.z, acc[3] += pe.w;
+        }
+        *reinterpret_cast<float4*>(a.tokens + static_cast<long long>(tok) * a.D + d) = make_float4(acc[0], acc[1], acc[2], acc[3]);
       }
     }
   }
@@ -416,7 +429,7 @@ int patch_embed(const ln3_patch_embed_args* a, cudaStream_t stream) {
   if (a->S % 2 || a->Cin <= 0 || a->Cin > 16 || a->D <= 0)
     return set_error(LN3_EINVAL, "patch_embed: need even S, 1 <= Cin <= 16");
   const int L = (a->S / 2) * (a->S / 2);
-  if (a->Cin == 4)
+  if (a->Cin == 4 && a->D % 4 == 0)
     patch_embed_k16_kernel<<<(a->B * 3 * L + kPeTok - 1) / kPeTok, 256, 0, stream>>>(*a);
   else
     patch_embed_kernel<<<a->B * 3 * L, 256, 0, stream>>>(*a);
@@ -429,6 +442,98 @@ int patch_embed(const ln3_patch_embed_args* a, cudaStream_t stream) {
 // ------------------------------------------------------------------ final layer
 // One warp per token: LN + modulate in registers, then 4*Cout dot products (warp reductions),
 // scattered into the unpatchified '(b, c*3+n, 2i+p, 2j+q)' layout.
+// Two tokens per warp: the 4*Cout weight rows are read once for both, and the 2 x 16 dot-product partials
+// are reduced with one 31-shuffle reduce-scatter (lane tk*16 + o ends up with output o of token tk) instead
+// of 32 five-step warp sums.  Requires 4*Cout == 16 (every release config: Cout = 4); other sizes take
+// the one-token kernel below.
+template <int NV>
+__global__ void __launch_bounds__(128)
+final_layer2_kernel(const ln3_final_layer_args a) {
+  const int P = a.S / 2, L = P * P;
+  const int ntok = a.B * 3 * L;
+  const int tok0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 2;
+  if (tok0 >= ntok) return;
+  const int lane = threadIdx.x & 31;
+  float4 v[2][NV];
+#pragma unroll
+  for (int tk = 0; tk < 2; ++tk) {
+    const int tok = tok0 + tk < ntok ? tok0 + tk : ntok - 1;
+    const int b = tok / (3 * L);
+    const float* x = a.x + static_cast<long long>(tok) * a.D;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[tk][i] = *reinterpret_cast<const float4*>(x + (i * 32 + lane) * 4);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) s += (v[tk][i].x + v[tk][i].y) + (v[tk][i].z + v[tk][i].w);
+    const float mean = warp_sum(s) / static_cast<float>(a.D);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float dx = v[tk][i].x - mean, dy = v[tk][i].y - mean, dz = v[tk][i].z - mean, dw = v[tk][i].w - mean;
+      q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+    }
+    const float rstd = rsqrtf(warp_sum(q) / static_cast<float>(a.D) + 1e-6f);
+    const float* sh = a.shift + static_cast<long long>(b) * a.mod_ld;
+    const float* sc = a.scale + static_cast<long long>(b) * a.mod_ld;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      float4 s1 = __ldg(reinterpret_cast<const float4*>(sc + c));
+      float4 s0 = __ldg(reinterpret_cast<const float4*>(sh + c));
+      if (a.scale_tab != nullptr) {
+        const float4 t1 = __ldg(reinterpret_cast<const float4*>(a.scale_tab + c));
+        const float4 t0 = __ldg(reinterpret_cast<const float4*>(a.shift_tab + c));
+        s1.x += t1.x; s1.y += t1.y; s1.z += t1.z; s1.w += t1.w;
+        s0.x += t0.x; s0.y += t0.y; s0.z += t0.z; s0.w += t0.w;
+      }
+      v[tk][i].x = fmaf((v[tk][i].x - mean) * rstd, 1.f + s1.x, s0.x);
+      v[tk][i].y = fmaf((v[tk][i].y - mean) * rstd, 1.f + s1.y, s0.y);
+      v[tk][i].z = fmaf((v[tk][i].z - mean) * rstd, 1.f + s1.z, s0.z);
+      v[tk][i].w = fmaf((v[tk][i].w - mean) * rstd, 1.f + s1.w, s0.w);
+    }
+  }
+  float acc[32];  // [tk * 16 + o]
+#pragma unroll
+  for (int o = 0; o < 16; ++o) {
+    const float* w = a.weight + static_cast<long long>(o) * a.D;
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float4 ww = __ldg(reinterpret_cast<const float4*>(w + (i * 32 + lane) * 4));
+      a0 = fmaf(v[0][i].x, ww.x, a0); a0 = fmaf(v[0][i].y, ww.y, a0);
+      a0 = fmaf(v[0][i].z, ww.z, a0); a0 = fmaf(v[0][i].w, ww.w, a0);
+      a1 = fmaf(v[1][i].x, ww.x, a1); a1 = fmaf(v[1][i].y, ww.y, a1);
+      a1 = fmaf(v[1][i].z, ww.z, a1); a1 = fmaf(v[1][i].w, ww.w, a1);
+    }
+    acc[o] = a0;
+    acc[16 + o] = a1;
+  }
+  // reduce-scatter over the warp: after the stage with offset h, acc[0 .. h) holds partial sums of the
+  // values whose index has bit h equal to the lane's bit h
+#pragma unroll
+  for (int h = 16; h >= 1; h >>= 1) {
+    const bool up = (lane & h) != 0;
+#pragma unroll
+    for (int i = 0; i < h; ++i) {
+      const float send = up ? acc[i] : acc[i + h];
+      const float keep = up ? acc[i + h] : acc[i];
+      acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+    }
+  }
+  const int tk = lane >> 4, oidx = lane & 15;
+  const int tok = tok0 + tk;
+  if (tok < ntok) {
+    const int b = tok / (3 * L);
+    const int nl = tok - b * 3 * L;
+    const int n = nl / L, l = nl - n * L;
+    const int pi = l / P, pj = l - pi * P;
+    // unpatchify: feature index = (p * 2 + q) * Cout + c   ('nhwpqc->nchpwq')
+    const int c = oidx % a.Cout, pq = oidx / a.Cout, pp = pq >> 1, qq = pq & 1;
+    a.out[((static_cast<long long>(b) * (3 * a.Cout) + c * 3 + n) * a.S + 2 * pi + pp) * a.S + 2 * pj + qq] =
+        acc[0] + (a.bias ? a.bias[oidx] : 0.f);
+  }
+}
+
 template <int NV>
 __global__ void __launch_bounds__(128)
 final_layer_kernel(const ln3_final_layer_args a) {
@@ -503,6 +608,15 @@ int final_layer(const ln3_final_layer_args* a, cudaStream_t stream) {
   const int L = (a->S / 2) * (a->S / 2);
   const int toks = a->B * 3 * L;
   dim3 grid((toks + 3) / 4), block(128);
+  if (4 * a->Cout == 16 && (a->D == 768 || a->D == 1024)) {
+    dim3 grid2((toks + 7) / 8);
+    if (a->D == 1024) final_layer2_kernel<8><<<grid2, block, 0, stream>>>(*a);
+    else final_layer2_kernel<6><<<grid2, block, 0, stream>>>(*a);
+    cudaError_t e2 = cudaGetLastError();
+    if (e2 != cudaSuccess) return set_error(LN3_ECUDA, "final_layer launch: %s", cudaGetErrorString(e2));
+    count_launch();
+    return LN3_OK;
+  }
   switch (a->D / 128) {
 #define LN3_FL_CASE(n) \
   case n: final_layer_kernel<n><<<grid, block, 0, stream>>>(*a); break;
