@@ -355,6 +355,7 @@ typedef struct ln3_conv_args {
   const float* residual;
   float* out;
   int N, H, W, Cin, Cout, ksize, upsample, in_swish;
+  int precision; /* LN3_MLP_FP32 (exact SIMT) or LN3_MLP_TF32 (3x3 only: mma.sync tensor cores, fp32 accumulate) */
 } ln3_conv_args;
 
 int ln3_conv_nhwc(const ln3_conv_args* args, void* stream);

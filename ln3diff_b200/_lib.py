@@ -121,7 +121,7 @@ class ConvArgs(C.Structure):
         ("x", C.c_void_p), ("w", C.c_void_p), ("bias", C.c_void_p), ("in_scale", C.c_void_p),
         ("in_shift", C.c_void_p), ("residual", C.c_void_p), ("out", C.c_void_p),
         ("N", C.c_int), ("H", C.c_int), ("W", C.c_int), ("Cin", C.c_int), ("Cout", C.c_int),
-        ("ksize", C.c_int), ("upsample", C.c_int), ("in_swish", C.c_int),
+        ("ksize", C.c_int), ("upsample", C.c_int), ("in_swish", C.c_int), ("precision", C.c_int),
     ]
 
 

@@ -109,6 +109,97 @@ conv_nhwc_kernel(const ln3_conv_args a) {
   }
 }
 
+// ------------------------------------------------------------------ 3x3 conv on the tensor cores (TF32)
+// Same tiling and the same fused prologue as conv_nhwc_kernel<COT, 3>; the inner product becomes an implicit
+// GEMM per block -- M = 64 output pixels, N = COT channels, K = 16 input channels x 9 taps per staged chunk --
+// issued as mma.sync.m16n8k8 TF32 (fp32 accumulate): 72 MMAs + 216 LDS per warp and chunk instead of
+// 2304 FFMA + 720 LDS per thread.  Warp w: pixel rows 2*(w&3), 2*(w&3)+1 of the 8x8 tile (one m-tile),
+// channel half w>>2.  smem rows are padded to strides = 8 (mod 32) words so that the (g, t) fragment
+// pattern of a warp touches 32 distinct banks.
+template <int COT>
+__global__ void __launch_bounds__(256)
+conv3x3_tf32_kernel(const ln3_conv_args a) {
+  constexpr int TW = kCT + 2;            // staged tile edge (halo 1)
+  constexpr int SIN = 104;               // >= TW*TW, = 8 (mod 32)
+  constexpr int SW = COT + 8;            // = 8 (mod 32)
+  constexpr int NT = COT / 16;           // n-tiles (of 8 channels) per warp
+  __shared__ uint32_t s_in[kCinChunk][SIN];
+  __shared__ uint32_t s_w[9][kCinChunk][SW];
+
+  const int n = blockIdx.z;
+  const int tiles_x = (a.W + kCT - 1) / kCT;
+  const int ty0 = (blockIdx.x / tiles_x) * kCT, tx0 = (blockIdx.x % tiles_x) * kCT;
+  const int co0 = blockIdx.y * COT;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int mt = warp & 3, nh = warp >> 2;
+  const int Hin = a.upsample ? a.H / 2 : a.H, Win = a.upsample ? a.W / 2 : a.W;
+
+  float acc[NT][4];
+#pragma unroll
+  for (int i = 0; i < NT; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+
+  for (int c0 = 0; c0 < a.Cin; c0 += kCinChunk) {
+    for (int i = threadIdx.x; i < TW * TW * kCinChunk; i += 256) {
+      const int ci = i % kCinChunk, tt = i / kCinChunk;   // channel fastest in gmem (NHWC)
+      const int yy = ty0 + tt / TW - 1, xx = tx0 + tt % TW - 1;
+      float v = 0.f;
+      if (yy >= 0 && yy < a.H && xx >= 0 && xx < a.W && c0 + ci < a.Cin) {
+        const int ys = a.upsample ? (yy >> 1) : yy, xs = a.upsample ? (xx >> 1) : xx;
+        v = a.x[((static_cast<long long>(n) * Hin + ys) * Win + xs) * a.Cin + c0 + ci];
+        if (a.in_scale != nullptr) {
+          v = fmaf(v, a.in_scale[n * a.Cin + c0 + ci], a.in_shift[n * a.Cin + c0 + ci]);
+          if (a.in_swish) v = v / (1.f + __expf(-v));
+        }
+      }
+      s_in[ci][tt] = to_tf32(v);
+    }
+    for (int i = threadIdx.x; i < 9 * kCinChunk * COT; i += 256) {
+      const int co = i % COT, r = i / COT, ci = r % kCinChunk, tap = r / kCinChunk;
+      float w = 0.f;
+      if (c0 + ci < a.Cin && co0 + co < a.Cout)
+        w = a.w[(static_cast<long long>(tap) * a.Cin + c0 + ci) * a.Cout + co0 + co];
+      s_w[tap][ci][co] = to_tf32(w);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      // A rows: g -> pixel (2*mt, g), g + 8 -> pixel (2*mt + 1, g); shifted by the tap inside the halo tile
+      const int p0 = (2 * mt + tap / 3) * TW + g + tap % 3;
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        const uint32_t af[4] = {s_in[8 * ks + t][p0], s_in[8 * ks + t][p0 + TW], s_in[8 * ks + t + 4][p0],
+                                s_in[8 * ks + t + 4][p0 + TW]};
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          const int cb = nh * (COT / 2) + nt * 8 + g;
+          mma_tf32(acc[nt], af, s_w[tap][8 * ks + t][cb], s_w[tap][8 * ks + t + 4][cb]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // D fragment: rows g / g + 8 = pixels (2*mt, g) / (2*mt + 1, g); columns 2t, 2t + 1 of each n-tile
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int oy = ty0 + 2 * mt + half, ox = tx0 + g;
+    if (oy < a.H && ox < a.W) {
+      const long long o = ((static_cast<long long>(n) * a.H + oy) * a.W + ox) * a.Cout;
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        const int co = co0 + nh * (COT / 2) + nt * 8 + 2 * t;
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+          if (co + e < a.Cout) {
+            float v = acc[nt][2 * half + e] + (a.bias ? a.bias[co + e] : 0.f);
+            if (a.residual) v += a.residual[o + co + e];
+            a.out[o + co + e] = v;
+          }
+      }
+    }
+  }
+}
+
 int conv_nhwc(const ln3_conv_args* a, cudaStream_t stream) {
   if (a->N <= 0) return LN3_OK;
   if (a->ksize != 1 && a->ksize != 3) return set_error(LN3_EUNSUPPORTED, "conv: ksize must be 1 or 3");
@@ -119,7 +210,10 @@ int conv_nhwc(const ln3_conv_args* a, cudaStream_t stream) {
   const int tiles = ((a->H + kCT - 1) / kCT) * ((a->W + kCT - 1) / kCT);
   const int cot = (a->Cout >= 64) ? 64 : 32;
   dim3 grid(tiles, (a->Cout + cot - 1) / cot, a->N);
-  if (a->ksize == 3) {
+  if (a->ksize == 3 && a->precision == LN3_MLP_TF32) {
+    if (cot == 64) conv3x3_tf32_kernel<64><<<grid, 256, 0, stream>>>(*a);
+    else conv3x3_tf32_kernel<32><<<grid, 256, 0, stream>>>(*a);
+  } else if (a->ksize == 3) {
     if (cot == 64) conv_nhwc_kernel<64, 3><<<grid, 256, 0, stream>>>(*a);
     else conv_nhwc_kernel<32, 3><<<grid, 256, 0, stream>>>(*a);
   } else {

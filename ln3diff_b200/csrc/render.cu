@@ -142,20 +142,6 @@ struct BlockSmem {
   WarpSmem warp[kWarpsPerBlock];
 };
 
-__device__ __forceinline__ uint32_t to_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return r;
-}
-// D (16x8, fp32) += A (16x8, tf32, row) * B (8x8, tf32, col).  Lane = 4g + t holds
-//   A: a0 (g, t)  a1 (g+8, t)  a2 (g, t+4)  a3 (g+8, t+4);   B: b0 (k=t, n=g)  b1 (k=t+4, n=g)
-//   D: d0 (g, 2t)  d1 (g, 2t+1)  d2 (g+8, 2t)  d3 (g+8, 2t+1)
-__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-
 // Fill the weight copies of a block (fp32 rows for the SIMT path, tf32 B fragments for the mma path).
 __device__ __forceinline__ void load_osg_weights(BlockSmem& bs, const float* w1, const float* b1, const float* w2,
                                                  const float* b2) {

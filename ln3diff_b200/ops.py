@@ -433,8 +433,10 @@ def query_points(planes_cl: torch.Tensor, osg: tuple, *, points: torch.Tensor | 
 
 def conv_nhwc(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor | None, *, ksize: int,
               upsample: bool = False, gn: tuple | None = None, swish: bool = False,
-              residual: torch.Tensor | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
-    """NHWC fp32 conv (stride 1, pad ksize//2).  x (N,Hin,Win,Cin); w_packed (ksize*ksize, Cin, Cout);
+              residual: torch.Tensor | None = None, out: torch.Tensor | None = None,
+              tf32: bool = False) -> torch.Tensor:
+    """NHWC fp32 conv (stride 1, pad ksize//2); tf32=True runs 3x3 convs on the tensor cores (TF32 operands,
+    fp32 accumulate).  x (N,Hin,Win,Cin); w_packed (ksize*ksize, Cin, Cout);
     gn = (scale, shift) (N,Cin) fuses GroupNorm-apply (+ swish) into the input load; upsample = fused
     nearest 2x of the input; residual (N,H,W,Cout) is added to the result."""
     _cuda(x, "x", torch.float32)
@@ -462,6 +464,7 @@ def conv_nhwc(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor | None
         a.residual = residual.data_ptr()
     a.N, a.H, a.W, a.Cin, a.Cout = N, H, W, Cin, Cout
     a.ksize, a.upsample, a.in_swish = ksize, int(upsample), int(swish)
+    a.precision = _lib.MLP_TF32 if (tf32 and ksize == 3) else _lib.MLP_FP32
     _lib.check(_lib.lib().ln3_conv_nhwc(C.byref(a), _lib.current_stream()), "ln3_conv_nhwc")
     return out
 

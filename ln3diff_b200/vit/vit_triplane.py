@@ -101,11 +101,15 @@ class RodinSR_256_fusionv6_ConvQuant_liteSR_dinoInit3DAttn_SD_B_3L_C_withrollout
         return P
 
     # ------------------------------------------------------------------ fused decode
-    @staticmethod
-    def _res(x, W):
-        h = ops.conv_nhwc(x, *W["c1"], ksize=3, gn=ops.groupnorm_stats(x, *W["n1"]), swish=True)
+    # 3x3 convolutions of the SD upsampler on the tensor cores (TF32 operands, fp32 accumulate); set to False
+    # for exact fp32 arithmetic
+    conv_tf32 = True
+
+    def _res(self, x, W):
+        tf = self.conv_tf32
+        h = ops.conv_nhwc(x, *W["c1"], ksize=3, gn=ops.groupnorm_stats(x, *W["n1"]), swish=True, tf32=tf)
         sc = ops.conv_nhwc(x, *W["nin"], ksize=1) if "nin" in W else x
-        return ops.conv_nhwc(h, *W["c2"], ksize=3, gn=ops.groupnorm_stats(h, *W["n2"]), swish=True, residual=sc)
+        return ops.conv_nhwc(h, *W["c2"], ksize=3, gn=ops.groupnorm_stats(h, *W["n2"]), swish=True, residual=sc, tf32=tf)
 
     @torch.no_grad()
     def decode_to_channels_last(self, latent, in_mul: float = 1.0):
@@ -158,7 +162,8 @@ class RodinSR_256_fusionv6_ConvQuant_liteSR_dinoInit3DAttn_SD_B_3L_C_withrollout
         # tokens (B, 3*16*16, D) are already NHWC (3B, 16, 16, D)
         S = P["sr"]
         ts = self.token_size
-        h = ops.conv_nhwc(x.view(B * 3, ts, ts, D), *S["conv_in"], ksize=3)
+        tf = self.conv_tf32
+        h = ops.conv_nhwc(x.view(B * 3, ts, ts, D), *S["conv_in"], ksize=3, tf32=tf)
         h = self._res(h, S["mid1"])
         A = S["attn"]
         gn = ops.groupnorm_stats(h, *A["n"])
@@ -169,8 +174,8 @@ class RodinSR_256_fusionv6_ConvQuant_liteSR_dinoInit3DAttn_SD_B_3L_C_withrollout
             for W in S["up"][lvl]["blocks"]:
                 h = self._res(h, W)
             if S["up"][lvl]["upsample"] is not None:
-                h = ops.conv_nhwc(h, *S["up"][lvl]["upsample"], ksize=3, upsample=True)
-        out = ops.conv_nhwc(h, *S["conv_out"], ksize=3, gn=ops.groupnorm_stats(h, *S["nout"]), swish=True)
+                h = ops.conv_nhwc(h, *S["up"][lvl]["upsample"], ksize=3, upsample=True, tf32=tf)
+        out = ops.conv_nhwc(h, *S["conv_out"], ksize=3, gn=ops.groupnorm_stats(h, *S["nout"]), swish=True, tf32=tf)
         return out.view(B, 3, out.shape[1], out.shape[2], out.shape[3])
 
     # ------------------------------------------------------------------ reference-named entry points

@@ -334,6 +334,15 @@ def test_decoder_conv_ops(dev):
     res = torch.randn(2, 40, 40, 48, generator=g)                # NCHW: Cout=40, 2H=40, 2W=48
     out = ops.conv_nhwc(xh, pk(w), b.to(dev), ksize=3, upsample=True, residual=res.permute(0, 2, 3, 1).contiguous().to(dev))
     assert _rel(out.permute(0, 3, 1, 2), ref_up + res) < 1e-5
+    # tensor-core (TF32) 3x3 path: ragged tiles (20x24), Cin = 48 (3 chunks), Cout = 40 (tail of a 64-wide
+    # tile), fused GroupNorm + swish, fused upsample + residual; and a 32-channel output (the other template)
+    out_tf = ops.conv_nhwc(xh, pk(w), b.to(dev), ksize=3, gn=gn, swish=True, tf32=True)
+    assert _rel(out_tf.permute(0, 3, 1, 2), ref) < 2e-3
+    out_tf = ops.conv_nhwc(xh, pk(w), b.to(dev), ksize=3, upsample=True, tf32=True,
+                           residual=res.permute(0, 2, 3, 1).contiguous().to(dev))
+    assert _rel(out_tf.permute(0, 3, 1, 2), ref_up + res) < 2e-3
+    w32 = torch.randn(32, 48, 3, 3, generator=g) * 0.1
+    assert _rel(ops.conv_nhwc(xh, pk(w32), None, ksize=3, tf32=True).permute(0, 3, 1, 2), F.conv2d(x, w32, padding=1)) < 2e-3
     w1 = torch.randn(40, 48, 1, 1, generator=g) * 0.1
     assert _rel(ops.conv_nhwc(xh, pk(w1), None, ksize=1).permute(0, 3, 1, 2), F.conv2d(x, w1)) < 1e-5
     q, k, v = (torch.randn(3, 256, 128, generator=g) for _ in range(3))
