@@ -90,7 +90,10 @@ struct FmhaParams {
 template <bool SPLIT>
 constexpr int fmha_threads() { return SPLIT ? 576 : kFmhaThreads; }
 
-template <int kPolyPer8, bool PINGPONG, bool SPLIT = false>
+// PTMEM = true: P_t is written to tensor memory (columns 384 + 64 t, bf16 pairs per 32-bit column) and fed
+// to P_t V as the TMEM A operand: no st.shared / proxy fence for P, and the N = 64 MMA no longer re-reads a
+// 4 KB A slice from shared memory per k-step.
+template <int kPolyPer8, bool PINGPONG, bool SPLIT = false, bool PTMEM = false>
 __global__ void __launch_bounds__(fmha_threads<SPLIT>(), 1)
 fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_k2,
@@ -255,9 +258,13 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           if (elect_one_sync()) {
 #pragma unroll
             for (int k = 0; k < kKT / 16; ++k)
-              if (k < ksteps)
-                umma_f16_ss(tm + 256 + t * 64, pd + (k >> 2) * kTileD + (k & 3) * 2, vd + k * 128, idesc_o,
-                            (j | k) != 0);
+              if (k < ksteps) {
+                if constexpr (PTMEM)
+                  umma_f16_ts(tm + 256 + t * 64, tm + 384 + t * 64 + k * 8, vd + k * 128, idesc_o, (j | k) != 0);
+                else
+                  umma_f16_ss(tm + 256 + t * 64, pd + (k >> 2) * kTileD + (k & 3) * 2, vd + k * 128, idesc_o,
+                              (j | k) != 0);
+              }
             umma_commit(&o_full[t]);
           }
           __syncwarp();
@@ -276,6 +283,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
     const uint32_t tS = tmem_base + t * 128 + lane_off;
     const uint32_t tO = tmem_base + 256 + t * 64 + lane_off;
+    const uint32_t tP = tmem_base + 384 + t * 64 + lane_off;   // PTMEM: P_t as packed bf16 pairs
     const uint32_t p_row = smem_u32(sP + t * 2 * kTileBytes) + row * 128;
     const int swz = row & 7;
     int g = 0;
@@ -365,11 +373,27 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
               e[i] = (i < kPolyPer8) ? exp2_poly(x) : fast_exp2(x);
             }
             rs += ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));
-            const uint32_t addr = p_row + (c >> 6) * kTileBytes + ((((c & 63) >> 3) ^ swz) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pack_bf16x2(e[0], e[1])),
-                         "r"(pack_bf16x2(e[2], e[3])), "r"(pack_bf16x2(e[4], e[5])),
-                         "r"(pack_bf16x2(e[6], e[7]))
-                         : "memory");
+            if constexpr (PTMEM) {
+              // in place: the score registers of this chunk become the packed probabilities; every 64 columns
+              // (32 packed words) go to tensor memory with one tcgen05.st
+              s[c / 2 + 0] = pack_bf16x2(e[0], e[1]);
+              s[c / 2 + 1] = pack_bf16x2(e[2], e[3]);
+              s[c / 2 + 2] = pack_bf16x2(e[4], e[5]);
+              s[c / 2 + 3] = pack_bf16x2(e[6], e[7]);
+              if ((c & 63) == 56) tmem_st_32x32(tP + (c >> 6) * 32, s + (c >> 6) * 32);
+            } else {
+              const uint32_t addr = p_row + (c >> 6) * kTileBytes + ((((c & 63) >> 3) ^ swz) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pack_bf16x2(e[0], e[1])),
+                           "r"(pack_bf16x2(e[2], e[3])), "r"(pack_bf16x2(e[4], e[5])),
+                           "r"(pack_bf16x2(e[6], e[7]))
+                           : "memory");
+            }
+          }
+          if constexpr (PTMEM && !FULL) {  // ragged block: flush the half that the loop left unfinished
+            if ((c_end & 63) != 0) {
+              if (c_end < 64) tmem_st_32x32(tP, s);
+              else tmem_st_32x32(tP + 32, s + 32);
+            }
           }
         };
         if (kv_valid >= kKT) exp_store(std::true_type{});
@@ -391,7 +415,8 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           }
           tmem_st_wait();
         }
-        fence_proxy_async_smem();  // P (generic-proxy stores) -> visible to the tensor core
+        if constexpr (PTMEM) tmem_st_wait();          // P (tcgen05.st) complete
+        else fence_proxy_async_smem();                // P (generic-proxy stores) -> visible to the tensor core
         tc_fence_before();
         mbar_arrive(&p_full[t]);
         if (row == 0) LN3_TR(t, g, 7);  // P handed to the tensor core
@@ -616,11 +641,15 @@ int fmha_fwd(const ln3_fmha_args* a, cudaStream_t stream) {
     set(fmha_fwd_kernel<3, false>); set(fmha_fwd_kernel<3, true>);
     set(fmha_fwd_kernel<4, false>); set(fmha_fwd_kernel<4, true>);
     set(fmha_fwd_kernel<0, false, true>); set(fmha_fwd_kernel<2, false, true>);
+    set(fmha_fwd_kernel<0, false, false, true>);
     if (e != cudaSuccess) return set_error(LN3_ECUDA, "fmha: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     // LN3_FMHA_SPLIT = 1: 16 softmax warps, each tile's score columns split over two warpgroups
     const char* sp = getenv("LN3_FMHA_SPLIT");
     const int split = (sp && atoi(sp) != 0) ? 1 : 0;
-    variant = split ? 100 + (v == 2 ? 2 : 0) : v * 2 + ping;
+    // LN3_FMHA_PTMEM = 1: P through tensor memory (TMEM A operand of P V)
+    const char* pt = getenv("LN3_FMHA_PTMEM");
+    const int ptmem = (pt && atoi(pt) != 0) ? 1 : 0;
+    variant = split ? 100 + (v == 2 ? 2 : 0) : (ptmem ? 200 : v * 2 + ping);
   }
   if (a->k2 != nullptr || a->v2 != nullptr) {
     if (!a->k2 || !a->v2 || a->Lkv2 <= 0) return set_error(LN3_EINVAL, "fmha: k2/v2/Lkv2 must be given together");
@@ -666,6 +695,7 @@ int fmha_fwd(const ln3_fmha_args* a, cudaStream_t stream) {
     LN3_FMHA_CASE(3, 0) LN3_FMHA_CASE(3, 1) LN3_FMHA_CASE(4, 0) LN3_FMHA_CASE(4, 1)
 #undef LN3_FMHA_CASE
     case 100: le = launch_pdl(fmha_fwd_kernel<0, false, true>, dim3(grid), dim3(fmha_threads<true>()), kFmhaSmem, stream, tq, tk, tv, tk2, tv2, to, p); break;
+    case 200: le = launch_pdl(fmha_fwd_kernel<0, false, false, true>, dim3(grid), dim3(kFmhaThreads), kFmhaSmem, stream, tq, tk, tv, tk2, tv2, to, p); break;
     case 102: le = launch_pdl(fmha_fwd_kernel<2, false, true>, dim3(grid), dim3(fmha_threads<true>()), kFmhaSmem, stream, tq, tk, tv, tk2, tv2, to, p); break;
     default: return set_error(LN3_EINVAL, "fmha: bad variant");
   }
