@@ -50,6 +50,8 @@ def workload_config(n_gpus):
             "prompts_per_gpu": PROMPTS_PER_GPU, "global_batch": PROMPTS_PER_GPU * n_gpus,
             "parallelism": f"prompt-sharded x{n_gpus} (replicated weights, no data-path collective)",
             "l2": "inputs larger than L2: 1.1 GB of bf16 weights stream through every forward",
+              "adaln": "one modulation row per step shared by the batch, all 250 steps' rows computed in one pass per "
+                       "sampling run (same arithmetic, bit-identical latents; LN3_SHARED_MODULATION=0 disables)",
               "uncond_cross_attention": "closed form for the zero-embedding CFG half (identical context tokens -> "
                                         "uniform softmax -> to_out(v_row)); LN3_UNCOND_CLOSED_FORM=0 disables"}
 

@@ -237,9 +237,27 @@ class DiT_TriLatent(nn.Module):
         t = timesteps.to(device=x.device, dtype=torch.float32).contiguous()
         return self._forward_impl(x.float().contiguous(), t, cx, in_scale)
 
-    def _forward_impl(self, x, t, cx, in_scale):
+    @torch.no_grad()
+    def modulation_table(self, t_values: torch.Tensor) -> torch.Tensor:
+        """adaLN modulations of every block + final layer for S timestep values at once: (S, (6L+2)·D) fp32.
+        In a sampling loop all samples of a step share one timestep, so the reference's per-step
+        `t_embedder` + 25 `adaLN_modulation` evaluations (identical rows for the whole batch,
+        dit_trilatent.py:91, dit_models_xformers.py:285-294) collapse into one row per step; computing all
+        steps' rows in one pass reads the 302 MB of adaLN weights once per sampling run instead of once per
+        step.  Same kernels, same per-row arithmetic as the in-forward path."""
+        if self._prep is None:
+            self.prepare()
+        P = self._prep
+        t = t_values.to(device=self.pos_embed.device, dtype=torch.float32).contiguous()
+        tf = ops.timestep_embedding(t)
+        th = ops.gemm(tf, P["t0_w"], P["t0_b"], act=ops.ACT_SILU)
+        st = ops.gemm(th, P["t2_w"], P["t2_b"], act=ops.ACT_SILU)
+        return ops.gemm(st, P["ada_w"], P["ada_b"], out_kind=ops.OUT_F32)
+
+    def _forward_impl(self, x, t, cx, in_scale, mod_row=None):
         """The fixed launch sequence of one forward (capturable in a CUDA graph: no host syncs, all
-        intermediates in the per-batch workspace)."""
+        intermediates in the per-batch workspace).  `mod_row` (1, (6L+2)·D): a row of modulation_table()
+        shared by every sample of the batch (replaces the timestep embedder + adaLN GEMM)."""
         P = self._prep
         B = x.shape[0]
         D, H, T = self.embed_dim, self.num_heads, self.pos_embed.shape[1]
@@ -247,10 +265,13 @@ class DiT_TriLatent(nn.Module):
         kv, (g0, g1), oconst = cx["kv"], cx["rows"], cx["oconst"]
         r0, r1 = g0 * T, g1 * T        # token rows that need real cross-attention
         ws = self._workspace(B)
-        ops.timestep_embedding(t, out=ws["tfeat"])
-        ops.gemm(ws["tfeat"], P["t0_w"], P["t0_b"], act=ops.ACT_SILU, out=ws["th"])
-        ops.gemm(ws["th"], P["t2_w"], P["t2_b"], act=ops.ACT_SILU, out=ws["st"])  # silu(t_emb)
-        mod = ops.gemm(ws["st"], P["ada_w"], P["ada_b"], out_kind=ops.OUT_F32, out=ws["mod"])
+        if mod_row is not None:
+            mod = mod_row.expand(B, mod_row.shape[1])       # stride-0 rows: every sample reads the same row
+        else:
+            ops.timestep_embedding(t, out=ws["tfeat"])
+            ops.gemm(ws["tfeat"], P["t0_w"], P["t0_b"], act=ops.ACT_SILU, out=ws["th"])
+            ops.gemm(ws["th"], P["t2_w"], P["t2_b"], act=ops.ACT_SILU, out=ws["st"])  # silu(t_emb)
+            mod = ops.gemm(ws["st"], P["ada_w"], P["ada_b"], out_kind=ops.OUT_F32, out=ws["mod"])
 
         xs = ops.patch_embed(x, P["pe_w"], P["pe_b"], P["pos"], in_scale=in_scale, out=ws["x"])
         x2 = xs.view(M, D)
@@ -288,7 +309,7 @@ class DiT_TriLatent(nn.Module):
                                P["fin_b"], self.input_size)
 
     @torch.no_grad()
-    def capture_graph(self, B, context):
+    def capture_graph(self, B, context, shared_mod: bool = False):
         """CUDA-graph one forward for a fixed batch B and a fixed (step-invariant) context: the ~250
         launches of a forward replay as one graph launch, removing the host launch gaps between the
         short kernels.  Returns an object with static inputs .x (B,3C,S,S), .t (B,), .in_scale (B,),
@@ -309,16 +330,18 @@ class DiT_TriLatent(nn.Module):
         g.x = torch.zeros(B, 3 * self.in_channels, self.input_size, self.input_size, device=dev)
         g.t = torch.zeros(B, device=dev)
         g.in_scale = torch.ones(B, device=dev)
+        # shared_mod: the caller writes one modulation_table() row per step into g.mod (g.t is then unused)
+        g.mod = torch.zeros(1, self._prep["ada_w"].shape[0], device=dev) if shared_mod else None
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
             for _ in range(2):  # warm-up outside capture (function attributes, workspaces)
-                self._forward_impl(g.x, g.t, kv, g.in_scale)
+                self._forward_impl(g.x, g.t, kv, g.in_scale, g.mod)
         torch.cuda.current_stream(dev).wait_stream(side)
         g.graph = torch.cuda.CUDAGraph()
         n0 = _lib.launch_count()
         with torch.cuda.graph(g.graph):
-            g.out = self._forward_impl(g.x, g.t, kv, g.in_scale)
+            g.out = self._forward_impl(g.x, g.t, kv, g.in_scale, g.mod)
         g.n_kernels = _lib.launch_count() - n0
 
         def replay():

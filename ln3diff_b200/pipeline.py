@@ -11,6 +11,8 @@ which is algebraically the reference's  D = x - sq*net;  x' = x + (x - cfg(D))/s
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import ops
@@ -58,11 +60,17 @@ def sample_t23d(model, randn: torch.Tensor, c: dict, uc: dict, num_steps: int = 
     xa, xb = x, torch.empty_like(x)
     if use_graph and num_steps >= 4:
         # one CUDA graph = one DiT forward of the 2B CFG batch; replayed every step
-        g = model.capture_graph(2 * B, ctx)
+        # every sample of a step shares its timestep: the adaLN modulations of all steps in one pass
+        shared = hasattr(model, "modulation_table") and os.environ.get("LN3_SHARED_MODULATION", "1") != "0"
+        g = model.capture_graph(2 * B, ctx, shared_mod=True) if shared else model.capture_graph(2 * B, ctx)
+        mod_table = model.modulation_table(tables["t_idx"][:num_steps, 0]) if shared else None
         for i in range(num_steps):
             g.x[:B].copy_(xa)
             g.x[B:].copy_(xa)
-            g.t.copy_(tables["t_idx"][i])
+            if shared:
+                g.mod.copy_(mod_table[i:i + 1])
+            else:
+                g.t.copy_(tables["t_idx"][i])
             g.in_scale.copy_(tables["c_in"][i])
             g.replay()
             ops.sampler_affine_update(xa, tables["coef"][i], g.out[:B], g.out[B:], out=xb)

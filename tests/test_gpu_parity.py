@@ -2,6 +2,8 @@
 seeded inputs and against the committed golden fixtures.  Tolerances: bf16 tensor-core operands ->
 rel-L2 <= 1e-2 per op / 2e-2 per DiT forward; fp32 kernels <= 1e-5; rendered pixels <= 1e-3
 (north_star); integer bookkeeping bit-exact where the float inputs are identical."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -167,6 +169,13 @@ def test_edm_cfg_pipeline_vs_oracle(dev):
     cd, ucd = {"crossattn": c["crossattn"].to(dev)}, {"crossattn": uc["crossattn"].to(dev)}
     out = pipeline.sample_t23d(m, x0.to(dev), cd, ucd, 4, 6.5)
     assert _rel(out, ref) < 2e-2
+    # the shared per-step modulation table (one adaLN row per step) is the same arithmetic as the per-forward path
+    os.environ["LN3_SHARED_MODULATION"] = "0"
+    try:
+        out_per_forward = pipeline.sample_t23d(m, x0.to(dev), cd, ucd, 4, 6.5)
+    finally:
+        del os.environ["LN3_SHARED_MODULATION"]
+    assert torch.equal(out, out_per_forward)
     disc = {"target": "sgm.modules.diffusionmodules.discretizer.LegacyDDPMDiscretization"}
     s = EulerEDMSampler(discretization_config=disc, num_steps=4, device=str(dev), guider_config={
         "target": "sgm.modules.diffusionmodules.guiders.VanillaCFG", "params": {"scale": 6.5}})
