@@ -165,3 +165,24 @@ def test_overlay_routes_reference_import_names(tmp_path):
                 del sys.modules[k]
         sys.modules.update(saved)
     assert overlay._finder is None
+
+
+def test_identical_token_row_detection(monkeypatch):
+    """dit_trilatent._attention_rows: which samples of a CFG batch still need real cross-attention."""
+    import torch
+    from ln3diff_b200.dit.dit_trilatent import _attention_rows
+    g = torch.Generator().manual_seed(0)
+    c = torch.randn(3, 5, 8, generator=g)
+    same = torch.randn(3, 1, 8, generator=g).expand(3, 5, 8)                 # identical tokens within a sample
+    assert _attention_rows(torch.cat([same, c])) == (3, 6)                   # sgm VanillaCFG order (uc, c)
+    assert _attention_rows(torch.cat([c, same])) == (0, 3)                   # forward_with_cfg order (c, uc)
+    assert _attention_rows(torch.cat([same, c, same])) == (3, 6)             # prefix and suffix
+    assert _attention_rows(torch.cat([same, same])) == (6, 6)                # nothing needs attention
+    assert _attention_rows(torch.cat([c, c])) is None                        # nothing to skip
+    assert _attention_rows(torch.cat([c[:1], same[:1], c[1:]])) is None      # identical sample in the middle: no
+    assert _attention_rows(c[:, :1]) is None                                 # a single token is not "identical tokens"
+    almost = same.clone()
+    almost[1, 2, 3] += 1e-6
+    assert _attention_rows(torch.cat([almost, c])) is None                   # exact comparison, nothing assumed
+    monkeypatch.setenv("LN3_UNCOND_CLOSED_FORM", "0")
+    assert _attention_rows(torch.cat([same, c])) is None
