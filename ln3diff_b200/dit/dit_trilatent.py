@@ -15,6 +15,7 @@ import torch.nn as nn
 
 from .. import _lib, ops
 from .._lib import NORM_LAYER, NORM_NONE, NORM_RMS
+from ._pixart import pixart_forward, pixart_workspace
 from .dit_models_xformers import (CaptionEmbedder, DiTBlock, FinalLayer, PixelArtTextCondDiTBlock, T2IFinalLayer,
                                   TextCondDiTBlock, TimestepEmbedder, _PatchEmbed,
                                   get_2d_sincos_pos_embed)
@@ -493,15 +494,7 @@ class DiT_TriLatent_PixelArt(nn.Module):
     def _workspace(self, B):
         ws = self._ws.get(B)
         if ws is None:
-            dev = self.pos_embed.device
-            D, T = self.embed_dim, self.pos_embed.shape[1]
-            M = B * T
-            e = lambda *s, dt=torch.bfloat16: torch.empty(*s, device=dev, dtype=dt)
-            ws = dict(tfeat=e(B, 256), th=e(B, D), t=e(B, D, dt=torch.float32), st=e(B, D),
-                      t0=e(B, 6 * D, dt=torch.float32), mod=e(self.depth, B, 6 * D, dt=torch.float32),
-                      x=e(B, T, D, dt=torch.float32), xb=e(M, D), a=e(M, D), v=e(M, D), qkv=e(M, 3 * D), att=e(M, D), q=e(M, D),
-                      h=e(M, int(self.mlp_ratio) * D))
-            self._ws[B] = ws
+            ws = self._ws[B] = pixart_workspace(self, B)
         return ws
 
     @torch.no_grad()
@@ -513,48 +506,9 @@ class DiT_TriLatent_PixelArt(nn.Module):
             raise RuntimeError("ln3diff_b200 DiT runs on CUDA only (no CPU fallback)")
         if self._prep is None:
             self.prepare()
-        P, cx = self._prep, self._context(context)
-        B = x.shape[0]
-        D, H, T = self.embed_dim, self.num_heads, self.pos_embed.shape[1]
-        M = B * T
-        ws = self._workspace(B)
         t = timesteps.to(device=x.device, dtype=torch.float32).contiguous()
-        ops.timestep_embedding(t, out=ws["tfeat"])
-        ops.gemm(ws["tfeat"], P["t0_w"], P["t0_b"], act=ops.ACT_SILU, out=ws["th"])
-        ws["t"].copy_(cx["cls"])                                                       # t = t_emb + clip_cls
-        ops.gemm(ws["th"], P["t2_w"], P["t2_b"], out_kind=ops.OUT_RESID_F32, out=ws["t"])
-        ops.norm_modulate(ws["t"], norm=NORM_NONE, act=ops.ACT_SILU, out=ws["st"])
-        ops.gemm(ws["st"], P["ada_w"], P["ada_b"], out_kind=ops.OUT_F32, out=ws["t0"])  # shared adaLN (B, 6D)
-        torch.add(P["tables"][:, None, :], ws["t0"][None], out=ws["mod"])              # + per-block tables
-        xs = ops.patch_embed(x.float().contiguous(), P["pe_w"], P["pe_b"], P["pos"], out=ws["x"])
-        x2 = xs.view(M, D)
-        qkv3, att3, q3 = ws["qkv"].view(B, T, 3 * D), ws["att"].view(B, T, D), ws["q"].view(B, T, D)
-        (g0, g1), oconst = cx["rows"], cx["oconst"]
-        r0, r1 = g0 * T, g1 * T
-        val, pend_gate = ws["v"], None   # deferred residuals (see DiT_TriLatent._forward_impl)
-        for l, W in enumerate(P["blocks"]):
-            mod = ws["mod"][l]
-            sl = lambda j: mod[:, j * D:(j + 1) * D]
-            ops.norm_modulate(x2, norm=NORM_RMS, weight=W["n1_w"], eps=1e-5, shift=sl(0), scale=sl(1), mod_rows=T, out=ws["a"],
-                              resid=val if l > 0 else None, resid_gate=pend_gate, resid_gate_rows=T)
-            ops.gemm(ws["a"], W["qkv_w"], W["qkv_b"], out=ws["qkv"])
-            ops.fmha(qkv3[:, :, :D], qkv3[:, :, D:2 * D], qkv3[:, :, 2 * D:], H, out=att3)
-            ops.gemm(ws["att"], W["proj_w"], W["proj_b"], out=val)
-            ops.norm_modulate(x2, norm=NORM_NONE, out=ws["xb"], resid=val, resid_gate=sl(2), resid_gate_rows=T)
-            if r1 > r0:
-                ops.gemm(ws["xb"][r0:r1], W["cq_w"], out=ws["q"][r0:r1])
-                ckv = cx["ckv"][l]
-                ops.fmha(q3[g0:g1], ckv[g0:g1, :, :D], ckv[g0:g1, :, D:], H, out=att3[g0:g1])
-                ops.gemm(ws["att"][r0:r1], W["co_w"], W["co_b"], out=val[r0:r1])
-            ops.norm_modulate(x2, norm=NORM_RMS, weight=W["n2_w"], eps=1e-5, shift=sl(3), scale=sl(4), mod_rows=T, out=ws["a"],
-                              resid=val, resid_bcast=oconst[l] if oconst is not None else None, resid_bcast_rows=T,
-                              resid_rows=(r0, r1) if oconst is not None else None)
-            ops.gemm(ws["a"], W["fc1_w"], W["fc1_b"], act=ops.ACT_GELU_ERF, out=ws["h"])
-            ops.gemm(ws["h"], W["fc2_w"], W["fc2_b"], out=val)
-            pend_gate = sl(5)
-        ops.norm_modulate(x2, norm=NORM_NONE, resid=val, resid_gate=pend_gate, resid_gate_rows=T, want_out=False)
-        return ops.final_layer(xs, ws["t"], ws["t"], P["fin_w"], P["fin_b"], self.input_size,
-                               shift_tab=P["fin_tab"][0].contiguous(), scale_tab=P["fin_tab"][1].contiguous())
+        return pixart_forward(self, self._prep, self._context(context), self._workspace(x.shape[0]),
+                              x.float().contiguous(), t)
 
     @torch.no_grad()
     def forward_with_cfg(self, x, t, context, cfg_scale):
