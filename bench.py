@@ -30,7 +30,11 @@ ARCH = "DiT-L/2"
 PROMPTS_PER_GPU = 8
 DENOISE_STEPS = 250
 CFG_SCALE = 6.5
-FLOPS_PER_FORWARD_PER_SAMPLE = 0.613e12  # SURVEY.md section 8d (T23D DiT-L/2, MAC = 2 FLOP)
+FLOPS_PER_FORWARD_PER_SAMPLE = 0.613e12  # SURVEY.md section 8d (T23D DiT-L/2, MAC = 2 FLOP), as the reference computes it
+# what this implementation executes per sample-forward: the context K/V projection is hoisted out of the loop
+# (-0.32 GF/layer) and the zero-embedding CFG half skips its cross-attention q GEMM / FMHA / out GEMM
+# (-3.46 GF/layer for half of the samples): 24 x (25.18 + 21.72) / 2 GF + 1 GF of embedders / final layer
+FLOPS_EXECUTED_PER_FORWARD_PER_SAMPLE = 0.564e12
 
 
 def parse():
@@ -57,71 +61,106 @@ def workload_config(n_gpus):
 
 
 # ------------------------------------------------------------------ CPU reference arm / baseline
-def cpu_reference_sample(n_steps_sample=1, prompts=1, threads=None):
-    """Time `n_steps_sample` Euler-EDM+CFG steps of DiT-L/2 for `prompts` prompts with the oracle
-    port on the host cores; returns (latents_per_sec extrapolated to 250 steps, seconds, cores)."""
-    import torch
-    from oracle import dit as odit
-    from oracle import samplers as osmp
-    from ln3diff_b200.utils import build_t23d
-    cores = threads or os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    m = build_t23d(ARCH)
-    sd = {k: v.float() for k, v in m.state_dict().items()}
-    del m
-    g = torch.Generator().manual_seed(41)
-    x = torch.randn(prompts, 12, 32, 32, generator=g)
-    c = {"crossattn": torch.randn(prompts, 77, 768, generator=g)}
-    uc = {"crossattn": torch.zeros(prompts, 77, 768)}
-    calls = []
+def host_cores() -> int:
+    """Threads this process may actually use: the scheduler affinity mask, capped by the cgroup CPU quota
+    (os.cpu_count() reports the whole node, which oversubscribes a 1-GPU lease)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except Exception:
+        pass
+    return max(1, n)
 
-    def net(xin, idx, cond):
+
+# bounded samples of one Euler-EDM+CFG denoising step, largest first: (name, prompts, forwards, layers)
+REF_SAMPLES = (("1 of 250 Euler-EDM+CFG steps for 1 prompt (2 DiT-L/2 fp32 forwards: uncond + cond)", 2, 24),
+               ("1 of the 2 CFG forwards of 1 of 250 steps for 1 prompt (1 DiT-L/2 fp32 forward)", 1, 24),
+               ("6 of the 24 blocks of 1 of the 2 CFG forwards of 1 of 250 steps for 1 prompt", 1, 6))
+REF_BUDGET_S = 360.0          # whole `--impl reference` run (driver: "ends within a few minutes")
+
+
+class CpuReference:
+    """The oracle port of the DiT-L/2 denoising step on the host cores.  The model state is built ONCE;
+    `step(level)` times one bounded sample and returns (latents/s extrapolated to the full 250-step job for
+    one prompt, seconds).  Extrapolation is linear in blocks x forwards x steps (every block costs the same;
+    embedders / final layer are < 0.2 % of a forward)."""
+
+    def __init__(self, threads=None):
+        import torch
+        from oracle import dit as odit
+        from ln3diff_b200.utils import build_t23d
+        self.torch, self.odit = torch, odit
+        self.cores = threads or host_cores()
+        torch.set_num_threads(self.cores)
+        m = build_t23d(ARCH)
+        self.sd = {k: v.float() for k, v in m.state_dict().items()}
+        del m
+        g = torch.Generator().manual_seed(41)
+        self.x = torch.randn(1, 12, 32, 32, generator=g)
+        self.ctx = torch.cat([torch.zeros(1, 77, 768), torch.randn(1, 77, 768, generator=g)], 0)   # (uc, c)
+        from oracle import samplers as osmp
+        self.table = osmp.legacy_ddpm_sigmas(1000, append_zero=False, flip=True)
+        self.sigmas = osmp.legacy_ddpm_sigmas(DENOISE_STEPS)
+        self.osmp = osmp
+
+    def step(self, level=0):
+        torch, osmp = self.torch, self.osmp
+        _, forwards, layers = REF_SAMPLES[level]
         t0 = time.perf_counter()
-        out = odit.dit_t23d_forward(sd, ARCH, xin, idx, cond["crossattn"])
-        calls.append(time.perf_counter() - t0)
-        return out
-
-    # run the first `n_steps_sample` steps of the real 250-step schedule
-    table = osmp.legacy_ddpm_sigmas(1000, append_zero=False, flip=True)
-    sigmas = osmp.legacy_ddpm_sigmas(DENOISE_STEPS)
-    t0 = time.perf_counter()
-    with torch.no_grad():
-        xx = x * torch.sqrt(1.0 + sigmas[0] ** 2.0)
-        for i in range(n_steps_sample):
-            s = torch.ones(prompts) * sigmas[i]
-            nxt = torch.ones(prompts) * sigmas[i + 1]
+        with torch.no_grad():
+            xx = self.x * torch.sqrt(1.0 + self.sigmas[0] ** 2.0)
+            s = torch.ones(1) * self.sigmas[0]
             xin, sin = torch.cat([xx] * 2), torch.cat([s] * 2)
-            sq = table[osmp.sigma_to_idx(sin, table)]
+            sq = self.table[osmp.sigma_to_idx(sin, self.table)]
             sq4 = sq[:, None, None, None]
-            den = net(xin / (sq4 ** 2 + 1.0) ** 0.5, osmp.sigma_to_idx(sq, table),
-                      {"crossattn": torch.cat((uc["crossattn"], c["crossattn"]), 0)}) * (-sq4) + xin
-            x_u, x_c = den.chunk(2)
-            d = (xx - (x_u + CFG_SCALE * (x_c - x_u))) / s[:, None, None, None]
-            xx = xx + (nxt - s)[:, None, None, None] * d
-    dt = time.perf_counter() - t0
-    per_step = dt / n_steps_sample
-    return prompts / (per_step * DENOISE_STEPS), dt, cores
+            sel = slice(0, 2) if forwards == 2 else slice(1, 2)
+            net = self.odit.dit_t23d_forward(self.sd, ARCH, (xin / (sq4 ** 2 + 1.0) ** 0.5)[sel],
+                                             osmp.sigma_to_idx(sq, self.table)[sel], self.ctx[sel],
+                                             first_blocks=None if layers == 24 else layers)
+            if forwards == 2:
+                den = net * (-sq4) + xin
+                x_u, x_c = den.chunk(2)
+                d = (xx - (x_u + CFG_SCALE * (x_c - x_u))) / s[:, None, None, None]
+                xx = xx + (self.sigmas[1] - s)[:, None, None, None] * d
+        dt = time.perf_counter() - t0
+        per_step = dt * (2 / forwards) * (24 / layers)       # one full CFG denoising step for one prompt
+        return 1.0 / (per_step * DENOISE_STEPS), dt
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    vals = []
     t_all = time.perf_counter()
-    for i in range(args.warmup + args.steps):
-        v, dt, cores = cpu_reference_sample(n_steps_sample=1, prompts=1)
+    ref = CpuReference()
+    n_iter = args.warmup + args.steps
+    # the first pass (cold caches, thread pool start-up) picks the largest sample that keeps the whole run
+    # inside REF_BUDGET_S; it is not one of the counted iterations
+    level = 0
+    _, dt0 = ref.step(0)
+    while level + 1 < len(REF_SAMPLES):
+        _, fw, ly = REF_SAMPLES[level]
+        if dt0 * (fw / 2) * (ly / 24) * n_iter <= REF_BUDGET_S - (time.perf_counter() - t_all):
+            break
+        level += 1
+    vals = []
+    for i in range(n_iter):
+        v, dt = ref.step(level)
         if i >= args.warmup:
             vals.append((v, dt))
     value = sum(v for v, _ in vals) / len(vals)
     ms = 1e3 * sum(dt for _, dt in vals) / len(vals)
-    sample = ("1 of 250 Euler-EDM+CFG steps for 1 prompt (2 DiT-L/2 fp32 forwards) per bench step, "
-              "latents/s extrapolated linearly in steps x prompts")
+    sample = REF_SAMPLES[level][0] + " per bench step; latents/s extrapolated linearly in blocks x forwards x steps x prompts"
     line = {"impl": "reference", "metric": "denoised-latents/sec", "value": value, "unit": "latents/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": workload_config(args.gpus),
-            "cpu_baseline": {"value": value, "unit": "latents/s", "cores": cores, "kind": "port",
+            "cpu_baseline": {"value": value, "unit": "latents/s", "cores": ref.cores, "kind": "port",
                              "sample": sample},
             "e2e": {"value": value, "unit": "latents/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "wall_s": time.perf_counter() - t_all}
@@ -171,12 +210,43 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+# ------------------------------------------------------------------ GPU reference leg (eager PyTorch)
+def gpu_reference_leg(torch, dev, state_dict, B, nsteps, randn_d, ctx_d):
+    """The reference's GPU arithmetic (stock eager PyTorch under bf16 autocast: cuBLAS + SDPA-flash, the
+    reference's per-step recomputation and sampler launches left in; baseline/torch_eager.py) on the same
+    B200, same workload, timed BEFORE the repo's arm in the same process (SURVEY.md 8d timing protocol).
+    Bounded sample: `sample_steps` of the 250 denoising steps for the full 8-prompt batch, 3 repeats after a
+    warm-up, extrapolated linearly in steps (every step launches the same kernels on the same shapes)."""
+    from baseline.torch_eager import EagerDiT, euler_edm_cfg_steps
+    sample_steps = 20
+    m = EagerDiT(depth=24, dim=1024, heads=16, ctx_dim=768).to(dev).load_mirror_state_dict(state_dict).eval()
+    uc = torch.zeros_like(ctx_d)
+    run = lambda: euler_edm_cfg_steps(m, randn_d, ctx_d, uc, nsteps, CFG_SCALE, first_steps=sample_steps)
+    run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 3
+    e0.record()
+    for _ in range(reps):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
+    ms_step = e0.elapsed_time(e1) / reps / sample_steps
+    del m
+    torch.cuda.empty_cache()
+    return {"value": B / (ms_step * nsteps / 1e3), "unit": "latents/s", "ms_per_denoise_step": ms_step,
+            "kind": "port", "impl": "baseline/torch_eager.py: eager PyTorch, bf16 autocast, cuBLAS GEMMs + "
+                                    "F.scaled_dot_product_attention, the reference's module structure and sgm sampler",
+            "sample": f"{sample_steps} of {nsteps} Euler-EDM+CFG steps for {B} prompts x {reps} repeats, "
+                      "extrapolated linearly in steps"}
+
+
 # ------------------------------------------------------------------ our arm
 def run_ours(args):
     import torch
     import torch.distributed as dist
     from ln3diff_b200 import _lib, ops, pipeline
-    from ln3diff_b200.utils import build_t23d
+    from ln3diff_b200.utils import build_ae_decoder, build_t23d, orbit_cameras
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -192,7 +262,6 @@ def run_ours(args):
     nsteps = args.denoise_steps
 
     model = build_t23d(ARCH, seed=0, device=dev)
-    model.prepare()
     # identical-seed inputs as the reference engine draws them (CPU generator, then moved):
     # one global randn for all prompts, sliced per rank
     g = torch.Generator().manual_seed(41)
@@ -204,6 +273,16 @@ def run_ours(args):
     out_h = torch.empty(B, 12, 32, 32).pin_memory()
     randn_d, ctx_d = randn_h.to(dev), ctx_h.to(dev)
     uc_d = torch.zeros_like(ctx_d)
+
+    # ---- the reference's GPU path first (same process, same box), then ours
+    gpu_ref = None
+    if rank == 0 and n_gpus == 1:
+        try:
+            gpu_ref = gpu_reference_leg(torch, dev, model.state_dict(), B, nsteps, randn_d, ctx_d)
+        except Exception as e:  # noqa
+            gpu_ref = {"error": repr(e)}
+
+    model.prepare()
     tables = pipeline.edm_cfg_tables(nsteps, CFG_SCALE, B, dev)
     gathered = torch.empty(n_gpus * B, 12, 32, 32, device=dev) if world > 1 else None
 
@@ -215,6 +294,8 @@ def run_ours(args):
         return lat
 
     def one_step_e2e():
+        # the public pipeline call with HOST inputs: H2D of noise + prompt embeddings, the per-prompt-batch
+        # conditioning (context projection, all layers' K/V), 250 steps, D2H of the latents
         x = randn_h.to(dev, non_blocking=True)
         c = ctx_h.to(dev, non_blocking=True)
         lat = pipeline.sample_t23d(model, x, {"crossattn": c}, {"crossattn": torch.zeros_like(c)}, nsteps,
@@ -255,6 +336,53 @@ def run_ours(args):
     ms_e2e_total, _ = timed(one_step_e2e, args.steps, 1)
     e2e_value = B * n_gpus / (ms_e2e_total / args.steps / 1e3)
 
+    # ---- BASELINE configs[4], every rank: 32 prompts/GPU -> 250-step sampling ->
+    #      VAE decode -> 24 views at 256x256 -> uint8 frames -> NCCL all-gather of the frames (151 MB/rank)
+    c5 = None
+    try:
+        P5, V5, R5 = 32, 24, 256
+        dec = build_ae_decoder("DiT2-L/2", device=dev)
+        cams5 = orbit_cameras(V5).to(dev)
+        g5 = torch.Generator().manual_seed(43)
+        c5_all = {"crossattn": torch.randn(P5 * n_gpus, 77, 768, generator=g5)}
+        uc5_all = {"crossattn": torch.zeros(P5 * n_gpus, 77, 768)}
+        run5 = lambda steps: pipeline.generate_sharded(model, dec, c5_all, uc5_all, cams5, seed=41, num_steps=steps,
+                                                       scale=CFG_SCALE, resolution=R5, batch=P5)
+        run5(3)                                   # warm-up: workspaces, the 64-sample graph, NCCL buffers
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        o5 = run5(nsteps)
+        e1.record()
+        torch.cuda.synchronize()
+        ms5 = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms5, op=dist.ReduceOp.MAX)
+        ms5 = ms5.item()
+        # stage split on this rank (un-overlapped, informational)
+        lat5 = o5["latents"]
+        e0.record()
+        r5 = pipeline.decode_and_render(dec, lat5, cams5, R5)
+        e1.record()
+        torch.cuda.synchronize()
+        ms5_render = e0.elapsed_time(e1)
+        c5 = {"rendered_views_per_s": P5 * n_gpus * V5 / (ms5 / 1e3), "latents_per_s": P5 * n_gpus / (ms5 / 1e3),
+              "ms": ms5, "prompts_per_gpu": P5, "views_per_prompt": V5, "res": R5, "denoise_steps": nsteps,
+              "samples_per_forward": 2 * P5, "decode_render_ms_per_gpu": ms5_render,
+              "gather": "all_gather_into_tensor of uint8 HWC frames on a side stream" if world > 1 else "none (1 GPU)",
+              "gather_bytes_per_rank": o5["gather_bytes_per_rank"],
+              "frames_shape": list(o5["frames_all"].shape), "frames_checksum": int(o5["frames_all"][::7, ::5].sum().item()),
+              "what": "BASELINE configs[4] / SURVEY 8d config 5 through pipeline.generate_sharded: global CPU noise "
+                      "draw sliced per rank -> sample_t23d -> decode_and_render -> frame sink -> NCCL all-gather"}
+        del o5, r5, lat5, dec
+        torch.cuda.empty_cache()
+    except Exception as e:  # noqa
+        c5 = {"error": repr(e)}
+        if world > 1:
+            raise
+
     line = None
     if rank == 0:
         # ---- roofline of the dominant kernel (tcgen05 GEMM): instrumented pass over one forward,
@@ -283,66 +411,74 @@ def run_ours(args):
 
         x2 = torch.randn(2 * B, 12, 32, 32, device=dev)
         ctx2 = torch.cat([uc_d, ctx_d], 0)
-        model(x2, tables["t_idx"][0], ctx2, in_scale=tables["c_in"][0])
-        torch.cuda.synchronize()
-        ops.gemm = gemm_probe
-        import ln3diff_b200.dit.dit_trilatent as _dt
+        os.environ["LN3_CUDA_GRAPH"] = "0"      # eager launches so that every GEMM can be bracketed by events
         try:
-            _dt.ops.gemm = gemm_probe
+            model(x2, tables["t_idx"][0], ctx2, in_scale=tables["c_in"][0])
+            torch.cuda.synchronize()
+            ops.gemm = gemm_probe
             model(x2, tables["t_idx"][1], ctx2, in_scale=tables["c_in"][1])
             torch.cuda.synchronize()
         finally:
             ops.gemm = real_gemm
-            _dt.ops.gemm = real_gemm
+            os.environ.pop("LN3_CUDA_GRAPH", None)
         big = [(f, e0.elapsed_time(e1)) for f, (e0, e1) in zip(flops, ev) if f > 1e10]
         gemm_ms = sum(t for _, t in big)
         gemm_fl = sum(f for f, _ in big)
         achieved = gemm_fl / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+        traffic, traffic_src = None, None
+        try:   # dram bytes of the dominant launch from this round's `ncu --set full` capture (tools/summarize_ncu.py)
+            with open(os.path.join(ROOT, "profiles", "r2_gemm_traffic.json")) as f:
+                tj = json.load(f)
+            traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
+        except Exception:
+            pass
         roofline = {"kernel": "ln3::gemm2_bf16_kernel (tcgen05 cta_group::2, 256x256x64 per CTA pair, fused epilogues)",
                     "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                     "frac": achieved / peak_tf, "peak_source": peak_src,
-                    "traffic": 69.57e6,  # dram read+write of the captured qkv launch (profiles/r1_ncu_gemm_pair_v1.txt)
+                    "traffic": traffic, "traffic_source": traffic_src,
                     "launches_measured": len(big), "avg_launch_us": 1e3 * gemm_ms / max(len(big), 1),
                     "flops_per_launch_avg": gemm_fl / max(len(big), 1),
                     "note": "events add launch gaps; gemm share of the forward in profiles/"}
-        model_tf = FLOPS_PER_FORWARD_PER_SAMPLE * 2 * B * nsteps / (ms_step / 1e3) / 1e12
+        model_tf = FLOPS_EXECUTED_PER_FORWARD_PER_SAMPLE * 2 * B * nsteps / (ms_step / 1e3) / 1e12
+        model_tf_ref = FLOPS_PER_FORWARD_PER_SAMPLE * 2 * B * nsteps / (ms_step / 1e3) / 1e12
 
         # ---- second headline quantity: rendered views/sec of the fused ray-march kernel
         views = None
         try:
             gg = torch.Generator().manual_seed(4)
-            n_obj, V, res = 4, 16, 128
+            n_obj, V = 4, 16
             planes = (5 * torch.randn(n_obj, 3, 32, 128, 128, generator=gg)).to(dev)
             osg = [torch.randn(64, 32, generator=gg), torch.randn(64, generator=gg) * 0.1,
                    torch.randn(4, 64, generator=gg), torch.randn(4, generator=gg) * 0.1]
             osg[3][0] += 2.0
             osg = tuple(t.to(dev) for t in osg)
-            from ln3diff_b200.utils import orbit_cameras
-            cams = orbit_cameras(V).repeat(n_obj, 1).to(dev)
-            M = res * res
-            nc = torch.rand(n_obj * V, M, 64, device=dev)
-            nf = torch.rand(n_obj * V, M, 64, device=dev)
             pcl = ops.planes_to_channels_last(planes)
-            o, d = ops.generate_rays(cams, res)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
-            def time_render(tf32):
+            def time_render(res, tf32, nv):
+                cams = orbit_cameras(nv).repeat(n_obj, 1).to(dev)
+                M = res * res
+                nc = torch.rand(n_obj * nv, M, 64, device=dev)
+                nf = torch.rand(n_obj * nv, M, 64, device=dev)
+                o, d = ops.generate_rays(cams, res)
                 for _ in range(2):
-                    ops.render_views(pcl, o, d, nc, nf, osg, views_per_obj=V, mlp_tf32=tf32)
+                    ops.render_views(pcl, o, d, nc, nf, osg, views_per_obj=nv, mlp_tf32=tf32)
                 torch.cuda.synchronize()
                 e0.record()
                 for _ in range(3):
-                    ops.render_views(pcl, o, d, nc, nf, osg, views_per_obj=V, mlp_tf32=tf32)
+                    ops.render_views(pcl, o, d, nc, nf, osg, views_per_obj=nv, mlp_tf32=tf32)
                 e1.record()
                 torch.cuda.synchronize()
                 return e0.elapsed_time(e1) / 3
 
-            rms, rms32 = time_render(True), time_render(False)
-            views = {"value": n_obj * V / (rms / 1e3), "unit": "views/s", "res": res, "views": n_obj * V,
+            rms, rms32 = time_render(128, True, V), time_render(128, False, V)
+            rms256 = time_render(256, True, 8)
+            views = {"value": n_obj * V / (rms / 1e3), "unit": "views/s", "res": 128, "views": n_obj * V,
                      "samples_per_ray": "64+64", "ms": rms,
                      "mlp": "TF32 tensor-core OSG MLP (product default; pixels within 1e-4 rel-L2 of fp32)",
                      "exact_fp32_mlp_views_per_s": n_obj * V / (rms32 / 1e3),
-                     "flops_per_s_T": 0.70e6 * M * n_obj * V / (rms / 1e3) / 1e12,
+                     "views_per_s_256": n_obj * 8 / (rms256 / 1e3),
+                     "flops_per_s_T": 0.70e6 * 128 * 128 * n_obj * V / (rms / 1e3) / 1e12,
                      "data": "synthetic planes 5*randn, explicit noise (SURVEY.md 8d config 3 render-only)"}
         except Exception as e:  # noqa
             views = {"error": repr(e)}
@@ -350,7 +486,6 @@ def run_ours(args):
         # ---- VAE decode (DiT2-L/2 + conv upsampler) throughput: latent -> channels-last tri-plane
         vae = None
         try:
-            from ln3diff_b200.utils import build_ae_decoder
             dec = build_ae_decoder("DiT2-L/2", device=dev)
             lat8 = torch.randn(B, 12, 32, 32, device=dev)
             for _ in range(2):
@@ -367,15 +502,13 @@ def run_ours(args):
                    "what": "latent (12,32,32) -> tri-plane (3,128,128,32): PatchEmbedTriplane + DiT2-L/2 + SD conv decoder"}
             # BASELINE configs[2]: 64 denoised latents -> decode -> 16 views each at 128x128, through the
             # public pipeline call (device RNG for the sampler noise), 8 latents per call
-            from ln3diff_b200 import pipeline as _pl
-            from ln3diff_b200.utils import orbit_cameras as _oc
-            cams16 = _oc(16).to(dev)
+            cams16 = orbit_cameras(16).to(dev)
             lat64 = torch.randn(64, 12, 32, 32, device=dev)
-            _pl.decode_and_render(dec, lat64[:8], cams16, 128)
+            pipeline.decode_and_render(dec, lat64[:8], cams16, 128)
             torch.cuda.synchronize()
             e0.record()
             for i0 in range(0, 64, 8):
-                _pl.decode_and_render(dec, lat64[i0:i0 + 8], cams16, 128)
+                pipeline.decode_and_render(dec, lat64[i0:i0 + 8], cams16, 128)
             e1.record()
             torch.cuda.synchronize()
             c2ms = e0.elapsed_time(e1)
@@ -410,7 +543,8 @@ def run_ours(args):
             ims = e0.elapsed_time(e1)
             i23d = {"value": B / (ims / 1e3), "unit": "latents/s", "images_per_gpu": B, "ode_points": 50, "cfg_scale": 4.0,
                     "ms": ims, "what": "BASELINE configs[3] shard: DiT-PixArt-L/2 sample_ode('euler', 50) + forward_with_cfg "
-                                       "(49 network evaluations of 16 samples), through the transport mirror (no CUDA graph)"}
+                                       "(49 network evaluations of 16 samples), through the transport mirror "
+                                       "(every forward replays the model's cached CUDA graph)"}
             del mi
         except Exception as e:  # noqa
             i23d = {"error": repr(e)}
@@ -418,18 +552,17 @@ def run_ours(args):
         # ---- mesh-extraction lattice: 192^3 point queries (triplane_decode_grid) on one object
         grid = None
         try:
-            from ln3diff_b200 import ops as _ops
             gen = torch.Generator(device=dev).manual_seed(5)
             pl = torch.randn(1, 3, 128, 128, 32, device=dev, generator=gen)
             osg_w = (torch.randn(64, 32, device=dev, generator=gen), torch.zeros(64, device=dev),
                      torch.randn(4, 64, device=dev, generator=gen), torch.zeros(4, device=dev))
             for _ in range(2):
-                _ops.query_points(pl, osg_w, grid_size=192)
+                ops.query_points(pl, osg_w, grid_size=192)
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for _ in range(3):
-                _ops.query_points(pl, osg_w, grid_size=192)
+                ops.query_points(pl, osg_w, grid_size=192)
             e1.record()
             torch.cuda.synchronize()
             gms = e0.elapsed_time(e1) / 3
@@ -440,10 +573,15 @@ def run_ours(args):
 
         cpu = None
         if n_gpus == 1:
-            v, dt, cores = cpu_reference_sample(n_steps_sample=1, prompts=1)
-            cpu = {"value": v, "unit": "latents/s", "cores": cores, "kind": "port",
-                   "sample": f"1 of 250 Euler-EDM+CFG steps for 1 prompt (2 DiT-L/2 fp32 forwards, {dt:.1f} s); "
-                             "latents/s extrapolated linearly in steps x prompts"}
+            try:
+                ref = CpuReference()
+                ref.step(0)                        # cold pass (thread pool, page faults)
+                v, dt = ref.step(0)
+                cpu = {"value": v, "unit": "latents/s", "cores": ref.cores, "kind": "port",
+                       "sample": f"{REF_SAMPLES[0][0]} ({dt:.1f} s); latents/s extrapolated linearly in steps x prompts"}
+                del ref
+            except Exception as e:  # noqa
+                cpu = {"error": repr(e)}
         line = {"metric": "denoised-latents/sec", "value": value, "unit": "latents/s", "n_gpus": n_gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
@@ -452,7 +590,12 @@ def run_ours(args):
                         "h2d_bytes_per_step": randn_h.numel() * 4 + ctx_h.numel() * 4,
                         "d2h_bytes_per_step": out_h.numel() * 4},
                 "gpu_launches": int(launches), "clocks": clk, "roofline": roofline,
-                "model_tflops": model_tf, "rendered_views": views, "vae_decode": vae, "i23d_flow": i23d, "point_queries": grid, "cpu_baseline": cpu}
+                "ms_per_denoise_step": ms_step / nsteps,
+                "model_tflops": model_tf, "model_tflops_reference_flop_count": model_tf_ref,
+                "gpu_reference": gpu_ref,
+                "vs_gpu_reference": (value / gpu_ref["value"]) if gpu_ref and "value" in gpu_ref else None,
+                "config5_sharded_generation": c5,
+                "rendered_views": views, "vae_decode": vae, "i23d_flow": i23d, "point_queries": grid, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -327,6 +327,29 @@ int ln3_generate_rays(const float* cams, int V, int res, float* ray_o, float* ra
 int ln3_planes_to_channels_last(const float* planes, int n_obj, int C, int H, int W, float* out,
                                 void* stream);
 
+/* ------------------------------------------------------------------ frame sink
+ * TrainLoopDiffusionWithRec.render_video_given_triplane's per-view host loop
+ * (nsr/train_util_diffusion.py:292-376): `.cpu()` + numpy + matplotlib per view, replaced by one device
+ * pass over all views so that one batched D2H copy (or the NCCL all-gather of frames) moves uint8.
+ *   image  fp32 [N,3,H,W] in [-1,1] ('image_raw')
+ *   depth  fp32 [N,1,H,W] ('image_depth') or NULL
+ *   out    u8 [N, H, Wout, 3] (HWC video frames), Wout = W, or 2W with depth: [image | colour-mapped depth]
+ * Arithmetic as the reference: byte = uint8(clip(float64(v) * 127.5 + 127.5, 0, 255)) (truncation);
+ * depth -> (d - min_view) / (max_view - min_view) in fp32, colormap index min(trunc(x * 256), 255), the
+ * byte table `lut` u8 [256,3] = uint8(clip((cmap_rgb * 2 - 1) * 127.5 + 127.5, 0, 255)) of the 256-entry
+ * colormap (plt.cm.viridis in the reference); max == min gives the colormap's "bad" colour (0,0,0).
+ * workspace: 2*N floats (per-view min / max).  W % 4 == 0. */
+typedef struct ln3_pack_frames_args {
+  const float* image;
+  const float* depth;
+  const unsigned char* lut;
+  unsigned char* out;
+  float* workspace;
+  int N, H, W;
+} ln3_pack_frames_args;
+
+int ln3_pack_frames(const ln3_pack_frames_args* args, void* stream);
+
 /* ------------------------------------------------------------------ VAE decoder: conv tail (NHWC fp32)
  * The reference's superresolution['conv_sr'] = ldm Decoder (ldm/modules/diffusionmodules/model.py:
  * 625-731) and PatchEmbedTriplane (vit/vit_triplane.py:58-108).  Activations are NHWC so the DiT2

@@ -116,6 +116,14 @@ class QueryPointsArgs(C.Structure):
     ]
 
 
+class PackFramesArgs(C.Structure):
+    _fields_ = [
+        ("image", C.c_void_p), ("depth", C.c_void_p), ("lut", C.c_void_p), ("out", C.c_void_p),
+        ("workspace", C.c_void_p),
+        ("N", C.c_int), ("H", C.c_int), ("W", C.c_int),
+    ]
+
+
 class ConvArgs(C.Structure):
     _fields_ = [
         ("x", C.c_void_p), ("w", C.c_void_p), ("bias", C.c_void_p), ("in_scale", C.c_void_p),

@@ -29,13 +29,16 @@ bool pdl_enabled() {
 }
 
 int device_sm_count() {
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 1;
-    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 1;
+  static std::atomic<int> sms[64];   // per device ordinal; 0 = not queried yet
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 1;
+  std::atomic<int>& slot = sms[dev & 63];
+  int n = slot.load(std::memory_order_relaxed);
+  if (n == 0) {
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 1;
+    slot.store(n, std::memory_order_relaxed);
   }
-  return sms;
+  return n;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
@@ -158,6 +161,11 @@ int ln3_planes_to_channels_last(const float* planes, int n_obj, int C, int H, in
                                 void* stream) {
   if (!planes || !out) return set_error(LN3_EINVAL, "planes_to_channels_last: null pointer");
   return planes_to_channels_last(planes, n_obj, C, H, W, out, static_cast<cudaStream_t>(stream));
+}
+
+int ln3_pack_frames(const ln3_pack_frames_args* args, void* stream) {
+  if (!args) return set_error(LN3_EINVAL, "pack_frames: null args");
+  return pack_frames(args, static_cast<cudaStream_t>(stream));
 }
 
 int ln3_conv_nhwc(const ln3_conv_args* args, void* stream) {

@@ -625,32 +625,35 @@ int fmha_fwd(const ln3_fmha_args* a, cudaStream_t stream) {
     return set_error(LN3_EINVAL, "fmha: pointers must be 16-byte aligned");
   // tuning knobs, read once: LN3_FMHA_POLY = exponentials per 8 on the FMA pipe (0, 2, 3, 4);
   // LN3_FMHA_PINGPONG = 1 enables the XU baton between the two softmax warpgroups (measured: no gain)
-  static int variant = -1;
-  if (variant < 0) {
+  static const int variant = [] {   // environment knobs: device-independent, read once (thread-safe static init)
     const char* ev = getenv("LN3_FMHA_POLY");
     int v = ev ? atoi(ev) : kPolyPer8Default;
     if (v != 0 && v != 2 && v != 3 && v != 4) v = kPolyPer8Default;
     const char* pp = getenv("LN3_FMHA_PINGPONG");
     const int ping = (pp && atoi(pp) != 0) ? 1 : 0;
-    cudaError_t e = cudaSuccess;
-    auto set = [&](auto* k) {
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kFmhaSmem);
-    };
-    set(fmha_fwd_kernel<0, false>); set(fmha_fwd_kernel<0, true>);
-    set(fmha_fwd_kernel<2, false>); set(fmha_fwd_kernel<2, true>);
-    set(fmha_fwd_kernel<3, false>); set(fmha_fwd_kernel<3, true>);
-    set(fmha_fwd_kernel<4, false>); set(fmha_fwd_kernel<4, true>);
-    set(fmha_fwd_kernel<0, false, true>); set(fmha_fwd_kernel<2, false, true>);
-    set(fmha_fwd_kernel<0, false, false, true>);
-    if (e != cudaSuccess) return set_error(LN3_ECUDA, "fmha: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     // LN3_FMHA_SPLIT = 1: 16 softmax warps, each tile's score columns split over two warpgroups
     const char* sp = getenv("LN3_FMHA_SPLIT");
     const int split = (sp && atoi(sp) != 0) ? 1 : 0;
     // LN3_FMHA_PTMEM = 1: P through tensor memory (TMEM A operand of P V)
     const char* pt = getenv("LN3_FMHA_PTMEM");
     const int ptmem = (pt && atoi(pt) != 0) ? 1 : 0;
-    variant = split ? 100 + (v == 2 ? 2 : 0) : (ptmem ? 200 : v * 2 + ping);
-  }
+    return split ? 100 + (v == 2 ? 2 : 0) : (ptmem ? 200 : v * 2 + ping);
+  }();
+  static DeviceOnce once;   // the shared-memory opt-in is per device
+  if (int rc = once.run([] {
+        cudaError_t e = cudaSuccess;
+        auto set = [&](auto* k) {
+          if (e == cudaSuccess) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kFmhaSmem);
+        };
+        set(fmha_fwd_kernel<0, false>); set(fmha_fwd_kernel<0, true>);
+        set(fmha_fwd_kernel<2, false>); set(fmha_fwd_kernel<2, true>);
+        set(fmha_fwd_kernel<3, false>); set(fmha_fwd_kernel<3, true>);
+        set(fmha_fwd_kernel<4, false>); set(fmha_fwd_kernel<4, true>);
+        set(fmha_fwd_kernel<0, false, true>); set(fmha_fwd_kernel<2, false, true>);
+        set(fmha_fwd_kernel<0, false, false, true>);
+        return e == cudaSuccess ? LN3_OK : set_error(LN3_ECUDA, "fmha: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      }))
+    return rc;
   if (a->k2 != nullptr || a->v2 != nullptr) {
     if (!a->k2 || !a->v2 || a->Lkv2 <= 0) return set_error(LN3_EINVAL, "fmha: k2/v2/Lkv2 must be given together");
     if (a->Lkv % kKT != 0) return set_error(LN3_EINVAL, "fmha: Lkv must be a multiple of 128 with a second K/V source");

@@ -360,15 +360,13 @@ template <int BN, bool HN>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
                        int num_sms, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<BN, HN>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg::kSmemBytes);
-    if (e != cudaSuccess) return set_error(LN3_ECUDA, "gemm: cudaFuncSetAttribute: %s",
-                                           cudaGetErrorString(e));
-    attr_set = true;
-  }
+  static DeviceOnce once;
+  if (int rc = once.run([] {
+        cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<BN, HN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             Cfg::kSmemBytes);
+        return e == cudaSuccess ? LN3_OK : set_error(LN3_ECUDA, "gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      }))
+    return rc;
   const int tiles = ((p.M + BM - 1) / BM) * (p.N / BN);
   const int grid = tiles < num_sms ? tiles : num_sms;
   cudaError_t e = launch_pdl(gemm_bf16_kernel<BN, HN>, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, stream, ta, tb, p);
@@ -807,14 +805,13 @@ size_t gemm_workspace_bytes() {
 template <int ACT, int OUT, bool HN>
 static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams p, int num_sms,
                         void* workspace, size_t workspace_bytes, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm2_bf16_kernel<ACT, OUT, HN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         kSmemBytes2);
-    if (e != cudaSuccess)
-      return set_error(LN3_ECUDA, "gemm2: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr_set = true;
-  }
+  static DeviceOnce once;
+  if (int rc = once.run([] {
+        cudaError_t e = cudaFuncSetAttribute(gemm2_bf16_kernel<ACT, OUT, HN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             kSmemBytes2);
+        return e == cudaSuccess ? LN3_OK : set_error(LN3_ECUDA, "gemm2: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      }))
+    return rc;
   const int tiles = ((p.M + 2 * BM - 1) / (2 * BM)) * (p.N / 256);
   const int num_kb = p.K / BK;
   const int all_pairs = num_sms / 2;

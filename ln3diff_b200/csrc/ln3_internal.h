@@ -3,6 +3,9 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <atomic>
+#include <mutex>
+
 #include "../../include/ln3b200.h"
 
 namespace ln3 {
@@ -11,6 +14,26 @@ namespace ln3 {
 int set_error(int code, const char* fmt, ...);
 void count_launch(int n = 1);
 int device_sm_count();
+// Per-device one-shot guard.  cudaFuncSetAttribute(MaxDynamicSharedMemorySize) and the SM count belong to
+// the device that is current at the call; one process may drive several GPUs and two host threads may race
+// the first call, so "done" is tracked per device ordinal (bit d of a mask) under a mutex.
+struct DeviceOnce {
+  std::atomic<unsigned long long> done{0};
+  std::mutex mu;
+  template <class F>
+  int run(F&& init) {   // init() -> LN3_OK or a negative LN3_E* code (after set_error)
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (done.load(std::memory_order_acquire) & bit) return LN3_OK;
+    std::lock_guard<std::mutex> lk(mu);
+    if (done.load(std::memory_order_relaxed) & bit) return LN3_OK;
+    const int rc = init();
+    if (rc == LN3_OK) done.fetch_or(bit, std::memory_order_release);
+    return rc;
+  }
+};
+
 // Programmatic dependent launch (opt-in with LN3_PDL=1; 12.05 vs 12.04 ms per forward, i.e. no gain): kernels that call pdl_wait() before their first
 // dependent memory access may be launched with this; their CTAs are scheduled while the previous
 // kernel of the stream drains, hiding launch latency and the per-CTA prologue.
@@ -55,6 +78,8 @@ int query_points(const ln3_query_points_args* a, cudaStream_t stream);
 int generate_rays(const float* cams, int V, int res, float* ray_o, float* ray_d, cudaStream_t stream);
 int planes_to_channels_last(const float* planes, int n_obj, int C, int H, int W, float* out,
                             cudaStream_t stream);
+
+int pack_frames(const ln3_pack_frames_args* a, cudaStream_t stream);
 
 int conv_nhwc(const ln3_conv_args* a, cudaStream_t stream);
 int groupnorm_stats(const float* x, const float* gamma, const float* beta, int N, int HW, int C, int G,

@@ -681,16 +681,16 @@ int render_views(const ln3_render_args* a, cudaStream_t stream) {
   p.dbg_inbox = a->dbg_inbox; p.dbg_inds = a->dbg_inds; p.dbg_order = a->dbg_order;
   p.dbg_zfine = a->dbg_zfine;
 
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(render_rays_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(sizeof(BlockSmem)));
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(render_rays_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               static_cast<int>(sizeof(BlockSmem)));
-    if (e != cudaSuccess) return set_error(LN3_ECUDA, "render: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr_set = true;
-  }
+  static DeviceOnce once;
+  if (int rc = once.run([] {
+        cudaError_t e = cudaFuncSetAttribute(render_rays_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             static_cast<int>(sizeof(BlockSmem)));
+        if (e == cudaSuccess)
+          e = cudaFuncSetAttribute(render_rays_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   static_cast<int>(sizeof(BlockSmem)));
+        return e == cudaSuccess ? LN3_OK : set_error(LN3_ECUDA, "render: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      }))
+    return rc;
   const int sms = device_sm_count();
   long long blocks = (rays + kWarpsPerBlock - 1) / kWarpsPerBlock;
   if (blocks > 2LL * sms) blocks = 2LL * sms;  // persistent: 2 CTAs per SM, grid-stride over rays
@@ -803,16 +803,16 @@ int query_points(const ln3_query_points_args* a, cudaStream_t stream) {
   p.bbox_min = 0.f; p.bbox_max = 0.f;
   p.no_filter = 1;
   p.mlp_tf32 = a->mlp_precision == LN3_MLP_TF32;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(query_points_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(sizeof(BlockSmem)));
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(query_points_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               static_cast<int>(sizeof(BlockSmem)));
-    if (e != cudaSuccess) return set_error(LN3_ECUDA, "query_points: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr_set = true;
-  }
+  static DeviceOnce once;
+  if (int rc = once.run([] {
+        cudaError_t e = cudaFuncSetAttribute(query_points_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             static_cast<int>(sizeof(BlockSmem)));
+        if (e == cudaSuccess)
+          e = cudaFuncSetAttribute(query_points_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   static_cast<int>(sizeof(BlockSmem)));
+        return e == cudaSuccess ? LN3_OK : set_error(LN3_ECUDA, "query_points: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      }))
+    return rc;
   const long long chunks = ((q.P + 31) / 32) * q.n_obj;
   long long blocks = (chunks + kWarpsPerBlock - 1) / kWarpsPerBlock;
   const int sms = device_sm_count();

@@ -8,6 +8,7 @@ import torch
 
 from .. import ops
 from .._lib import NORM_NONE, NORM_RMS
+from ._graph import ContextCache, ForwardGraph, capture_forward, graphs_enabled
 
 
 def pixart_forward(model, P: dict, cx: dict, ws: dict, x: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
@@ -71,3 +72,61 @@ def pixart_workspace(model, B: int) -> dict:
                 t0=e(B, 6 * D, dt=torch.float32), mod=e(model.depth, B, 6 * D, dt=torch.float32),
                 x=e(B, T, D, dt=torch.float32), xb=e(M, D), a=e(M, D), v=e(M, D), qkv=e(M, 3 * D), att=e(M, D), q=e(M, D),
                 h=e(M, int(model.mlp_ratio) * D))
+
+
+class PixArtGraphMixin:
+    """Derived-state management shared by the PixArt-style denoisers: bf16 repacks (`_prep`), per-batch
+    workspaces, the step-invariant conditioning cache with its model-owned static buffers, and the
+    CUDA-graph cache of a forward (see dit/_graph.py)."""
+
+    def _invalidate(self):
+        self._prep = None
+        self._ws = {}
+        self._ctx_cache = ContextCache()
+        self._ctx_static = {}
+        self._graphs = {}
+
+    def _apply(self, fn, *a, **kw):
+        self._invalidate()
+        return super()._apply(fn, *a, **kw)
+
+    def load_state_dict(self, *a, **kw):
+        self._invalidate()
+        return super().load_state_dict(*a, **kw)
+
+    def _static(self, key, make):
+        st = self._ctx_static.get(key)
+        if st is None:
+            st = self._ctx_static[key] = make()
+        return st
+
+    def _workspace(self, B):
+        ws = self._ws.get(B)
+        if ws is None:
+            ws = self._ws[B] = pixart_workspace(self, B)
+        return ws
+
+    def _graph(self, B, cx) -> ForwardGraph:
+        key = (B, cx["ckv"].shape[2], cx["dkv"].shape[2] if "dkv" in cx else 0, cx["rows"], cx["oconst"] is not None)
+        g = self._graphs.get(key)
+        if g is None:
+            dev = self.pos_embed.device
+            g = ForwardGraph()
+            g.key, g.cross_attention_rows = key, cx["rows"]
+            g.x = torch.zeros(B, 3 * self.in_channels, self.input_size, self.input_size, device=dev)
+            g.t = torch.zeros(B, device=dev)
+            ws = self._workspace(B)
+            capture_forward(g, lambda: pixart_forward(self, self._prep, cx, ws, g.x, g.t), dev)
+            self._graphs[key] = g
+        return g
+
+    def _run(self, x, t, cx):
+        """One forward: a replay of the cached CUDA graph (captured on first use), or the eager launch
+        sequence under LN3_CUDA_GRAPH=0 / inside a caller's own capture."""
+        if graphs_enabled() and not torch.cuda.is_current_stream_capturing():
+            g = self._graph(x.shape[0], cx)
+            g.x.copy_(x)
+            g.t.copy_(t)
+            g.replay()
+            return g.out.clone()
+        return pixart_forward(self, self._prep, cx, self._workspace(x.shape[0]), x.float().contiguous(), t)

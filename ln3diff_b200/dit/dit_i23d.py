@@ -18,7 +18,7 @@ import torch.nn as nn
 
 from .. import _lib, ops
 from .._lib import NORM_LAYER, NORM_NONE, NORM_RMS
-from ._pixart import pixart_forward, pixart_workspace
+from ._pixart import PixArtGraphMixin
 from .dit_trilatent import _attention_rows
 from .dit_models_xformers import (Attention, CaptionEmbedder, MemoryEfficientCrossAttention, T2IFinalLayer,
                                   TimestepEmbedder, _FusedMLP, _PatchEmbed, _RMSNormParam,
@@ -43,7 +43,7 @@ class ImageCondDiTBlockPixelArtRMSNorm(nn.Module):
         self.adaLN_modulation = None
 
 
-class DiT_I23D_PixelArt(nn.Module):
+class DiT_I23D_PixelArt(PixArtGraphMixin, nn.Module):
     _ln3_fused_in_scale = False
 
     def __init__(self, input_size=32, patch_size=2, in_channels=4, hidden_size=1152, depth=28, num_heads=16,
@@ -76,8 +76,7 @@ class DiT_I23D_PixelArt(nn.Module):
         self.cap_embedder = nn.Sequential(nn.LayerNorm(pooling_ctx_dim), nn.Linear(pooling_ctx_dim, hidden_size))
         self.attention_y_norm = _RMSNormParam(1024, eps=1e-5)
         self.initialize_weights()
-        self._prep = None
-        self._ctx_cache = None
+        self._invalidate()
 
     def initialize_weights(self):
         def _basic_init(m):
@@ -101,16 +100,6 @@ class DiT_I23D_PixelArt(nn.Module):
         D = self.pos_embed.shape[-1]
         pe = get_2d_sincos_pos_embed(D, (3, p * p)).reshape(3 * p * p, D)
         self.pos_embed.data.copy_(torch.from_numpy(pe).float().unsqueeze(0))
-
-    def _apply(self, fn, *a, **kw):
-        self._prep = None
-        self._ctx_cache = None
-        return super()._apply(fn, *a, **kw)
-
-    def load_state_dict(self, *a, **kw):
-        self._prep = None
-        self._ctx_cache = None
-        return super().load_state_dict(*a, **kw)
 
     @torch.no_grad()
     def prepare(self):
@@ -149,8 +138,8 @@ class DiT_I23D_PixelArt(nn.Module):
                 fc1_w=bf(b.mlp.mlp[0].weight), fc1_b=f32(b.mlp.mlp[1].bias),
                 fc2_w=bf(b.mlp.mlp[2].weight), fc2_b=f32(b.mlp.mlp[3].bias)))
         P["blocks"] = blocks
+        self._invalidate()
         self._prep = P
-        self._ws = {}
         return P
 
     @torch.no_grad()
@@ -158,25 +147,30 @@ class DiT_I23D_PixelArt(nn.Module):
         """Step-invariant conditioning, once per prompt batch: pooled-CLIP embedding, per-layer
         cross-attention K/V of the RMS-normed CLIP tokens, per-layer self-attention K/V of the
         projected DINO tokens."""
-        vec, ca = context["vector"], context["crossattn"]
-        key = (vec.data_ptr(), vec._version, ca.data_ptr(), ca._version, tuple(ca.shape))
-        if self._ctx_cache is not None and self._ctx_cache[0] == key:
-            return self._ctx_cache[1]
+        vec0, ca0 = vec, ca = context["vector"], context["crossattn"]
+        hit = self._ctx_cache.get(vec0, ca0)
+        if hit is not None:
+            return hit
         P, D = self._prep, self.embed_dim
         B, Lc, _ = ca.shape
         dev = ca.device
+        # model-owned static outputs (captured graphs read them through raw pointers; see dit/_graph.py)
+        st = self._static((B, Lc), lambda: dict(
+            cls=torch.empty(B, D, device=dev, dtype=torch.float32),
+            ckv=torch.empty(self.depth, B, Lc, 2 * D, device=dev, dtype=torch.bfloat16),
+            dkv=torch.empty(self.depth, B, Lc, 2 * D, device=dev, dtype=torch.bfloat16),
+            oc=torch.empty(self.depth, B, D, device=dev, dtype=torch.bfloat16)))
         vec = vec.float().contiguous()
         ones = torch.ones(1, device=dev)
         # cap_embedder: LayerNorm(affine, eps 1e-5) -> Linear.  LN(x)*w + b == LN(x)*(1 + (w-1)) + b
         vn = ops.norm_modulate(vec, norm=NORM_LAYER, eps=1e-5, shift=P["cap_ln_b"][None], scale=(P["cap_ln_w"] - 1)[None],
                                mod_rows=B)
-        cls = ops.gemm(vn, P["cap_w"], P["cap_b"], out_kind=ops.OUT_F32)            # (B, D) fp32
+        cls = ops.gemm(vn, P["cap_w"], P["cap_b"], out_kind=ops.OUT_F32, out=st["cls"])   # (B, D) fp32
         ca = ca.float()
         clip = ops.norm_modulate(ca[..., :1024].reshape(B * Lc, 1024).contiguous(), norm=NORM_RMS, weight=P["ynorm_w"], eps=1e-5)
         dino_in = ops.norm_modulate(ca[..., 1024:].reshape(B * Lc, -1).contiguous(), norm=NORM_NONE)
         dino = ops.gemm(ops.gemm(dino_in, P["d1_w"], P["d1_b"], act=ops.ACT_GELU_TANH), P["d2_w"], P["d2_b"])
-        ckv = torch.empty(self.depth, B, Lc, 2 * D, device=dev, dtype=torch.bfloat16)
-        dkv = torch.empty(self.depth, B, Lc, 2 * D, device=dev, dtype=torch.bfloat16)
+        ckv, dkv = st["ckv"], st["dkv"]
         for l, W in enumerate(P["blocks"]):
             ops.gemm(clip, W["ckv_w"], out=ckv[l].view(B * Lc, 2 * D), head_norm=W["ck_norm"], head_norm_sec_cols=D)
             ops.gemm(dino, W["kv_w"], W["kv_b"], out=dkv[l].view(B * Lc, 2 * D), head_norm=W["k_norm"], head_norm_sec_cols=D)
@@ -185,18 +179,11 @@ class DiT_I23D_PixelArt(nn.Module):
         # keys is uniform -> cross-attention output = to_out(v_row); see DiT_TriLatent._context_kv
         rows = _attention_rows(ca[..., :1024])
         if rows is not None:
-            oc = torch.empty(self.depth, B, D, device=dev, dtype=torch.bfloat16)
+            oc = st["oc"]
             for l, W in enumerate(P["blocks"]):
                 ops.gemm(ckv[l][:, 0, D:].contiguous(), W["co_w"], W["co_b"], out=oc[l])
             out.update(rows=rows, oconst=oc)
-        self._ctx_cache = (key, out)
-        return out
-
-    def _workspace(self, B):
-        ws = self._ws.get(B)
-        if ws is None:
-            ws = self._ws[B] = pixart_workspace(self, B)
-        return ws
+        return self._ctx_cache.put((vec0, ca0), out)
 
     @torch.no_grad()
     def forward(self, x, timesteps=None, context=None, y=None, get_attr="", **kwargs):
@@ -209,8 +196,7 @@ class DiT_I23D_PixelArt(nn.Module):
         if self._prep is None:
             self.prepare()
         t = timesteps.to(device=x.device, dtype=torch.float32).contiguous()
-        return pixart_forward(self, self._prep, self._context(context), self._workspace(x.shape[0]),
-                              x.float().contiguous(), t)
+        return self._run(x, t, self._context(context))
 
     @torch.no_grad()
     def forward_with_cfg(self, x, t, context, cfg_scale):

@@ -15,7 +15,8 @@ import torch.nn as nn
 
 from .. import _lib, ops
 from .._lib import NORM_LAYER, NORM_NONE, NORM_RMS
-from ._pixart import pixart_forward, pixart_workspace
+from ._graph import ContextCache, ForwardGraph, capture_forward, graphs_enabled
+from ._pixart import PixArtGraphMixin
 from .dit_models_xformers import (CaptionEmbedder, DiTBlock, FinalLayer, PixelArtTextCondDiTBlock, T2IFinalLayer,
                                   TextCondDiTBlock, TimestepEmbedder, _PatchEmbed,
                                   get_2d_sincos_pos_embed)
@@ -85,8 +86,16 @@ class DiT_TriLatent(nn.Module):
                     context_dim=context_dim) for _ in range(depth)])
         self.final_layer = final_layer_blk(hidden_size, patch_size, self.out_channels)
         self.initialize_weights()
+        self._invalidate()
+
+    def _invalidate(self):
+        """Drop everything derived from the parameters: bf16 repacks, workspaces, the cached conditioning
+        and its static buffers, and the captured graphs (they hold raw pointers into all of those)."""
         self._prep = None
-        self._ctx_cache = None
+        self._ws = {}
+        self._ctx_cache = ContextCache()
+        self._ctx_static = {}
+        self._graphs = {}
 
     # ------------------------------------------------------------------ init (reference :786-819)
     def initialize_weights(self):
@@ -119,13 +128,11 @@ class DiT_TriLatent(nn.Module):
 
     # ------------------------------------------------------------------ weight repack
     def _apply(self, fn, *a, **kw):
-        self._prep = None
-        self._ctx_cache = None
+        self._invalidate()
         return super()._apply(fn, *a, **kw)
 
     def load_state_dict(self, *a, **kw):
-        self._prep = None
-        self._ctx_cache = None
+        self._invalidate()
         return super().load_state_dict(*a, **kw)
 
     @torch.no_grad()
@@ -168,8 +175,8 @@ class DiT_TriLatent(nn.Module):
         P["pe_w"], P["pe_b"] = f32(self.x_embedder.proj.weight), f32(self.x_embedder.proj.bias)
         P["pos"] = f32(self.pos_embed)
         P["fin_w"], P["fin_b"] = f32(self.final_layer.linear.weight), f32(self.final_layer.linear.bias)
+        self._invalidate()
         self._prep = P
-        self._ws = {}
         return P
 
     def _workspace(self, B):
@@ -198,26 +205,33 @@ class DiT_TriLatent(nn.Module):
         output of every query is `to_out(v_row)`: one (D,) row per layer and sample, computed here once.
         `rows` is the contiguous block of samples that still needs real attention (the identical-token
         samples must form a prefix and/or suffix of the batch, as both CFG layouts of the reference do)."""
-        key = (context.data_ptr(), context._version, tuple(context.shape))
-        if self._ctx_cache is not None and self._ctx_cache[0] == key:
-            return self._ctx_cache[1]
+        hit = self._ctx_cache.get(context)
+        if hit is not None:
+            return hit
         P = self._prep
         B, Lc, Cc = context.shape
+        D = self.embed_dim
+        # Static, model-owned output buffers per (B, Lc): captured graphs read K/V and the closed-form rows
+        # through raw pointers, so a new prompt batch rewrites them in place and replays the same graph.
+        st = self._ctx_static.get((B, Lc))
+        if st is None:
+            st = dict(kv=torch.empty(B * Lc, self.depth * 2 * D, device=context.device, dtype=torch.bfloat16),
+                      oc=torch.empty(self.depth, B, D, device=context.device, dtype=torch.bfloat16))
+            self._ctx_static[(B, Lc)] = st
         c = context.reshape(B * Lc, Cc).float().contiguous()
         cb = ops.norm_modulate(c, norm=NORM_NONE)
         c1 = ops.gemm(cb, P["c1_w"], P["c1_b"], act=ops.ACT_GELU_TANH)
         c2 = ops.gemm(c1, P["c2_w"], P["c2_b"])
-        kv = ops.gemm(c2, P["kv_w"])  # (B*Lc, depth*2*D)
-        kv = kv.view(B, Lc, self.depth, 2, self.embed_dim)
+        ops.gemm(c2, P["kv_w"], out=st["kv"])  # (B*Lc, depth*2*D)
+        kv = st["kv"].view(B, Lc, self.depth, 2, D)
         out = dict(kv=kv, rows=(0, B), oconst=None)
         rows = _attention_rows(c2.view(B, Lc, -1))                        # one host sync per prompt batch
         if rows is not None:
-            oc = torch.empty(self.depth, B, self.embed_dim, device=context.device, dtype=torch.bfloat16)
+            oc = st["oc"]
             for l, W in enumerate(P["blocks"]):
                 ops.gemm(kv[:, 0, l, 1].contiguous(), W["o_w"], W["o_b"], out=oc[l])
             out = dict(kv=kv, rows=rows, oconst=oc)
-        self._ctx_cache = (key, out)
-        return out
+        return self._ctx_cache.put((context,), out)
 
     # ------------------------------------------------------------------ forward
     @torch.no_grad()
@@ -236,6 +250,17 @@ class DiT_TriLatent(nn.Module):
             self.prepare()
         cx = self._context_kv(context)
         t = timesteps.to(device=x.device, dtype=torch.float32).contiguous()
+        if graphs_enabled() and not torch.cuda.is_current_stream_capturing():
+            # one graph launch instead of ~270 kernel launches; the result leaves the static buffer
+            g = self._graph(x.shape[0], cx, shared_mod=False)
+            g.x.copy_(x)
+            g.t.copy_(t)
+            if in_scale is None:
+                g.in_scale.fill_(1.0)
+            else:
+                g.in_scale.copy_(in_scale)
+            g.replay()
+            return g.out.clone()
         return self._forward_impl(x.float().contiguous(), t, cx, in_scale)
 
     @torch.no_grad()
@@ -309,47 +334,37 @@ class DiT_TriLatent(nn.Module):
         return ops.final_layer(xs, mod[:, f0:f0 + D], mod[:, f0 + D:f0 + 2 * D], P["fin_w"],
                                P["fin_b"], self.input_size)
 
+    def _graph(self, B, cx, shared_mod: bool) -> ForwardGraph:
+        """The captured forward for batch B and the launch sequence `cx` implies (context length,
+        closed-form row split); captured on first use, then cached on the model."""
+        key = (B, cx["kv"].shape[1], cx["rows"], cx["oconst"] is not None, bool(shared_mod))
+        g = self._graphs.get(key)
+        if g is None:
+            dev = self.pos_embed.device
+            g = ForwardGraph()
+            g.key, g.cross_attention_rows = key, cx["rows"]
+            g.x = torch.zeros(B, 3 * self.in_channels, self.input_size, self.input_size, device=dev)
+            g.t = torch.zeros(B, device=dev)
+            g.in_scale = torch.ones(B, device=dev)
+            # shared_mod: the caller writes one modulation_table() row per step into g.mod (g.t is then unused)
+            g.mod = torch.zeros(1, self._prep["ada_w"].shape[0], device=dev) if shared_mod else None
+            capture_forward(g, lambda: self._forward_impl(g.x, g.t, cx, g.in_scale, g.mod), dev)
+            self._graphs[key] = g
+        return g
+
     @torch.no_grad()
-    def capture_graph(self, B, context, shared_mod: bool = False):
-        """CUDA-graph one forward for a fixed batch B and a fixed (step-invariant) context: the ~250
-        launches of a forward replay as one graph launch, removing the host launch gaps between the
-        short kernels.  Returns an object with static inputs .x (B,3C,S,S), .t (B,), .in_scale (B,),
-        static output .out and .replay()."""
+    def capture_graph(self, B, context, shared_mod: bool = False) -> ForwardGraph:
+        """CUDA graph of one forward for batch B conditioned on `context`: the ~270 launches of a forward
+        replay as one graph launch.  Computes the step-invariant conditioning of `context` (into the model's
+        static buffers) and returns the graph cached for this launch-sequence shape -- a later call with a
+        new prompt batch of the same shape refreshes the buffers and returns the SAME graph object, it does
+        not capture again.  Static inputs .x (B,3C,S,S), .t (B,), .in_scale (B,), [.mod]; static output .out;
+        .replay().  The graph always reflects the context of the most recent `capture_graph`/`forward` call."""
         if self._prep is None:
             self.prepare()
         if isinstance(context, dict):
             context = context["crossattn"]
-        dev = context.device
-        kv = self._context_kv(context)
-
-        class _G:
-            pass
-
-        g = _G()
-        g.kv = kv  # keep the cached K/V (+ closed-form rows) alive: the graph holds raw pointers into them
-        g.cross_attention_rows = kv["rows"]
-        g.x = torch.zeros(B, 3 * self.in_channels, self.input_size, self.input_size, device=dev)
-        g.t = torch.zeros(B, device=dev)
-        g.in_scale = torch.ones(B, device=dev)
-        # shared_mod: the caller writes one modulation_table() row per step into g.mod (g.t is then unused)
-        g.mod = torch.zeros(1, self._prep["ada_w"].shape[0], device=dev) if shared_mod else None
-        side = torch.cuda.Stream(device=dev)
-        side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):
-            for _ in range(2):  # warm-up outside capture (function attributes, workspaces)
-                self._forward_impl(g.x, g.t, kv, g.in_scale, g.mod)
-        torch.cuda.current_stream(dev).wait_stream(side)
-        g.graph = torch.cuda.CUDAGraph()
-        n0 = _lib.launch_count()
-        with torch.cuda.graph(g.graph):
-            g.out = self._forward_impl(g.x, g.t, kv, g.in_scale, g.mod)
-        g.n_kernels = _lib.launch_count() - n0
-
-        def replay():
-            g.graph.replay()
-            _lib.add_launch_count(g.n_kernels)
-        g.replay = replay
-        return g
+        return self._graph(B, self._context_kv(context), shared_mod)
 
     @torch.no_grad()
     def forward_with_cfg(self, x, t, context, cfg_scale):
@@ -360,7 +375,7 @@ class DiT_TriLatent(nn.Module):
         return torch.cat([half, half], dim=0)
 
 
-class DiT_TriLatent_PixelArt(nn.Module):
+class DiT_TriLatent_PixelArt(PixArtGraphMixin, nn.Module):
     """reference dit/dit_trilatent.py:146-246: the PixArt-style T23D denoiser -- one shared adaLN
     (`adaLN_modulation` on t_emb + cap_embedder(pooled CLIP)) plus per-block `scale_shift_table`,
     `PixelArtTextCondDiTBlock` blocks, `T2IFinalLayer`.  context = {'vector': (B, context_dim) pooled
@@ -399,8 +414,7 @@ class DiT_TriLatent_PixelArt(nn.Module):
         self.adaLN_modulation = nn.Sequential(nn.SiLU(), nn.Linear(hidden_size, 6 * hidden_size, bias=True))
         self.cap_embedder = nn.Sequential(nn.LayerNorm(context_dim), nn.Linear(context_dim, hidden_size))
         self.initialize_weights()
-        self._prep = None
-        self._ctx_cache = None
+        self._invalidate()
 
     def initialize_weights(self):
         def _basic_init(m):
@@ -422,16 +436,6 @@ class DiT_TriLatent_PixelArt(nn.Module):
         D = self.pos_embed.shape[-1]
         pe = get_2d_sincos_pos_embed(D, (3, p * p)).reshape(3 * p * p, D)
         self.pos_embed.data.copy_(torch.from_numpy(pe).float().unsqueeze(0))
-
-    def _apply(self, fn, *a, **kw):
-        self._prep = None
-        self._ctx_cache = None
-        return super()._apply(fn, *a, **kw)
-
-    def load_state_dict(self, *a, **kw):
-        self._prep = None
-        self._ctx_cache = None
-        return super().load_state_dict(*a, **kw)
 
     @torch.no_grad()
     def prepare(self):
@@ -458,25 +462,29 @@ class DiT_TriLatent_PixelArt(nn.Module):
             co_w=bf(b.cross_attn.to_out[0].weight), co_b=f32(b.cross_attn.to_out[0].bias),
             fc1_w=bf(b.mlp.mlp[0].weight), fc1_b=f32(b.mlp.mlp[1].bias),
             fc2_w=bf(b.mlp.mlp[2].weight), fc2_b=f32(b.mlp.mlp[3].bias)) for b in self.blocks]
+        self._invalidate()
         self._prep = P
-        self._ws = {}
         return P
 
     @torch.no_grad()
     def _context(self, context):
-        vec, ca = context["vector"], context["crossattn"]
-        key = (vec.data_ptr(), vec._version, ca.data_ptr(), ca._version, tuple(ca.shape))
-        if self._ctx_cache is not None and self._ctx_cache[0] == key:
-            return self._ctx_cache[1]
+        vec0, ca0 = vec, ca = context["vector"], context["crossattn"]
+        hit = self._ctx_cache.get(vec0, ca0)
+        if hit is not None:
+            return hit
         P, D = self._prep, self.embed_dim
         B, Lc, Cc = ca.shape
+        st = self._static((B, Lc), lambda: dict(
+            cls=torch.empty(B, D, device=ca.device, dtype=torch.float32),
+            ckv=torch.empty(self.depth, B, Lc, 2 * D, device=ca.device, dtype=torch.bfloat16),
+            oc=torch.empty(self.depth, B, D, device=ca.device, dtype=torch.bfloat16)))
         vec = vec.float().contiguous()
         # cap_embedder: LayerNorm(affine, eps 1e-5) -> Linear.  LN(x)*w + b == LN(x)*(1 + (w-1)) + b
         vn = ops.norm_modulate(vec, norm=NORM_LAYER, eps=1e-5, shift=P["cap_ln_b"][None], scale=(P["cap_ln_w"] - 1)[None],
                                mod_rows=B)
-        cls = ops.gemm(vn, P["cap_w"], P["cap_b"], out_kind=ops.OUT_F32)            # (B, D) fp32
+        cls = ops.gemm(vn, P["cap_w"], P["cap_b"], out_kind=ops.OUT_F32, out=st["cls"])   # (B, D) fp32
         ca2 = ca.float().reshape(B * Lc, Cc).contiguous()
-        ckv = torch.empty(self.depth, B, Lc, 2 * D, device=ca.device, dtype=torch.bfloat16)
+        ckv = st["ckv"]
         for l, W in enumerate(P["blocks"]):
             y = ops.norm_modulate(ca2, norm=NORM_RMS, weight=W["yn_w"], eps=1e-5)
             ops.gemm(y, W["ckv_w"], out=ckv[l].view(B * Lc, 2 * D))
@@ -484,18 +492,11 @@ class DiT_TriLatent_PixelArt(nn.Module):
         # identical text tokens (the zero-embedding CFG half): closed-form cross-attention, see DiT_TriLatent
         rows = _attention_rows(ca.float())
         if rows is not None:
-            oc = torch.empty(self.depth, B, D, device=ca.device, dtype=torch.bfloat16)
+            oc = st["oc"]
             for l, W in enumerate(P["blocks"]):
                 ops.gemm(ckv[l][:, 0, D:].contiguous(), W["co_w"], W["co_b"], out=oc[l])
             out.update(rows=rows, oconst=oc)
-        self._ctx_cache = (key, out)
-        return out
-
-    def _workspace(self, B):
-        ws = self._ws.get(B)
-        if ws is None:
-            ws = self._ws[B] = pixart_workspace(self, B)
-        return ws
+        return self._ctx_cache.put((vec0, ca0), out)
 
     @torch.no_grad()
     def forward(self, x, timesteps=None, context=None, y=None, get_attr="", **kwargs):
@@ -507,8 +508,7 @@ class DiT_TriLatent_PixelArt(nn.Module):
         if self._prep is None:
             self.prepare()
         t = timesteps.to(device=x.device, dtype=torch.float32).contiguous()
-        return pixart_forward(self, self._prep, self._context(context), self._workspace(x.shape[0]),
-                              x.float().contiguous(), t)
+        return self._run(x, t, self._context(context))
 
     @torch.no_grad()
     def forward_with_cfg(self, x, t, context, cfg_scale):

@@ -22,7 +22,7 @@ class ImportanceRenderer(torch.nn.Module):
     def __init__(self):
         super().__init__()
         self.plane_axes = generate_planes()
-        self._cl_cache = None
+        self._cl_cache = None   # (planes tensor (strong ref), its _version, channels-last copy)
 
     @staticmethod
     def _check_options(o):
@@ -38,10 +38,14 @@ class ImportanceRenderer(torch.nn.Module):
             raise NotImplementedError("density_noise is a training-time option")
 
     def _planes_cl(self, planes):
-        key = (planes.data_ptr(), planes._version, tuple(planes.shape))
-        if self._cl_cache is None or self._cl_cache[0] != key:
-            self._cl_cache = (key, ops.planes_to_channels_last(planes.float().contiguous()))
-        return self._cl_cache[1]
+        """Channels-last copy of `planes`, reused while the caller keeps passing the same, unmodified tensor
+        object (one object is rendered from many cameras, one `forward` per view,
+        nsr/train_util_diffusion.py:292-302).  Identity + version, with the tensor kept alive: a different
+        object's planes at a recycled address can never hit."""
+        c = self._cl_cache
+        if c is None or c[0] is not planes or c[1] != planes._version:
+            c = self._cl_cache = (planes, planes._version, ops.planes_to_channels_last(planes.float().contiguous()))
+        return c[2]
 
     @torch.no_grad()
     def forward(self, planes, decoder, ray_origins, ray_directions, rendering_options, return_meta=False):

@@ -337,6 +337,37 @@ def planes_to_channels_last(planes: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def pack_frames(image: torch.Tensor, depth: torch.Tensor | None = None, lut_u8: torch.Tensor | None = None,
+                out: torch.Tensor | None = None) -> torch.Tensor:
+    """image (N,3,H,W) fp32 in [-1,1] [+ depth (N,1,H,W) fp32, lut_u8 (256,3) uint8 colormap bytes] ->
+    uint8 HWC video frames (N, H, W, 3), or (N, H, 2W, 3) = [image | colour-mapped, per-view normalised
+    depth] (the frame TrainLoopDiffusionWithRec.render_video_given_triplane appends,
+    nsr/train_util_diffusion.py:292-376)."""
+    _cuda(image, "image", torch.float32)
+    _req(image.dim() == 4 and image.shape[1] == 3 and image.is_contiguous(), "image must be contiguous (N,3,H,W)")
+    N, _, H, W = image.shape
+    _req(W % 4 == 0, "W must be a multiple of 4")
+    a = _lib.PackFramesArgs()
+    Wout = W
+    ws = None
+    if depth is not None:
+        _cuda(depth, "depth", torch.float32)
+        _req(depth.shape == (N, 1, H, W) and depth.is_contiguous(), "depth must be contiguous (N,1,H,W)")
+        _req(lut_u8 is not None, "depth needs the colormap byte table")
+        _cuda(lut_u8, "lut_u8", torch.uint8)
+        _req(lut_u8.shape == (256, 3) and lut_u8.is_contiguous(), "lut_u8 must be contiguous (256,3) uint8")
+        ws = torch.empty(2 * N, device=image.device, dtype=torch.float32)
+        a.depth, a.lut, a.workspace = depth.data_ptr(), lut_u8.data_ptr(), ws.data_ptr()
+        Wout = 2 * W
+    if out is None:
+        out = torch.empty((N, H, Wout, 3), device=image.device, dtype=torch.uint8)
+    _cuda(out, "out", torch.uint8)
+    _req(out.shape == (N, H, Wout, 3) and out.is_contiguous(), "out must be contiguous (N,H,Wout,3) uint8")
+    a.image, a.out, a.N, a.H, a.W = image.data_ptr(), out.data_ptr(), N, H, W
+    _lib.check(_lib.lib().ln3_pack_frames(C.byref(a), _lib.current_stream()), "ln3_pack_frames")
+    return out
+
+
 def render_views(planes_cl: torch.Tensor, ray_o: torch.Tensor, ray_d: torch.Tensor,
                  noise_coarse: torch.Tensor, noise_fine: torch.Tensor, osg: tuple, *,
                  view_obj: torch.Tensor | None = None, views_per_obj: int = 0, group_size: int = 1,

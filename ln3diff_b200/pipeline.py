@@ -16,6 +16,7 @@ import os
 import torch
 
 from . import ops
+from .dit._graph import graphs_enabled
 from .sgm.modules.diffusionmodules.discretizer import LegacyDDPMDiscretization
 
 
@@ -58,11 +59,13 @@ def sample_t23d(model, randn: torch.Tensor, c: dict, uc: dict, num_steps: int = 
     ctx = torch.cat((uc["crossattn"], c["crossattn"]), 0).contiguous()   # VanillaCFG order: (uc, c)
     x = (randn.float() * tables["init_scale"]).contiguous()
     xa, xb = x, torch.empty_like(x)
-    if use_graph and num_steps >= 4:
-        # one CUDA graph = one DiT forward of the 2B CFG batch; replayed every step
+    if use_graph and graphs_enabled() and hasattr(model, "capture_graph"):
+        # one CUDA graph = one DiT forward of the 2B CFG batch; replayed every step.  The graph is cached on
+        # the model per launch-sequence shape: this call computes the prompt batch's step-invariant
+        # conditioning into the model's static buffers and captures only the first time a shape is seen.
         # every sample of a step shares its timestep: the adaLN modulations of all steps in one pass
         shared = hasattr(model, "modulation_table") and os.environ.get("LN3_SHARED_MODULATION", "1") != "0"
-        g = model.capture_graph(2 * B, ctx, shared_mod=True) if shared else model.capture_graph(2 * B, ctx)
+        g = model.capture_graph(2 * B, ctx, shared_mod=shared)
         mod_table = model.modulation_table(tables["t_idx"][:num_steps, 0]) if shared else None
         for i in range(num_steps):
             g.x[:B].copy_(xa)
@@ -88,33 +91,48 @@ def sample_t23d(model, randn: torch.Tensor, c: dict, uc: dict, num_steps: int = 
 
 @torch.no_grad()
 def decode_and_render(decoder, latents: torch.Tensor, cameras: torch.Tensor, resolution: int = 128,
-                      scaling_divider: float = 0.96806, noise: tuple | None = None, mlp_tf32: bool = True):
+                      scaling_divider: float = 0.96806, noise: tuple | None = None, mlp_tf32: bool = True,
+                      max_views_per_launch: int | None = None):
     """`TrainLoopDiffusionWithRec.render_video_given_triplane` (nsr/train_util_diffusion.py:176-382)
     without the host round trips: latents (B,12,32,32) -> tri-planes (decoded ONCE; the reference
     decodes twice, :204-206 and :268-270) -> every camera of `cameras` (V,25) for every latent in
-    one fused renderer launch.  Per-view global reductions (group_size=1) reproduce the reference's
+    fused renderer launches.  Per-view global reductions (group_size=1) reproduce the reference's
     one-view-per-call loop (:292-302).  Returns image_raw (B,V,3,H,W) in [-1,1], image_depth
     (B,V,1,H,W), image_mask (B,V,1,H,W).  `noise` = (coarse, fine) tensors of shape (B*V, H*W, 64) to
-    override the device RNG (tests)."""
+    override the device RNG (tests).  The sampling noise costs 512 B per ray, so the views are rendered in
+    launches of whole objects with at most `max_views_per_launch` views (default: ~2 GiB of noise)."""
     if not latents.is_cuda:
         raise RuntimeError("decode_and_render runs on CUDA only (no CPU fallback)")
     B, V = latents.shape[0], cameras.shape[0]
-    planes_cl = decoder.decode_to_channels_last(latents, in_mul=scaling_divider)     # (B,3,128,128,32)
-    cams = cameras.to(latents.device, torch.float32).repeat(B, 1).contiguous()       # (B*V, 25)
-    ray_o, ray_d = ops.generate_rays(cams, resolution)
-    M = resolution * resolution
-    if noise is None:
-        noise = (torch.rand(B * V, M, 64, device=latents.device), torch.rand(B * V, M, 64, device=latents.device))
-    kw = decoder.rendering_kwargs
-    out = ops.render_views(planes_cl, ray_o, ray_d, noise[0].contiguous(), noise[1].contiguous(),
-                           decoder.triplane_decoder.decoder.raw_parameters(), views_per_obj=V, group_size=1,
-                           box_warp=kw.get("box_warp", 0.9), bbox_min=kw.get("sampler_bbox_min", -0.45),
-                           bbox_max=kw.get("sampler_bbox_max", 0.45), white_back=kw.get("white_back", True),
-                           mlp_tf32=mlp_tf32)
     H = W = resolution
-    w = out["weights"].view(B, V, 1, H, W)
-    return dict(image_raw=out["rgb"].view(B, V, 3, H, W), image_depth=out["depth"].view(B, V, 1, H, W),
-                weights_samples=w, image_mask=w * (1 + 2 * 0.001) - 0.001)
+    M = resolution * resolution
+    dev = latents.device
+    planes_cl = decoder.decode_to_channels_last(latents, in_mul=scaling_divider)     # (B,3,128,128,32)
+    cams1 = cameras.to(dev, torch.float32).contiguous()                               # (V, 25)
+    ray_o1, ray_d1 = ops.generate_rays(cams1, resolution)                              # shared by every object
+    if max_views_per_launch is None:
+        max_views_per_launch = max(V, (2 << 30) // (2 * M * 64 * 4))
+    obj_per_launch = max(1, min(B, max_views_per_launch // V))
+    kw = decoder.rendering_kwargs
+    osg = decoder.triplane_decoder.decoder.raw_parameters()
+    rgb = torch.empty(B, V, 3, H, W, device=dev)
+    depth = torch.empty(B, V, 1, H, W, device=dev)
+    wts = torch.empty(B, V, 1, H, W, device=dev)
+    for b0 in range(0, B, obj_per_launch):
+        nb = min(obj_per_launch, B - b0)
+        if noise is None:
+            nz = (torch.rand(nb * V, M, 64, device=dev), torch.rand(nb * V, M, 64, device=dev))
+        else:
+            nz = (noise[0][b0 * V:(b0 + nb) * V].contiguous(), noise[1][b0 * V:(b0 + nb) * V].contiguous())
+        out = ops.render_views(planes_cl[b0:b0 + nb], ray_o1.repeat(nb, 1, 1), ray_d1.repeat(nb, 1, 1), nz[0], nz[1],
+                               osg, views_per_obj=V, group_size=1,
+                               box_warp=kw.get("box_warp", 0.9), bbox_min=kw.get("sampler_bbox_min", -0.45),
+                               bbox_max=kw.get("sampler_bbox_max", 0.45), white_back=kw.get("white_back", True),
+                               mlp_tf32=mlp_tf32)
+        rgb[b0:b0 + nb].copy_(out["rgb"].view(nb, V, 3, H, W))
+        depth[b0:b0 + nb].copy_(out["depth"].view(nb, V, 1, H, W))
+        wts[b0:b0 + nb].copy_(out["weights"].view(nb, V, 1, H, W))
+    return dict(image_raw=rgb, image_depth=depth, weights_samples=wts, image_mask=wts * (1 + 2 * 0.001) - 0.001)
 
 
 @torch.no_grad()
@@ -124,3 +142,95 @@ def generate_t23d(model, decoder, randn, c, uc, cameras, num_steps: int = 250, s
     DiffusionEngineLSGM.eval_cldm, nsr/lsgm/sgm_DiffusionEngine.py:410-523, minus conditioner + video sink)."""
     latents = sample_t23d(model, randn, c, uc, num_steps, scale)
     return latents, decode_and_render(decoder, latents, cameras, resolution)
+
+
+# ---------------------------------------------------------------------------------------------- multi-GPU
+def shard_range(n_total: int, world: int, rank: int) -> tuple[int, int, int]:
+    """Contiguous block of ceil(P/G) prompts per rank: returns (lo, hi, per) with
+    hi - lo <= per valid prompts on this rank (trailing ranks may hold fewer, or none)."""
+    per = -(-n_total // world)
+    lo = min(rank * per, n_total)
+    return lo, min(lo + per, n_total), per
+
+
+@torch.no_grad()
+def generate_sharded(model, decoder, c_all: dict, uc_all: dict, cameras: torch.Tensor, *, seed: int = 41,
+                     num_steps: int = 250, scale: float = 6.5, resolution: int = 256, batch: int = 32,
+                     with_depth: bool = False, device=None, group=None, gather: bool = True,
+                     sample_fn=None, render_fn=None, pack_fn=None) -> dict:
+    """Text-to-3D for a list of P prompts sharded over the ranks of `group` (BASELINE configs[4]):
+
+        one global CPU-generator noise draw `manual_seed(seed); randn(P, 12, 32, 32)` sliced per rank (the
+        reference slices its own global draw the same way, nsr/lsgm/sgm_DiffusionEngine.py:395-398,456-470)
+        -> sample_t23d -> decode_and_render at `resolution` for every camera -> uint8 HWC frames (frame sink)
+        -> ONE NCCL all-gather of the frames per local batch, issued on a side stream so that it overlaps
+        the next batch's sampling (nsr/train_util_diffusion.py:177-382 is the per-rank body it replaces).
+
+    c_all / uc_all = {'crossattn': (P, 77, ctx_dim)} for ALL prompts on every rank (the reference's ranks all
+    read the same caption list); each rank uses rows [lo, hi).  There is no collective inside the data path;
+    ranks holding fewer than ceil(P/G) prompts contribute zero frames that are trimmed from the result.
+    Returns {'latents': (n_local,12,32,32), 'frames': uint8 (n_local, V, H, Wout, 3), 'frames_all': uint8
+    (P, V, H, Wout, 3) on every rank (None if not gathered), 'shard': (lo, hi), 'gather_bytes_per_rank': int}.
+    `sample_fn / render_fn / pack_fn` replace the three CUDA stages (the world-size-2 gloo test drives the
+    sharding, padding and gather logic of THIS function with CPU stand-ins)."""
+    import torch.distributed as dist
+    distributed = dist.is_available() and dist.is_initialized()
+    world = dist.get_world_size(group) if distributed else 1
+    rank = dist.get_rank(group) if distributed else 0
+    P = c_all["crossattn"].shape[0]
+    lo, hi, per = shard_range(P, world, rank)
+    dev = torch.device(device) if device is not None else next(model.parameters()).device
+    V = cameras.shape[0]
+    g = torch.Generator().manual_seed(seed)
+    randn_all = torch.randn(P, 12, 32, 32, generator=g)                      # identical on every rank
+    if sample_fn is None:
+        sample_fn = lambda x, c, uc: sample_t23d(model, x, c, uc, num_steps, scale)
+    if render_fn is None:
+        render_fn = lambda lat: decode_and_render(decoder, lat, cameras, resolution)
+    if pack_fn is None:
+        from .frames import FrameSink
+        sink = FrameSink(dev)
+        pack_fn = lambda r: sink.pack(r["image_raw"], r["image_depth"] if with_depth else None)
+    Wout = resolution * (2 if with_depth else 1)
+    frames = torch.zeros(per, V, resolution, Wout, 3, dtype=torch.uint8, device=dev)
+    latents = torch.zeros(per, 12, 32, 32, device=dev)
+    do_gather = gather and world > 1
+    frames_all = torch.empty(world, per, V, resolution, Wout, 3, dtype=torch.uint8, device=dev) if do_gather else None
+    cuda = dev.type == "cuda"
+    side = torch.cuda.Stream(device=dev) if (do_gather and cuda) else None
+    pending = []
+    for b0 in range(0, per, batch):                                          # same trip count on every rank
+        b1 = min(b0 + batch, per)
+        n_valid = max(0, min(hi - lo, b1) - b0)
+        if n_valid > 0:
+            sl = slice(lo + b0, lo + b0 + n_valid)
+            x = randn_all[sl].to(dev, non_blocking=True)
+            c = {"crossattn": c_all["crossattn"][sl].to(dev, non_blocking=True)}
+            uc = {"crossattn": uc_all["crossattn"][sl].to(dev, non_blocking=True)}
+            lat = sample_fn(x, c, uc)
+            latents[b0:b0 + n_valid].copy_(lat)
+            frames[b0:b0 + n_valid].copy_(pack_fn(render_fn(lat)))
+        if do_gather:
+            if b0 == 0 and b1 == per:                                        # one batch: gather straight into place
+                src, dst = frames, frames_all
+            else:
+                src = frames[b0:b1].contiguous()
+                dst = torch.empty(world, b1 - b0, *frames.shape[1:], dtype=torch.uint8, device=dev)
+            if side is not None:
+                side.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(side):
+                    dist.all_gather_into_tensor(dst.view(-1), src.view(-1), group=group)
+                    if dst is not frames_all:
+                        frames_all[:, b0:b1].copy_(dst)
+                src.record_stream(side); dst.record_stream(side)
+            else:
+                dist.all_gather_into_tensor(dst.view(-1), src.view(-1), group=group)
+                if dst is not frames_all:
+                    frames_all[:, b0:b1].copy_(dst)
+            pending.append((src, dst))
+    if side is not None:
+        torch.cuda.current_stream(dev).wait_stream(side)
+    n_local = hi - lo
+    out_all = frames_all.view(world * per, V, resolution, Wout, 3)[:P] if do_gather else (frames[:P] if gather else None)
+    return dict(latents=latents[:n_local], frames=frames[:n_local], frames_all=out_all, shard=(lo, hi),
+                gather_bytes_per_rank=int(frames.numel()) if do_gather else 0)

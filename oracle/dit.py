@@ -113,13 +113,17 @@ def unpatchify_rollout(x: torch.Tensor, out_ch: int, patch: int = 2) -> torch.Te
 
 
 def dit_t23d_forward(sd: dict, arch: str, x: torch.Tensor, timesteps: torch.Tensor,
-                     context: torch.Tensor) -> torch.Tensor:
+                     context: torch.Tensor, first_blocks: int | None = None) -> torch.Tensor:
     """DiT_TriLatent(vit_blk=TextCondDiTBlock, FinalLayer).forward, fp32.
 
     x (B,12,32,32); timesteps (B,) int64 index / float; context (B,77,ctx_dim) -> (B,12,32,32).
+    `first_blocks` runs only the first n transformer blocks (bench.py's bounded CPU-timing sample; every
+    block costs the same) -- never used by a parity test.
     """
     cfg = DIT_SIZES[arch]
     heads, depth = cfg["heads"], cfg["depth"]
+    if first_blocks is not None:
+        depth = min(depth, first_blocks)
     sd = {k: v.float() for k, v in sd.items()}
     x = x.float()
     t = timestep_embedding(timesteps)

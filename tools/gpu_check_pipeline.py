@@ -26,6 +26,6 @@ for _ in range(n):
 e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / n
-print(f"closed_form={os.environ.get('LN3_UNCOND_CLOSED_FORM', '1')} rows={m._ctx_cache[1]['rows']}: {ms:.1f} ms per batch, "
+print(f"closed_form={os.environ.get('LN3_UNCOND_CLOSED_FORM', '1')} rows={m._ctx_cache.value['rows']}: {ms:.1f} ms per batch, "
       f"{ms / 250:.3f} ms/step, {B / (ms / 1e3):.3f} latents/s, finite={bool(torch.isfinite(out).all())}, "
       f"checksum={float(out.double().abs().mean()):.6f}")
