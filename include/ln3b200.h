@@ -166,6 +166,16 @@ typedef struct ln3_norm_modulate_args {
   const void* resid_bcast;
   long long resid_bcast_ld;
   int resid_bcast_rows, resid_row_begin, resid_row_end;
+  /* optional, with resid_bcast: the rows OUTSIDE [resid_row_begin, resid_row_end) additionally add their own
+   * row of `resid` under a second gate,
+   *   x[r,:] += resid_out_gate[(r / resid_out_gate_rows), :] * resid[r,:] + resid_bcast[...]
+   * -- for those samples the preceding `x += gate_msa * attn` (dit/dit_models_xformers.py:311-312) has not been
+   * applied yet: the pass that applies it exists only to produce the bf16 cross-attention query input, which the
+   * closed-form samples do not need, so their self-attention and cross-attention residuals are applied together
+   * here and the in-between pass covers the attended rows only.  NULL -> unused. */
+  const float* resid_out_gate;
+  long long resid_out_gate_ld;
+  int resid_out_gate_rows;
 } ln3_norm_modulate_args;
 
 int ln3_norm_modulate(const ln3_norm_modulate_args* args, void* stream);
@@ -334,7 +344,9 @@ int ln3_planes_to_channels_last(const float* planes, int n_obj, int C, int H, in
  *   image  fp32 [N,3,H,W] in [-1,1] ('image_raw')
  *   depth  fp32 [N,1,H,W] ('image_depth') or NULL
  *   out    u8 [N, H, Wout, 3] (HWC video frames), Wout = W, or 2W with depth: [image | colour-mapped depth]
- * Arithmetic as the reference: byte = uint8(clip(float64(v) * 127.5 + 127.5, 0, 255)) (truncation);
+ * Arithmetic as the reference: byte = uint8(clip(v * 127.5 + 127.5, 0, 255)) (truncation), evaluated in float64
+ * for the video frame with depth (the cat with the float64 colormap output promotes it, :340-345,366-368) and in
+ * float32 (two rounded operations) for the image-only frame (the per-view image dump, :350-353);
  * depth -> (d - min_view) / (max_view - min_view) in fp32, colormap index min(trunc(x * 256), 255), the
  * byte table `lut` u8 [256,3] = uint8(clip((cmap_rgb * 2 - 1) * 127.5 + 127.5, 0, 255)) of the 256-entry
  * colormap (plt.cm.viridis in the reference); max == min gives the colormap's "bad" colour (0,0,0).

@@ -57,6 +57,7 @@ class NormModulateArgs(C.Structure):
         ("resid_gate_ld", C.c_longlong), ("resid_gate_rows", C.c_int),
         ("resid_bcast", C.c_void_p), ("resid_bcast_ld", C.c_longlong), ("resid_bcast_rows", C.c_int),
         ("resid_row_begin", C.c_int), ("resid_row_end", C.c_int),
+        ("resid_out_gate", C.c_void_p), ("resid_out_gate_ld", C.c_longlong), ("resid_out_gate_rows", C.c_int),
     ]
 
 

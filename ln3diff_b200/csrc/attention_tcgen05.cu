@@ -75,6 +75,10 @@ struct FmhaParams {
   int B, H, nq;  // work items = B * H * nq query-row pairs (256 rows each)
   float rcp_nq, rcp_H;  // 1 / nq, 1 / H (item index decomposition)
   float scale_log2;  // softmax scale * log2(e)
+  // Tail schedule (MMA2 kernels): items [0, full_items) are dealt round-robin as 256-row pairs; the
+  // n_split = nitems - full_items items of the last, partial round are dealt as single 128-row tiles to CTAs
+  // 0 .. 2*n_split-1 (CTA c: item full_items + c/2, tile c & 1).  n_split = 0: plain round-robin.
+  int full_items, n_split;
 };
 
 // Persistent: each CTA walks work items w = blockIdx.x, +gridDim.x, ... (item = one (batch, head,
@@ -87,14 +91,18 @@ struct FmhaParams {
 // instead of two cover each other's MUFU / barrier / TMEM latencies, and a thread holds 64 scores instead
 // of 128 (no spills, room to interleave).  The two halves of a row agree on the block maximum and the final
 // row sum through spare TMEM columns [384, 400) (lane = row, so partner warps address the same lanes).
-template <bool SPLIT>
-constexpr int fmha_threads() { return SPLIT ? 576 : kFmhaThreads; }
+// MMA2 = true: one tcgen05.mma issue warp PER query tile instead of one for both.  A single in-order issue
+// warp couples the two softmax warpgroups (QK_1(g+1) waits for warpgroup 1 to have read S_1(g) before P_0 V(g)
+// can be issued, so a lagging warpgroup stalls its sibling's o_full); with two issue warps each tile's
+// S -> P -> O chain only depends on its own warpgroup.  MMA2 kernels also use the tail schedule of FmhaParams.
+template <bool SPLIT, bool MMA2 = false>
+constexpr int fmha_threads() { return SPLIT ? 576 : (MMA2 ? kFmhaThreads + 32 : kFmhaThreads); }
 
 // PTMEM = true: P_t is written to tensor memory (columns 384 + 64 t, bf16 pairs per 32-bit column) and fed
 // to P_t V as the TMEM A operand: no st.shared / proxy fence for P, and the N = 64 MMA no longer re-reads a
 // 4 KB A slice from shared memory per k-step.
-template <int kPolyPer8, bool PINGPONG, bool SPLIT = false, bool PTMEM = false>
-__global__ void __launch_bounds__(fmha_threads<SPLIT>(), 1)
+template <int kPolyPer8, bool PINGPONG, bool SPLIT = false, bool PTMEM = false, bool MMA2 = false>
+__global__ void __launch_bounds__(fmha_threads<SPLIT, MMA2>(), 1)
 fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_k2,
                 const __grid_constant__ CUtensorMap tmap_v2, const __grid_constant__ CUtensorMap tmap_o,
@@ -134,6 +142,15 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     batch = __float2int_rz((static_cast<float>(bh) + 0.5f) * p.rcp_H);
     head = bh - batch * p.H;
   };
+  // this CTA's schedule: n_full_my round-robin pair items, then (tail schedule) at most one single-tile item
+  const int cta = static_cast<int>(blockIdx.x), ncta = static_cast<int>(gridDim.x);
+  const int n_full_my = cta < p.full_items ? (p.full_items - cta + ncta - 1) / ncta : 0;
+  const bool has_half = cta < 2 * p.n_split;
+  const int n_my = n_full_my + (has_half ? 1 : 0);
+  auto sched = [&](int it, int& w, int& mask) {
+    if (it < n_full_my) { w = cta + it * ncta; mask = 3; }
+    else { w = p.full_items + (cta >> 1); mask = 1 << (cta & 1); }
+  };
 
   if (tid == 0) {
     tma_prefetch_desc(&tmap_q);
@@ -146,7 +163,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&q_full[i], 1);
-      mbar_init(&q_empty[i], 1);
+      mbar_init(&q_empty[i], MMA2 ? 2 : 1);
       mbar_init(&s_full[i], 1);
       mbar_init(&s_empty[i], kTileThreads);
       mbar_init(&p_full[i], kTileThreads);
@@ -154,7 +171,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     }
     for (int i = 0; i < kKVStages; ++i) {
       mbar_init(&kv_full[i], 1);
-      mbar_init(&kv_empty[i], 1);
+      mbar_init(&kv_empty[i], MMA2 ? 2 : 1);
     }
     fence_barrier_init();
   }
@@ -172,15 +189,17 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   if (warp == kTmaWarp) {
     // ------------------------------------------------------------ TMA producer
     if ((tid & 31) == 0) {
-      int it = 0, kst = 0, kph = 0;
-      for (int w = blockIdx.x; w < nitems; w += gridDim.x, ++it) {
-        int q0, head, batch;
+      int kst = 0, kph = 0;
+      for (int it = 0; it < n_my; ++it) {
+        int w, mask, q0, head, batch;
+        sched(it, w, mask);
         item_coords(w, q0, head, batch);
         const int qb = it & 1;
         mbar_wait(&q_empty[qb], ((it >> 1) & 1) ^ 1);
-        mbar_arrive_expect_tx(&q_full[qb], 2 * kTileBytes);
+        mbar_arrive_expect_tx(&q_full[qb], (mask == 3 ? 2 : 1) * kTileBytes);
         for (int t = 0; t < 2; ++t)
-          tma_load_3d(sQ + (qb * 2 + t) * kTileBytes, &tmap_q, &q_full[qb], head * kHD, q0 + t * kQT, batch);
+          if (mask >> t & 1)
+            tma_load_3d(sQ + (qb * 2 + t) * kTileBytes, &tmap_q, &q_full[qb], head * kHD, q0 + t * kQT, batch);
         for (int j = 0; j < nkv; ++j) {
           const int b = kst;
           mbar_wait(&kv_empty[b], kph ^ 1);
@@ -196,10 +215,13 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         }
       }
     }
-  } else if (warp == kMmaWarp) {
-    // ------------------------------------------------------------ MMA issuer
+  } else if (warp == kMmaWarp || (MMA2 && warp == kMmaWarp + 1)) {
+    // ------------------------------------------------------------ MMA issuer(s)
     // The whole warp walks this loop with warp-uniform values (so descriptors live in uniform
     // registers); elect_one_sync() guards only the tcgen05 instructions themselves.
+    // MMA2: this warp issues for query tile t_lo only; the sibling warp takes the other tile.
+    const int t_lo = MMA2 ? warp - kMmaWarp : 0;
+    const int t_hi = MMA2 ? t_lo + 1 : 2;
     {
       constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
       constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);  // B (= V) is MN-major
@@ -209,9 +231,9 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       const uint64_t dV = make_smem_desc_sw128(smem_u32(sV), 1024, 1024);
       const uint64_t dP = make_smem_desc_sw128(smem_u32(sP), 0, 1024);
       constexpr uint32_t kTileD = kTileBytes >> 4;  // descriptor address units (16 B)
-      const int n_my = (nitems - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
-                       static_cast<int>(gridDim.x);
-      const int G = n_my * nkv;  // KV blocks this CTA walks, over all of its items
+      // the single-tile tail item (always the CTA's last) belongs to one issue warp only
+      const bool skip_last = MMA2 && has_half && ((cta & 1) != t_lo);
+      const int G = (n_my - (skip_last ? 1 : 0)) * nkv;  // KV blocks this warp issues for, over all of its items
       // All ring / item bookkeeping is incremental (no divisions on the issue path).
       int q_it = 0, q_j = 0, q_st = 0, q_ph = 0;  // next S block to issue: item, block in item, kv stage/phase
       auto issue_qk_block = [&](int gb) {
@@ -221,7 +243,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         LN3_TR(2, gb, 0);  // K of block gb landed
         const uint64_t kd = dK + static_cast<uint32_t>(q_st) * kTileD;
 #pragma unroll
-        for (int t = 0; t < 2; ++t) {
+        for (int t = t_lo; t < t_hi; ++t) {
           if (gb > 0) mbar_wait(&s_empty[t], (gb - 1) & 1);  // S_t of block gb-1 is in registers
           tc_fence_after();
           const uint64_t qd = dQ + static_cast<uint32_t>(qb * 2 + t) * kTileD;
@@ -250,7 +272,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         const int ksteps = kv_valid >= kKT ? kKT / 16 : (kv_valid + 15) >> 4;  // P beyond is never written
         const uint64_t vd = dV + static_cast<uint32_t>(st) * kTileD;
 #pragma unroll
-        for (int t = 0; t < 2; ++t) {
+        for (int t = t_lo; t < t_hi; ++t) {
           mbar_wait(&p_full[t], g & 1);  // P_t in smem, O_t rescaled if needed
           LN3_TR(2, g, 3 + 2 * t);  // p_full seen
           tc_fence_after();
@@ -275,6 +297,16 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         if (++j == nkv) j = 0;
         if (++st == kKVStages) st = 0;
       }
+      if (skip_last) {
+        // the sibling's single-tile item: this warp issues nothing, but the K/V ring needs both warps'
+        // releases per stage (the stage's previous user must have landed first: wait kv_full, then arrive)
+        for (int jj = 0; jj < nkv; ++jj) {
+          mbar_wait(&kv_full[q_st], q_ph);
+          if (elect_one_sync()) mbar_arrive(&kv_empty[q_st]);
+          __syncwarp();
+          if (++q_st == kKVStages) q_st = 0, q_ph ^= 1;
+        }
+      }
     }
   } else if (!SPLIT && warp < 8) {
     // ------------------------------------------------------------ softmax warpgroups
@@ -292,8 +324,10 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     // participants = 128 waiting + 128 arriving).  Left alone they fall into lock-step -- both in the
     // MUFU-bound phase together, then both idle on the tensor core -- and the XU pipe sits at ~45 %.
     if (PINGPONG && t == 1) named_bar_arrive(1, 256);  // warpgroup 0 goes first
-    for (int w = blockIdx.x; w < nitems; w += gridDim.x) {
-      int q0, head, batch;
+    for (int it = 0; it < n_my; ++it) {
+      int w, mask, q0, head, batch;
+      sched(it, w, mask);
+      if (!(mask >> t & 1)) break;  // the sibling tile's single-tile tail item (always last)
       item_coords(w, q0, head, batch);
       float m_ref = -INFINITY, l_run = 0.f;
       for (int j = 0; j < nkv; ++j, ++g) {
@@ -637,7 +671,13 @@ int fmha_fwd(const ln3_fmha_args* a, cudaStream_t stream) {
     // LN3_FMHA_PTMEM = 1: P through tensor memory (TMEM A operand of P V)
     const char* pt = getenv("LN3_FMHA_PTMEM");
     const int ptmem = (pt && atoi(pt) != 0) ? 1 : 0;
-    return split ? 100 + (v == 2 ? 2 : 0) : (ptmem ? 200 : v * 2 + ping);
+    // LN3_FMHA_MMA2 = 0 selects the round-1 kernel (one MMA issue warp for both tiles, plain round-robin)
+    const char* m2 = getenv("LN3_FMHA_MMA2");
+    const int mma2 = (m2 && atoi(m2) == 0) ? 0 : 1;
+    if (split) return 100 + (v == 2 ? 2 : 0);
+    if (ptmem) return 200;
+    if (mma2 && !ping) return 300 + v;
+    return v * 2 + ping;
   }();
   static DeviceOnce once;   // the shared-memory opt-in is per device
   if (int rc = once.run([] {
@@ -651,6 +691,8 @@ int fmha_fwd(const ln3_fmha_args* a, cudaStream_t stream) {
         set(fmha_fwd_kernel<4, false>); set(fmha_fwd_kernel<4, true>);
         set(fmha_fwd_kernel<0, false, true>); set(fmha_fwd_kernel<2, false, true>);
         set(fmha_fwd_kernel<0, false, false, true>);
+        set(fmha_fwd_kernel<0, false, false, false, true>); set(fmha_fwd_kernel<2, false, false, false, true>);
+        set(fmha_fwd_kernel<3, false, false, false, true>); set(fmha_fwd_kernel<4, false, false, false, true>);
         return e == cudaSuccess ? LN3_OK : set_error(LN3_ECUDA, "fmha: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       }))
     return rc;
@@ -690,6 +732,18 @@ int fmha_fwd(const ln3_fmha_args* a, cudaStream_t stream) {
   if (nitems >= (1 << 20)) return set_error(LN3_EUNSUPPORTED, "fmha: more than 2^20 (batch, head, 256-row) work items");
   const int sms = device_sm_count();
   const int grid = static_cast<int>(nitems < sms ? nitems : sms);
+  p.full_items = static_cast<int>(nitems);
+  p.n_split = 0;
+  if (variant >= 300) {
+    // tail schedule: the last, partial round as single-tile items on twice as many SMs (each warpgroup then has
+    // the SM's XU pipe to itself) when they fit.  LN3_FMHA_TAIL=0 disables.
+    static const bool tail = !(getenv("LN3_FMHA_TAIL") && atoi(getenv("LN3_FMHA_TAIL")) == 0);
+    const int rem = static_cast<int>(nitems % grid);
+    if (tail && nitems > grid && rem > 0 && 2 * rem <= grid) {
+      p.full_items = static_cast<int>(nitems) - rem;
+      p.n_split = rem;
+    }
+  }
   cudaError_t le = cudaSuccess;
   switch (variant) {
 #define LN3_FMHA_CASE(P, G) \
@@ -700,6 +754,10 @@ int fmha_fwd(const ln3_fmha_args* a, cudaStream_t stream) {
     case 100: le = launch_pdl(fmha_fwd_kernel<0, false, true>, dim3(grid), dim3(fmha_threads<true>()), kFmhaSmem, stream, tq, tk, tv, tk2, tv2, to, p); break;
     case 200: le = launch_pdl(fmha_fwd_kernel<0, false, false, true>, dim3(grid), dim3(kFmhaThreads), kFmhaSmem, stream, tq, tk, tv, tk2, tv2, to, p); break;
     case 102: le = launch_pdl(fmha_fwd_kernel<2, false, true>, dim3(grid), dim3(fmha_threads<true>()), kFmhaSmem, stream, tq, tk, tv, tk2, tv2, to, p); break;
+#define LN3_FMHA_CASE2(P) \
+  case 300 + (P): le = launch_pdl(fmha_fwd_kernel<P, false, false, false, true>, dim3(grid), dim3(fmha_threads<false, true>()), kFmhaSmem, stream, tq, tk, tv, tk2, tv2, to, p); break;
+    LN3_FMHA_CASE2(0) LN3_FMHA_CASE2(2) LN3_FMHA_CASE2(3) LN3_FMHA_CASE2(4)
+#undef LN3_FMHA_CASE2
     default: return set_error(LN3_EINVAL, "fmha: bad variant");
   }
   cudaError_t e = le != cudaSuccess ? le : cudaGetLastError();

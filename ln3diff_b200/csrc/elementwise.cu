@@ -43,18 +43,35 @@ norm_modulate_kernel(const ln3_norm_modulate_args a) {
   if (a.resid != nullptr) {
     // fused residual update: x += gate * resid (bf16), written back in place
     const __nv_bfloat16* rr = reinterpret_cast<const __nv_bfloat16*>(a.resid) + static_cast<long long>(row) * a.resid_ld;
-    if (a.resid_bcast != nullptr && (row < a.resid_row_begin || row >= a.resid_row_end))
+    const __nv_bfloat16* r2 = nullptr;   // outside rows with resid_out_gate: own resid row first, then the bcast row
+    const float* g2 = nullptr;
+    if (a.resid_bcast != nullptr && (row < a.resid_row_begin || row >= a.resid_row_end)) {
+      if (a.resid_out_gate != nullptr) {
+        r2 = rr;
+        g2 = a.resid_out_gate + static_cast<long long>(row / a.resid_out_gate_rows) * a.resid_out_gate_ld;
+      }
       rr = reinterpret_cast<const __nv_bfloat16*>(a.resid_bcast) + static_cast<long long>(row / a.resid_bcast_rows) * a.resid_bcast_ld;
+    }
     const float* gg = a.resid_gate ? a.resid_gate + static_cast<long long>(row / a.resid_gate_rows) * a.resid_gate_ld : nullptr;
     float* xw = const_cast<float*>(x);
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c = (i * 32 + lane) * 4;
+      if (r2 != nullptr) {
+        const uint2 qb = *reinterpret_cast<const uint2*>(r2 + c);
+        const __nv_bfloat162 q01 = *reinterpret_cast<const __nv_bfloat162*>(&qb.x);
+        const __nv_bfloat162 q23 = *reinterpret_cast<const __nv_bfloat162*>(&qb.y);
+        const float4 h = __ldg(reinterpret_cast<const float4*>(g2 + c));
+        v[i].x = fmaf(h.x, __low2float(q01), v[i].x);
+        v[i].y = fmaf(h.y, __high2float(q01), v[i].y);
+        v[i].z = fmaf(h.z, __low2float(q23), v[i].z);
+        v[i].w = fmaf(h.w, __high2float(q23), v[i].w);
+      }
       const uint2 rb = *reinterpret_cast<const uint2*>(rr + c);
       const __nv_bfloat162 r01 = *reinterpret_cast<const __nv_bfloat162*>(&rb.x);
       const __nv_bfloat162 r23 = *reinterpret_cast<const __nv_bfloat162*>(&rb.y);
       float4 g = make_float4(1.f, 1.f, 1.f, 1.f);
-      if (gg != nullptr) g = __ldg(reinterpret_cast<const float4*>(gg + c));
+      if (gg != nullptr && r2 == nullptr) g = __ldg(reinterpret_cast<const float4*>(gg + c));
       v[i].x = fmaf(g.x, __low2float(r01), v[i].x);
       v[i].y = fmaf(g.y, __high2float(r01), v[i].y);
       v[i].z = fmaf(g.z, __low2float(r23), v[i].z);
@@ -145,12 +162,33 @@ norm_modulate_wide_kernel(const ln3_norm_modulate_args a) {
     for (int i = 0; i < NV8; ++i) ldg256_na(x + (i * 32 + lane) * 8, v[i]);
     if (a.resid != nullptr) {
       const __nv_bfloat16* rr = reinterpret_cast<const __nv_bfloat16*>(a.resid) + static_cast<long long>(row) * a.resid_ld;
-      if (a.resid_bcast != nullptr && (row < a.resid_row_begin || row >= a.resid_row_end))
+      const __nv_bfloat16* r2 = nullptr;   // outside rows with resid_out_gate: own resid row first, then the bcast row
+      const float* g2 = nullptr;
+      if (a.resid_bcast != nullptr && (row < a.resid_row_begin || row >= a.resid_row_end)) {
+        if (a.resid_out_gate != nullptr) {
+          r2 = rr;
+          g2 = a.resid_out_gate + static_cast<long long>(row / a.resid_out_gate_rows) * a.resid_out_gate_ld;
+        }
         rr = reinterpret_cast<const __nv_bfloat16*>(a.resid_bcast) + static_cast<long long>(row / a.resid_bcast_rows) * a.resid_bcast_ld;
-      const float* gg = a.resid_gate ? a.resid_gate + static_cast<long long>(row / a.resid_gate_rows) * a.resid_gate_ld : nullptr;
+      }
+      const float* gg = (a.resid_gate && r2 == nullptr)
+                            ? a.resid_gate + static_cast<long long>(row / a.resid_gate_rows) * a.resid_gate_ld : nullptr;
 #pragma unroll
       for (int i = 0; i < NV8; ++i) {
         const int c = (i * 32 + lane) * 8;
+        if (r2 != nullptr) {
+          const uint4 qb = *reinterpret_cast<const uint4*>(r2 + c);
+          const uint32_t qw[4] = {qb.x, qb.y, qb.z, qb.w};
+          const float4 h0 = __ldg(reinterpret_cast<const float4*>(g2 + c));
+          const float4 h1 = __ldg(reinterpret_cast<const float4*>(g2 + c + 4));
+          const float h[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const __nv_bfloat162 q2 = *reinterpret_cast<const __nv_bfloat162*>(&qw[j]);
+            v[i][2 * j] = fmaf(h[2 * j], __low2float(q2), v[i][2 * j]);
+            v[i][2 * j + 1] = fmaf(h[2 * j + 1], __high2float(q2), v[i][2 * j + 1]);
+          }
+        }
         const uint4 rb = *reinterpret_cast<const uint4*>(rr + c);
         const uint32_t rw[4] = {rb.x, rb.y, rb.z, rb.w};
         float g[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
@@ -267,6 +305,9 @@ int norm_modulate(const ln3_norm_modulate_args* a, cudaStream_t stream) {
         (a->resid_bcast_rows <= 0 || a->resid_bcast_ld % 8 || (reinterpret_cast<uintptr_t>(a->resid_bcast) & 15) ||
          a->resid_row_begin < 0 || a->resid_row_end < a->resid_row_begin || a->resid_row_end > a->rows))
       return set_error(LN3_EINVAL, "norm_modulate: bad resid_bcast arguments");
+    if (a->resid_out_gate != nullptr &&
+        (a->resid_bcast == nullptr || a->resid_out_gate_rows <= 0 || a->resid_out_gate_ld % 4))
+      return set_error(LN3_EINVAL, "norm_modulate: resid_out_gate needs resid_bcast, rows > 0 and ld %% 4 == 0");
   } else if (a->resid_bcast != nullptr) {
     return set_error(LN3_EINVAL, "norm_modulate: resid_bcast needs resid");
   }

@@ -60,15 +60,23 @@ __global__ void __launch_bounds__(256) depth_minmax_kernel(const float* __restri
   }
 }
 
-// numpy: (float64(v) * 127.5 + 127.5).clip(0, 255).astype(uint8)   (:366-368; the cat with the float64
-// colour-mapped depth promotes the frame to float64)
+// numpy: (v * 127.5 + 127.5).clip(0, 255).astype(uint8).  The video frame (:340-345,366-368) is the cat of the
+// fp32 image with the float64 colour-mapped depth, which promotes it to float64 (F64 = true); the image-only
+// path (:350-353, the per-view JPEG) stays a float32 array: two separately rounded fp32 operations, no FMA.
+template <bool F64>
 __device__ __forceinline__ unsigned to_u8(float v) {
-  double d = static_cast<double>(v) * 127.5 + 127.5;
-  d = d < 0.0 ? 0.0 : (d > 255.0 ? 255.0 : d);
-  return static_cast<unsigned>(static_cast<int>(d));   // NaN -> 0 like numpy's undefined-but-zero cast on x86
+  if (F64) {
+    double d = static_cast<double>(v) * 127.5 + 127.5;
+    d = d < 0.0 ? 0.0 : (d > 255.0 ? 255.0 : d);
+    return static_cast<unsigned>(static_cast<int>(d));   // NaN -> 0
+  }
+  float f = __fadd_rn(__fmul_rn(v, 127.5f), 127.5f);
+  f = f < 0.f ? 0.f : (f > 255.f ? 255.f : f);
+  return static_cast<unsigned>(static_cast<int>(f));
 }
 
 // One thread = 4 horizontally adjacent output pixels = 12 bytes.
+template <bool F64>
 __global__ void __launch_bounds__(256)
 pack_frames_kernel(const float* __restrict__ image, const float* __restrict__ depth,
                    const unsigned char* __restrict__ lut, const float* __restrict__ ws,
@@ -93,10 +101,10 @@ pack_frames_kernel(const float* __restrict__ image, const float* __restrict__ de
       const float4 r = __ldg(reinterpret_cast<const float4*>(image + base));
       const float4 g = __ldg(reinterpret_cast<const float4*>(image + base + cs));
       const float4 bl = __ldg(reinterpret_cast<const float4*>(image + base + 2 * cs));
-      b[0] = to_u8(r.x); b[1] = to_u8(g.x); b[2] = to_u8(bl.x);
-      b[3] = to_u8(r.y); b[4] = to_u8(g.y); b[5] = to_u8(bl.y);
-      b[6] = to_u8(r.z); b[7] = to_u8(g.z); b[8] = to_u8(bl.z);
-      b[9] = to_u8(r.w); b[10] = to_u8(g.w); b[11] = to_u8(bl.w);
+      b[0] = to_u8<F64>(r.x); b[1] = to_u8<F64>(g.x); b[2] = to_u8<F64>(bl.x);
+      b[3] = to_u8<F64>(r.y); b[4] = to_u8<F64>(g.y); b[5] = to_u8<F64>(bl.y);
+      b[6] = to_u8<F64>(r.z); b[7] = to_u8<F64>(g.z); b[8] = to_u8<F64>(bl.z);
+      b[9] = to_u8<F64>(r.w); b[10] = to_u8<F64>(g.w); b[11] = to_u8<F64>(bl.w);
     } else {
       const float mn = ws[2 * n], mx = ws[2 * n + 1];
       const float range = __fsub_rn(mx, mn);
@@ -145,8 +153,12 @@ int pack_frames(const ln3_pack_frames_args* a, cudaStream_t stream) {
   long long blocks = (total + 255) / 256;
   const long long cap = static_cast<long long>(device_sm_count()) * 8;
   if (blocks > cap) blocks = cap;
-  pack_frames_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(a->image, a->depth, a->lut, a->workspace, a->out,
-                                                                      a->N, a->H, a->W, Wout);
+  if (a->depth)
+    pack_frames_kernel<true><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(a->image, a->depth, a->lut, a->workspace,
+                                                                                a->out, a->N, a->H, a->W, Wout);
+  else
+    pack_frames_kernel<false><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(a->image, nullptr, nullptr, nullptr, a->out,
+                                                                                 a->N, a->H, a->W, Wout);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(LN3_ECUDA, "pack_frames launch: %s", cudaGetErrorString(e));
   count_launch(launches);

@@ -11,6 +11,11 @@ from .._lib import NORM_NONE, NORM_RMS
 from ._graph import ContextCache, ForwardGraph, capture_forward, graphs_enabled
 
 
+def _split_residual_pass() -> bool:
+    import os
+    return os.environ.get("LN3_SPLIT_RESID_PASS", "1") != "0"
+
+
 def pixart_forward(model, P: dict, cx: dict, ws: dict, x: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
     """x (B, 3C, S, S) fp32, t (B,) fp32; cx = cached step-invariant conditioning: 'cls' (B, D) fp32 pooled
     embedding added to t_emb, 'ckv' (L, B, Lc, 2D) cross-attention K|V, optional 'dkv' (L, B, Ld, 2D) DINO
@@ -45,7 +50,13 @@ def pixart_forward(model, P: dict, cx: dict, ws: dict, x: torch.Tensor, t: torch
         else:
             ops.fmha(qkv3[:, :, :D], qkv3[:, :, D:2 * D], qkv3[:, :, 2 * D:], H, out=att3)
         ops.gemm(ws["att"], W["proj_w"], W["proj_b"], out=val)
-        ops.norm_modulate(x2, norm=NORM_NONE, out=ws["xb"], resid=val, resid_gate=sl(2), resid_gate_rows=T)
+        split = oconst is not None and _split_residual_pass()      # see DiT_TriLatent._forward_impl
+        if split:
+            if r1 > r0:
+                ops.norm_modulate(x2[r0:r1], norm=NORM_NONE, out=ws["xb"][r0:r1], resid=val[r0:r1],
+                                  resid_gate=sl(2)[g0:g1], resid_gate_rows=T)
+        else:
+            ops.norm_modulate(x2, norm=NORM_NONE, out=ws["xb"], resid=val, resid_gate=sl(2), resid_gate_rows=T)
         if r1 > r0:
             ops.gemm(ws["xb"][r0:r1], W["cq_w"], out=ws["q"][r0:r1], head_norm=W.get("cq_norm"), head_norm_sec_cols=D)
             ckv = cx["ckv"][l]
@@ -53,7 +64,8 @@ def pixart_forward(model, P: dict, cx: dict, ws: dict, x: torch.Tensor, t: torch
             ops.gemm(ws["att"][r0:r1], W["co_w"], W["co_b"], out=val[r0:r1])
         ops.norm_modulate(x2, norm=NORM_RMS, weight=W["n2_w"], eps=1e-5, shift=sl(3), scale=sl(4), mod_rows=T, out=ws["a"],
                           resid=val, resid_bcast=oconst[l] if oconst is not None else None, resid_bcast_rows=T,
-                          resid_rows=(r0, r1) if oconst is not None else None)
+                          resid_rows=(r0, r1) if oconst is not None else None,
+                          resid_out_gate=sl(2) if split else None, resid_out_gate_rows=T)
         ops.gemm(ws["a"], W["fc1_w"], W["fc1_b"], act=ops.ACT_GELU_ERF, out=ws["h"])
         ops.gemm(ws["h"], W["fc2_w"], W["fc2_b"], out=val)
         pend_gate = sl(5)

@@ -28,6 +28,12 @@ def _closed_form_uncond() -> bool:
     return os.environ.get("LN3_UNCOND_CLOSED_FORM", "1") != "0"
 
 
+def _split_residual_pass() -> bool:
+    """LN3_SPLIT_RESID_PASS=0: the post-self-attention residual pass covers every row (A/B, tests)."""
+    import os
+    return os.environ.get("LN3_SPLIT_RESID_PASS", "1") != "0"
+
+
 def _attention_rows(tokens: torch.Tensor):
     """tokens (B, L, C) as the cross-attention sees them.  Returns (g0, g1): the contiguous block of samples
     that needs real attention when the samples whose L tokens are all identical form a prefix and/or suffix
@@ -316,8 +322,16 @@ class DiT_TriLatent(nn.Module):
             ops.gemm(ws["a"], W["qkv_w"], W["qkv_b"], out=ws["qkv"])
             ops.fmha(qkv3[:, :, 0:D], qkv3[:, :, D:2 * D], qkv3[:, :, 2 * D:3 * D], H, out=att3)
             ops.gemm(ws["att"], W["proj_w"], W["proj_b"], out=val)
-            # x += gate_msa * attn ; xb = bf16(x): the un-normalised query input of the cross-attention
-            ops.norm_modulate(x2, norm=NORM_NONE, out=ws["xb"], resid=val, resid_gate=sl(2), resid_gate_rows=T)
+            # x += gate_msa * attn ; xb = bf16(x): the un-normalised query input of the cross-attention.  Only the
+            # attended rows need xb: with closed-form samples present the pass covers rows [r0, r1) only and the
+            # next pass applies the other rows' gate_msa * attn together with their closed-form cross-attention row.
+            split = oconst is not None and _split_residual_pass()
+            if split:
+                if r1 > r0:
+                    ops.norm_modulate(x2[r0:r1], norm=NORM_NONE, out=ws["xb"][r0:r1], resid=val[r0:r1],
+                                      resid_gate=sl(2)[g0:g1], resid_gate_rows=T)
+            else:
+                ops.norm_modulate(x2, norm=NORM_NONE, out=ws["xb"], resid=val, resid_gate=sl(2), resid_gate_rows=T)
             if r1 > r0:
                 ops.gemm(ws["xb"][r0:r1], W["q_w"], out=ws["q"][r0:r1])
                 ops.fmha(q3[g0:g1], kv[g0:g1, :, l, 0], kv[g0:g1, :, l, 1], H, out=att3[g0:g1])
@@ -325,7 +339,8 @@ class DiT_TriLatent(nn.Module):
             # x += cross_attn (no gate) ; a = modulate(LN(x)).  Identical-token samples take the closed form.
             ops.norm_modulate(x2, norm=NORM_LAYER, shift=sl(3), scale=sl(4), mod_rows=T, out=ws["a"], resid=val,
                               resid_bcast=oconst[l] if oconst is not None else None, resid_bcast_rows=T,
-                              resid_rows=(r0, r1) if oconst is not None else None)
+                              resid_rows=(r0, r1) if oconst is not None else None,
+                              resid_out_gate=sl(2) if split else None, resid_out_gate_rows=T)
             ops.gemm(ws["a"], W["fc1_w"], W["fc1_b"], act=ops.ACT_GELU_ERF, out=ws["h"])
             ops.gemm(ws["h"], W["fc2_w"], W["fc2_b"], out=val)
             pend_gate = sl(5)

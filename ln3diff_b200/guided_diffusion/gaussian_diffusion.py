@@ -104,14 +104,35 @@ class GaussianDiffusion:
                 w0 = -c1 * self.sqrt_recipm1_alphas_cumprod
             elif self.model_mean_type == ModelMeanType.START_X:
                 a, w0 = c2, c1
-            elif self.model_mean_type == ModelMeanType.V:  # x0 = sqrt(ac) x - sqrt(1-ac) v
-                a = c1 * self.sqrt_alphas_cumprod + c2
-                w0 = -c1 * self.sqrt_one_minus_alphas_cumprod
             else:
-                raise NotImplementedError(self.model_mean_type)
+                self._unsupported_mean_type()
             s = np.exp(0.5 * logvar)
             s[0] = 0.0  # nonzero_mask: no noise at t == 0
             tab = th.tensor(np.stack([a, w0, np.zeros_like(a), s], 1), dtype=th.float32, device=device)
+            self._coef_cache[key] = tab
+        return tab
+
+    def _unsupported_mean_type(self):
+        """Both p_sample paths reject the same configurations.  ModelMeanType.V only works together with
+        mixing_normal=True in the reference (the v output becomes eps inside the mixing branch, :340-343;
+        without it `assert v_transformed_to_eps_flag` fails, :405-406), and the LSGM mixing path is outside
+        the DiT hot path; PREVIOUS_X is unused by every release config."""
+        raise NotImplementedError(f"{self.model_mean_type}: the DiT path runs EPSILON / START_X with fixed variance "
+                                  "(V needs mixing_normal=True in the reference, which is not mirrored)")
+
+    def _pred_xstart_coef_table(self, device):
+        """(T, 4) rows [a, w, 0, 0] with pred_xstart = a x + w out (EPSILON: :422-427; START_X: the output)."""
+        key = ("x0", str(device))
+        tab = self._coef_cache.get(key)
+        if tab is None:
+            if self.model_mean_type == ModelMeanType.EPSILON:
+                a, w = self.sqrt_recip_alphas_cumprod, -self.sqrt_recipm1_alphas_cumprod
+            elif self.model_mean_type == ModelMeanType.START_X:
+                a, w = np.zeros_like(self.betas), np.ones_like(self.betas)
+            else:
+                self._unsupported_mean_type()
+            z = np.zeros_like(a)
+            tab = th.tensor(np.stack([a, w, z, z], 1), dtype=th.float32, device=device)
             self._coef_cache[key] = tab
         return tab
 
@@ -141,7 +162,7 @@ class GaussianDiffusion:
         elif self.model_mean_type == ModelMeanType.EPSILON:
             pred_xstart = process_xstart(self._predict_xstart_from_eps(x, t, model_output))
         else:
-            raise NotImplementedError(self.model_mean_type)
+            self._unsupported_mean_type()
         model_mean = (_extract_into_tensor(self.posterior_mean_coef1, t, x.shape) * pred_xstart +
                       _extract_into_tensor(self.posterior_mean_coef2, t, x.shape) * x)
         return {"mean": model_mean, "variance": model_variance, "log_variance": model_log_variance,
@@ -163,9 +184,11 @@ class GaussianDiffusion:
             model_kwargs = model_kwargs or {}
             out = self._wrap_model(model)(x, self._scale_timesteps(t), c=cond, mixing_normal=False, **model_kwargs)
             noise = th.randn_like(x)
-            coef = self._step_coef_table(x.device)[t].contiguous()
-            sample = ops.sampler_affine_update(x.contiguous(), coef, out.float().contiguous(), None, noise)
-            return {"sample": sample, "pred_xstart": None}
+            xc, oc = x.contiguous(), out.float().contiguous()
+            sample = ops.sampler_affine_update(xc, self._step_coef_table(x.device)[t].contiguous(), oc, None, noise)
+            # the reference always returns the x_0 estimate (progressive loops read it): one more affine launch
+            pred_xstart = ops.sampler_affine_update(xc, self._pred_xstart_coef_table(x.device)[t].contiguous(), oc)
+            return {"sample": sample, "pred_xstart": pred_xstart}
         assert cond_fn is None, "classifier guidance (cond_fn) is not on the hot path"
         out = self.p_mean_variance(model, x, t, c=cond, clip_denoised=clip_denoised, denoised_fn=denoised_fn,
                                    model_kwargs=model_kwargs, mixing_normal=mixing_normal)

@@ -55,7 +55,14 @@ class SpacedDiffusion(GaussianDiffusion):
     def _wrap_model(self, model):
         if isinstance(model, _WrappedModel):
             return model
-        return _WrappedModel(model, self.timestep_map, self.rescale_timesteps, self.original_num_steps)
+        # p_sample wraps on every step (reference respace.py:100-104 builds a new wrapper -- and re-uploads
+        # the timestep map -- each time); keep the wrapper of the model being sampled so its device-resident
+        # map is built once per sampling run
+        cached = getattr(self, "_wrapped", None)
+        if cached is None or cached.model is not model:
+            cached = self._wrapped = _WrappedModel(model, self.timestep_map, self.rescale_timesteps,
+                                                   self.original_num_steps)
+        return cached
 
     def _scale_timesteps(self, t):
         return t

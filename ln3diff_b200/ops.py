@@ -143,13 +143,15 @@ def norm_modulate(x: torch.Tensor, *, norm: int, shift: torch.Tensor | None = No
                   out: torch.Tensor | None = None, resid: torch.Tensor | None = None,
                   resid_gate: torch.Tensor | None = None, resid_gate_rows: int = 1,
                   want_out: bool = True, resid_bcast: torch.Tensor | None = None, resid_bcast_rows: int = 1,
-                  resid_rows: tuple | None = None) -> torch.Tensor | None:
+                  resid_rows: tuple | None = None, resid_out_gate: torch.Tensor | None = None,
+                  resid_out_gate_rows: int = 1) -> torch.Tensor | None:
     """bf16( norm(x) * (1 + scale[g]) + shift[g] ), x fp32 (rows, D); shift/scale 2-D fp32 views
     (groups, D) with unit inner stride and equal row stride; row r uses group r // mod_rows.
     With `resid` (bf16 (rows, D)) the residual update x += resid_gate[r // resid_gate_rows] * resid is
     applied first, IN PLACE on x; want_out=False then skips the normalised output.  With `resid_bcast`
     ((groups, D) bf16) rows outside resid_rows=(begin, end) use resid_bcast[r // resid_bcast_rows] as
-    their residual row instead of resid[r]."""
+    their residual row instead of resid[r]; with `resid_out_gate` ((groups, D) fp32) those outside rows first add
+    resid_out_gate[r // resid_out_gate_rows] * resid[r] (their own, not yet applied, gated residual) as well."""
     _cuda(x, "x", torch.float32)
     _req(x.dim() == 2 and x.stride(1) == 1, "x must be (rows, D) with unit inner stride")
     rows, D = x.shape
@@ -180,6 +182,14 @@ def norm_modulate(x: torch.Tensor, *, norm: int, shift: torch.Tensor | None = No
         _req(0 <= resid_rows[0] <= resid_rows[1] <= rows, "resid_rows out of range")
         a.resid_bcast, a.resid_bcast_ld, a.resid_bcast_rows = resid_bcast.data_ptr(), resid_bcast.stride(0), resid_bcast_rows
         a.resid_row_begin, a.resid_row_end = resid_rows
+        if resid_out_gate is not None:
+            _cuda(resid_out_gate, "resid_out_gate", torch.float32)
+            _req(resid_out_gate.dim() == 2 and resid_out_gate.shape[1] == D and resid_out_gate.stride(1) == 1
+                 and resid_out_gate.shape[0] * resid_out_gate_rows >= rows, "resid_out_gate must be a (groups, D) view")
+            a.resid_out_gate, a.resid_out_gate_ld = resid_out_gate.data_ptr(), resid_out_gate.stride(0)
+            a.resid_out_gate_rows = resid_out_gate_rows
+    else:
+        _req(resid_out_gate is None, "resid_out_gate needs resid_bcast")
     a.x, a.rows, a.D = x.data_ptr(), rows, D
     a.ldx = x.stride(0)
     if shift is not None:
@@ -295,9 +305,11 @@ def sampler_affine_update(x: torch.Tensor, coef: torch.Tensor, m0: torch.Tensor,
             continue
         _cuda(t_, nm, torch.float32)
         _req(t_.is_contiguous() and t_.shape[0] == B and t_[0].numel() == n, f"{nm} must be contiguous, same shape as x")
+        _req(t_.data_ptr() % 16 == 0, f"{nm} must be 16-byte aligned (the kernel uses 128-bit accesses)")
+    _req(n % 4 == 0, "elements per sample must be a multiple of 4")
     if out is None:
         out = torch.empty_like(x)
-    _req(out.is_contiguous() and out.shape == x.shape and out.dtype == torch.float32, "bad out")
+    _req(out.is_contiguous() and out.shape == x.shape and out.dtype == torch.float32 and out.data_ptr() % 16 == 0, "bad out")
     a = _lib.SamplerUpdateArgs()
     a.x, a.m0, a.coef, a.x_out = x.data_ptr(), m0.data_ptr(), coef.data_ptr(), out.data_ptr()
     a.m1 = m1.data_ptr() if m1 is not None else None

@@ -79,46 +79,64 @@ class ode:
         self.t = th.linspace(t0, t1, num_steps)
         self.atol, self.rtol, self.sampler_type = atol, rtol, sampler_type
 
-    def _axpy(self, x, dt, k):
-        """x + dt * k as one fused launch on CUDA."""
-        if x.is_cuda and x.dtype == th.float32:
-            B = x.shape[0]
-            coef = th.tensor([[1.0, float(dt), 0.0, 0.0]], device=x.device).repeat(B, 1)
+    def _axpy(self, x, dt, k, coef=None):
+        """x + dt * k as one fused launch on CUDA (`coef`: the step's device-resident (B, 4) row block)."""
+        if coef is not None:
             return ops.sampler_affine_update(x.contiguous(), coef, k.float().contiguous())
         return x + dt * k
 
     def sample(self, x, model, **model_kwargs):
         device = x.device
+        B = x.size(0)
 
         def _fn(t, x):
-            tt = th.ones(x.size(0)).to(device) * t
+            # `th.ones(B).to(device) * t` of the reference (integrators.py:104-107) without the H2D copy / sync
+            tt = th.full((B,), float(t), device=device, dtype=th.float32)
             return self.drift(x, tt, model, **model_kwargs)
 
-        t = self.t.to(device)
+        t = self.t                                                 # float32 grid, kept on the HOST
         if self.sampler_type in ("euler", "heun", "midpoint"):
+            n = len(t) - 1
+            dts = t[1:] - t[:-1]                                   # float32 arithmetic as the reference's tensors
+            halves = 0.5 * dts
+            fused = x.is_cuda and x.dtype == th.float32
+            tab = None
+            if fused:   # every step's update coefficients in one upload: [:, 0] = dt, [:, 1] = dt / 2
+                tab = th.zeros(n, 2, B, 4)
+                tab[..., 0] = 1.0
+                tab[:, 0, :, 1] = dts[:, None]
+                tab[:, 1, :, 1] = halves[:, None]
+                tab = tab.to(device)
             ys = [x]
-            for i in range(len(t) - 1):
-                t0, t1 = t[i], t[i + 1]
-                dt = t1 - t0
+            for i in range(n):
+                t0, t1, dt, half = t[i], t[i + 1], dts[i], halves[i]
+                cf = tab[i, 0] if fused else None
+                ch = tab[i, 1] if fused else None
                 y = ys[-1]
                 if self.sampler_type == "euler":
-                    y = self._axpy(y, dt, _fn(t0, y))
+                    y = self._axpy(y, dt, _fn(t0, y), cf)
                 elif self.sampler_type == "midpoint":
-                    half = 0.5 * dt
-                    y = self._axpy(y, dt, _fn(t0 + half, self._axpy(y, half, _fn(t0, y))))
+                    y = self._axpy(y, dt, _fn(t0 + half, self._axpy(y, half, _fn(t0, y), ch)), cf)
                 else:
                     k1 = _fn(t0, y)
-                    k2 = _fn(t1, self._axpy(y, dt, k1))
-                    y = self._axpy(self._axpy(y, 0.5 * dt, k1), 0.5 * dt, k2)
+                    k2 = _fn(t1, self._axpy(y, dt, k1, cf))
+                    y = self._axpy(self._axpy(y, half, k1, ch), half, k2, ch)
                 ys.append(y)
             return th.stack(ys, 0)
         try:
-            from torchdiffeq import odeint  # third-party adaptive solvers (dopri5, ...)
-        except ImportError as e:
-            raise NotImplementedError(
-                f"sampling_method='{self.sampler_type}' needs torchdiffeq (un-vendored dependency of "
-                "the reference); fixed-grid 'euler' / 'heun' / 'midpoint' are built in") from e
-        return odeint(_fn, x, t, method=self.sampler_type, atol=[self.atol], rtol=[self.rtol])
+            from torchdiffeq import odeint  # the reference's own third-party solver, when it is installed
+        except ImportError:
+            odeint = None
+        if odeint is not None:
+            return odeint(_fn, x, t.to(device), method=self.sampler_type, atol=[self.atol], rtol=[self.rtol])
+        if self.sampler_type == "dopri5":
+            # the shipped I23D default (transport.py:374-381): restated solver, see transport/dopri5.py
+            from .dopri5 import odeint_dopri5
+            self.last_stats = {}
+            return odeint_dopri5(_fn, x, t, rtol=self.rtol, atol=self.atol, stats=self.last_stats)
+        raise NotImplementedError(
+            f"sampling_method='{self.sampler_type}' needs torchdiffeq (un-vendored dependency of the reference); "
+            "'dopri5' and the fixed-grid 'euler' / 'heun' / 'midpoint' solvers are built in")
 
 
 class Sampler:

@@ -618,6 +618,12 @@ def test_closed_form_uncond_cross_attention(dev, monkeypatch):
         m._ctx_cache.clear()
         fast = m(x, t, ctx).clone()
         assert m._ctx_cache.value["rows"] == rows
+        # the attended-rows-only residual pass is a pure re-scheduling of the same fp32 operations: bit-identical
+        monkeypatch.setenv("LN3_SPLIT_RESID_PASS", "0")
+        m._graphs.clear()
+        assert torch.equal(m(x, t, ctx), fast)
+        monkeypatch.delenv("LN3_SPLIT_RESID_PASS")
+        m._graphs.clear()
         monkeypatch.setenv("LN3_UNCOND_CLOSED_FORM", "0")
         m._ctx_cache.clear()
         full = m(x, t, ctx).clone()
@@ -709,6 +715,11 @@ def test_closed_form_uncond_cross_attention_pixart_models(dev, monkeypatch):
         m._ctx_cache.clear()
         fast = m(x, t.to(dev), ctx).clone()
         assert m._ctx_cache.value["rows"] == (0, 2)
+        monkeypatch.setenv("LN3_SPLIT_RESID_PASS", "0")
+        m._graphs.clear()
+        assert torch.equal(m(x, t.to(dev), ctx), fast)
+        monkeypatch.delenv("LN3_SPLIT_RESID_PASS")
+        m._graphs.clear()
         monkeypatch.setenv("LN3_UNCOND_CLOSED_FORM", "0")
         m._ctx_cache.clear()
         full = m(x, t.to(dev), ctx).clone()

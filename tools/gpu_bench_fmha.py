@@ -35,5 +35,5 @@ rel = ((out.float() - ref).norm() / ref.norm()).item()
 qc = (torch.randn(B, L, H * 64, device=dev) * 0.5).bfloat16()
 kvc = (torch.randn(B, 77, 2 * H * 64, device=dev) * 0.5).bfloat16()
 us2 = timeit(lambda: ops.fmha(qc, kvc[:, :, :H * 64], kvc[:, :, H * 64:], H))
-print(f"ptmem={os.environ.get('LN3_FMHA_PTMEM','0')} split={os.environ.get('LN3_FMHA_SPLIT','0')} pp={os.environ.get('LN3_FMHA_PINGPONG','0')} poly={os.environ.get('LN3_FMHA_POLY', 'default')} self {us:.1f} us ({4.0 * B * H * L * L * 64 / us / 1e6:.0f} TF/s) "
+print(f"mma2={os.environ.get('LN3_FMHA_MMA2','1')} tail={os.environ.get('LN3_FMHA_TAIL','1')} ptmem={os.environ.get('LN3_FMHA_PTMEM','0')} split={os.environ.get('LN3_FMHA_SPLIT','0')} pp={os.environ.get('LN3_FMHA_PINGPONG','0')} poly={os.environ.get('LN3_FMHA_POLY', 'default')} self {us:.1f} us ({4.0 * B * H * L * L * 64 / us / 1e6:.0f} TF/s) "
       f"rel {rel:.2e}; cross {us2:.1f} us", flush=True)
