@@ -62,19 +62,8 @@ def workload_config(n_gpus):
 
 # ------------------------------------------------------------------ CPU reference arm / baseline
 def host_cores() -> int:
-    """Threads this process may actually use: the scheduler affinity mask, capped by the cgroup CPU quota
-    (os.cpu_count() reports the whole node, which oversubscribes a 1-GPU lease)."""
-    try:
-        n = len(os.sched_getaffinity(0))
-    except AttributeError:
-        n = os.cpu_count() or 1
-    try:
-        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
-        if quota != "max":
-            n = min(n, max(1, int(int(quota) / int(period))))
-    except Exception:
-        pass
-    return max(1, n)
+    from ln3diff_b200.utils import host_cores as hc
+    return hc()
 
 
 # bounded samples of one Euler-EDM+CFG denoising step, largest first: (name, prompts, forwards, layers)

@@ -296,6 +296,10 @@ typedef struct ln3_render_args {
   int group_size, views_per_obj, white_back;
   int mlp_precision; /* LN3_MLP_FP32 (exact, SIMT) or LN3_MLP_TF32 (mma.sync tensor cores, fp32 accumulate) */
   double box_warp, bbox_min, bbox_max;
+  /* optional: the M rays of a view are the pixels of an image of this width, m = y * image_w + x (RaySampler
+   * order, ray_sampler.py:180-195).  When width and height are multiples of 4 the kernel walks 4x4 pixel tiles
+   * (16 co-resident warps march through neighbouring texels in step: L1 reuse); 0 = plain ray order. */
+  int image_w;
 } ln3_render_args;
 
 size_t ln3_render_workspace_bytes(int V, int M, int group_size);

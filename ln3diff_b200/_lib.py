@@ -101,6 +101,7 @@ class RenderArgs(C.Structure):
         ("group_size", C.c_int), ("views_per_obj", C.c_int), ("white_back", C.c_int),
         ("mlp_precision", C.c_int),
         ("box_warp", C.c_double), ("bbox_min", C.c_double), ("bbox_max", C.c_double),
+        ("image_w", C.c_int),
     ]
 
 

@@ -236,14 +236,21 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       const int G = (n_my - (skip_last ? 1 : 0)) * nkv;  // KV blocks this warp issues for, over all of its items
       // All ring / item bookkeeping is incremental (no divisions on the issue path).
       int q_it = 0, q_j = 0, q_st = 0, q_ph = 0;  // next S block to issue: item, block in item, kv stage/phase
+      // tiles this warp issues for in item `it`: its own tile(s), minus the sibling's tile of a single-tile tail item
+      auto item_tiles = [&](int it) {
+        const int mine = MMA2 ? (1 << t_lo) : 3;
+        return (has_half && it == n_my - 1) ? (mine & (1 << (cta & 1))) : mine;
+      };
       auto issue_qk_block = [&](int gb) {
         const int qb = q_it & 1;
+        const int tiles = item_tiles(q_it);
         if (q_j == 0) mbar_wait(&q_full[qb], (q_it >> 1) & 1);
         mbar_wait(&kv_full[q_st], q_ph);
         LN3_TR(2, gb, 0);  // K of block gb landed
         const uint64_t kd = dK + static_cast<uint32_t>(q_st) * kTileD;
 #pragma unroll
         for (int t = t_lo; t < t_hi; ++t) {
+          if (!(tiles >> t & 1)) continue;
           if (gb > 0) mbar_wait(&s_empty[t], (gb - 1) & 1);  // S_t of block gb-1 is in registers
           tc_fence_after();
           const uint64_t qd = dQ + static_cast<uint32_t>(qb * 2 + t) * kTileD;
@@ -265,14 +272,16 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         if (++q_st == kKVStages) q_st = 0, q_ph ^= 1;
       };
       if (G > 0) issue_qk_block(0);
-      int j = 0, st = 0;
+      int j = 0, st = 0, pv_it = 0;
       for (int g = 0; g < G; ++g) {
         if (g + 1 < G) issue_qk_block(g + 1);
+        const int pv_tiles = item_tiles(pv_it);
         const int kv_valid = (j < nkv1) ? p.Lkv - j * kKT : p.Lkv2 - (j - nkv1) * kKT;
         const int ksteps = kv_valid >= kKT ? kKT / 16 : (kv_valid + 15) >> 4;  // P beyond is never written
         const uint64_t vd = dV + static_cast<uint32_t>(st) * kTileD;
 #pragma unroll
         for (int t = t_lo; t < t_hi; ++t) {
+          if (!(pv_tiles >> t & 1)) continue;
           mbar_wait(&p_full[t], g & 1);  // P_t in smem, O_t rescaled if needed
           LN3_TR(2, g, 3 + 2 * t);  // p_full seen
           tc_fence_after();
@@ -294,7 +303,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         }
         if (elect_one_sync()) umma_commit(&kv_empty[st]);  // every MMA that read K / V of block g has been issued
         __syncwarp();
-        if (++j == nkv) j = 0;
+        if (++j == nkv) j = 0, ++pv_it;
         if (++st == kKVStages) st = 0;
       }
       if (skip_last) {
@@ -671,9 +680,10 @@ int fmha_fwd(const ln3_fmha_args* a, cudaStream_t stream) {
     // LN3_FMHA_PTMEM = 1: P through tensor memory (TMEM A operand of P V)
     const char* pt = getenv("LN3_FMHA_PTMEM");
     const int ptmem = (pt && atoi(pt) != 0) ? 1 : 0;
-    // LN3_FMHA_MMA2 = 0 selects the round-1 kernel (one MMA issue warp for both tiles, plain round-robin)
+    // LN3_FMHA_MMA2 = 1: one MMA issue warp per query tile (measured slower: the second polling warp takes issue
+    // slots from the softmax warps of its scheduler -- 85 vs 77 us at the DiT-L/2 self-attention shape)
     const char* m2 = getenv("LN3_FMHA_MMA2");
-    const int mma2 = (m2 && atoi(m2) == 0) ? 0 : 1;
+    const int mma2 = (m2 && atoi(m2) != 0) ? 1 : 0;
     if (split) return 100 + (v == 2 ? 2 : 0);
     if (ptmem) return 200;
     if (mma2 && !ping) return 300 + v;
@@ -734,7 +744,7 @@ int fmha_fwd(const ln3_fmha_args* a, cudaStream_t stream) {
   const int grid = static_cast<int>(nitems < sms ? nitems : sms);
   p.full_items = static_cast<int>(nitems);
   p.n_split = 0;
-  if (variant >= 300) {
+  if (variant >= 300 || (variant < 100 && (variant & 1) == 0)) {
     // tail schedule: the last, partial round as single-tile items on twice as many SMs (each warpgroup then has
     // the SM's XU pipe to itself) when they fit.  LN3_FMHA_TAIL=0 disables.
     static const bool tail = !(getenv("LN3_FMHA_TAIL") && atoi(getenv("LN3_FMHA_TAIL")) == 0);

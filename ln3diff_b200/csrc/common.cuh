@@ -58,13 +58,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug becomes a trap (sticky CUDA error the host reports) instead of
-// a hung GPU.  ~4 s at 2 GHz.
+// Bounded wait: a protocol bug becomes a trap (sticky CUDA error the host reports) instead of a hung GPU.
+// The poll loop is just try_wait (which suspends the thread for a hardware time slice) + a spin counter:
+// reading clock64() in every iteration made a waiting producer / MMA warp issue several extra instructions
+// per poll on the scheduler it shares with the math warps.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
+  uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 8000000000LL) {
+    if (++spins == (1u << 26)) {
       printf("ln3: mbarrier timeout block=(%d,%d,%d) thread=%d parity=%u\n", blockIdx.x,
              blockIdx.y, blockIdx.z, threadIdx.x, parity);
       __trap();

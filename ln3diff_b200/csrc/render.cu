@@ -27,7 +27,7 @@ namespace ln3 {
 static constexpr int kS = 64;          // coarse == importance sample count (objaverse preset)
 static constexpr int kC = 32;          // plane feature channels
 static constexpr int kHid = 64;        // OSG hidden width
-static constexpr int kWarpsPerBlock = 8;
+static constexpr int kWarpsPerBlock = 16;  // one 512-thread CTA per SM: a 4x4 pixel tile of rays marches in lock-step
 
 __device__ __forceinline__ int float_key(float f) {  // monotone float -> int map
   int i = __float_as_int(f);
@@ -106,6 +106,7 @@ struct RenderParams {
   int* keys;
   const float* limits;
   int V, M, H, W, group_size, views_per_obj;
+  int image_w;        // > 0: ray m of a view is pixel (m % image_w, m / image_w) -> 4x4 pixel-tile schedule
   float coord_scale;  // 2 / box_warp (rounded to fp32 like the reference's scalar multiply)
   float bbox_min, bbox_max;
   int white_back;
@@ -371,8 +372,13 @@ __device__ __noinline__ void eval_batch(const RenderParams& p, const BlockSmem& 
   }
 }
 
+// Schedule: one CTA (16 warps = 16 rays) per SM walks work items; an item is a 4x4 PIXEL TILE of one view when the
+// rays of a view form an image (image_w > 0), else 16 consecutive rays.  Neighbouring pixels' rays pass through
+// neighbouring texels at every depth index, and the 16 warps of a tile stay in step (same trip counts, one
+// __syncthreads per item), so a texel line fetched by one warp is an L1 hit for its neighbours: the 64 KB of L1
+// left beside the shared-memory carve-out only helps rays that are co-resident in space AND time.
 template <bool TF32>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, 2)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 1)
 render_rays_kernel(const RenderParams p) {
   extern __shared__ uint8_t smem_raw[];
   BlockSmem& bs = *reinterpret_cast<BlockSmem*>(smem_raw);
@@ -382,9 +388,20 @@ render_rays_kernel(const RenderParams p) {
   WarpSmem& ws = bs.warp[warp];
 
   const long long total = static_cast<long long>(p.V) * p.M;
-  const long long stride = static_cast<long long>(gridDim.x) * kWarpsPerBlock;
-  for (long long ray = static_cast<long long>(blockIdx.x) * kWarpsPerBlock + warp; ray < total;
-       ray += stride) {
+  const int tiles_x = p.image_w > 0 ? p.image_w / 4 : 0;
+  const long long n_items = (total + kWarpsPerBlock - 1) / kWarpsPerBlock;   // tiles cover a view exactly (host check)
+  const int items_per_view = p.M / kWarpsPerBlock;
+  for (long long item = blockIdx.x; item < n_items; item += gridDim.x, __syncthreads()) {
+    long long ray;
+    if (tiles_x > 0) {
+      const int v = static_cast<int>(item / items_per_view);
+      const int tt = static_cast<int>(item - static_cast<long long>(v) * items_per_view);
+      const int ty = tt / tiles_x, tx = tt - ty * tiles_x;
+      ray = static_cast<long long>(v) * p.M + (ty * 4 + (warp >> 2)) * p.image_w + tx * 4 + (warp & 3);
+    } else {
+      ray = item * kWarpsPerBlock + warp;
+    }
+    if (ray >= total) continue;   // linear schedule, last item only (the loop increment still syncs)
     const int view = static_cast<int>(ray / p.M);
     const int grp = view / p.group_size;
     const int obj = p.view_obj ? p.view_obj[view] : view / p.views_per_obj;
@@ -671,6 +688,9 @@ int render_views(const ln3_render_args* a, cudaStream_t stream) {
   p.keys = keys;
   p.limits = limits;
   p.V = a->V; p.M = a->M; p.H = a->H; p.W = a->W;
+  // 2-D tile schedule when a view is an image whose width and height are multiples of 4
+  p.image_w = (a->image_w > 0 && a->image_w % 4 == 0 && a->M % a->image_w == 0 && (a->M / a->image_w) % 4 == 0)
+                  ? a->image_w : 0;
   p.group_size = a->group_size;
   p.views_per_obj = a->views_per_obj > 0 ? a->views_per_obj : 1;
   p.coord_scale = static_cast<float>(2.0 / a->box_warp);
@@ -693,7 +713,7 @@ int render_views(const ln3_render_args* a, cudaStream_t stream) {
     return rc;
   const int sms = device_sm_count();
   long long blocks = (rays + kWarpsPerBlock - 1) / kWarpsPerBlock;
-  if (blocks > 2LL * sms) blocks = 2LL * sms;  // persistent: 2 CTAs per SM, grid-stride over rays
+  if (blocks > sms) blocks = sms;  // persistent: one 16-warp CTA per SM, grid-stride over 16-ray items
   if (p.mlp_tf32)
     render_rays_kernel<true><<<static_cast<unsigned>(blocks), kWarpsPerBlock * 32, sizeof(BlockSmem), stream>>>(p);
   else
@@ -727,7 +747,7 @@ __device__ __forceinline__ float linspace_at(float lo, float hi, float step, int
 }
 
 template <bool TF32>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, 2)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 1)
 query_points_kernel(const RenderParams p, const QueryParams q) {
   extern __shared__ uint8_t smem_raw[];
   BlockSmem& bs = *reinterpret_cast<BlockSmem*>(smem_raw);
@@ -802,6 +822,7 @@ int query_points(const ln3_query_points_args* a, cudaStream_t stream) {
   p.coord_scale = static_cast<float>(2.0 / a->box_warp);
   p.bbox_min = 0.f; p.bbox_max = 0.f;
   p.no_filter = 1;
+  p.image_w = 0;
   p.mlp_tf32 = a->mlp_precision == LN3_MLP_TF32;
   static DeviceOnce once;
   if (int rc = once.run([] {
@@ -816,7 +837,7 @@ int query_points(const ln3_query_points_args* a, cudaStream_t stream) {
   const long long chunks = ((q.P + 31) / 32) * q.n_obj;
   long long blocks = (chunks + kWarpsPerBlock - 1) / kWarpsPerBlock;
   const int sms = device_sm_count();
-  if (blocks > 2LL * sms) blocks = 2LL * sms;
+  if (blocks > sms) blocks = sms;  // one 16-warp CTA per SM
   if (p.mlp_tf32)
     query_points_kernel<true><<<static_cast<unsigned>(blocks), kWarpsPerBlock * 32, sizeof(BlockSmem), stream>>>(p, q);
   else

@@ -384,7 +384,8 @@ def render_views(planes_cl: torch.Tensor, ray_o: torch.Tensor, ray_d: torch.Tens
                  noise_coarse: torch.Tensor, noise_fine: torch.Tensor, osg: tuple, *,
                  view_obj: torch.Tensor | None = None, views_per_obj: int = 0, group_size: int = 1,
                  box_warp: float = 0.9, bbox_min: float = -0.45, bbox_max: float = 0.45,
-                 white_back: bool = True, debug: bool = False, mlp_tf32: bool = False):
+                 white_back: bool = True, debug: bool = False, mlp_tf32: bool = False,
+                 image_width: int | None = None):
     """Fused ImportanceRenderer.forward for V views.  Returns dict(rgb (V,3,M), depth (V,1,M),
     weights (V,1,M)) (+ debug index tensors).  mlp_tf32: evaluate the OSG MLP on the tensor cores (TF32
     operands, fp32 accumulate; pixel error ~1e-4 rel-L2) instead of exact fp32."""
@@ -432,6 +433,12 @@ def render_views(planes_cl: torch.Tensor, ray_o: torch.Tensor, ray_d: torch.Tens
     a.group_size, a.views_per_obj, a.white_back = group_size, views_per_obj, int(white_back)
     a.box_warp, a.bbox_min, a.bbox_max = box_warp, bbox_min, bbox_max
     a.mlp_precision = _lib.MLP_TF32 if mlp_tf32 else _lib.MLP_FP32
+    # rays in RaySampler order (m = y*W + x): square views get the 4x4 pixel-tile schedule; image_width=0 forces
+    # the plain ray order (rays that are not an image, e.g. PatchRaySampler training patches)
+    if image_width is None:
+        r = int(round(M ** 0.5))
+        image_width = r if r * r == M else 0
+    a.image_w = int(image_width) if os.environ.get("LN3_RENDER_TILES", "1") != "0" else 0
     _lib.check(_lib.lib().ln3_render_views(C.byref(a), _lib.current_stream()), "ln3_render_views")
     return out
 

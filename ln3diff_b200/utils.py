@@ -4,6 +4,23 @@ from __future__ import annotations
 import torch
 
 
+def host_cores() -> int:
+    """Threads this process may actually use: the scheduler affinity mask capped by the cgroup CPU quota
+    (os.cpu_count() reports the whole node; oversubscribing a 16-core lease with 128 threads is ~20x slower)."""
+    import os
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except Exception:
+        pass
+    return max(1, n)
+
+
 def derandomize_zero_init(module: torch.nn.Module, std: float = 0.02, seed: int = 1234) -> None:
     """adaLN-Zero + the zero-initialised final layer make a freshly constructed DiT output exactly
     0 (reference dit/dit_models_xformers.py:807-819).  There are no checkpoints offline, so

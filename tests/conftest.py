@@ -12,6 +12,13 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA GPU (run on the B200 box with -m gpu)")
+    # CPU oracle legs of the GPU tests: use the cores this process really has (cgroup quota), not the node's
+    try:
+        import torch
+        from ln3diff_b200.utils import host_cores
+        torch.set_num_threads(host_cores())
+    except Exception:
+        pass
 
 
 @pytest.fixture(scope="session")

@@ -82,6 +82,10 @@ def test_dit2_L2_decode_and_pixels_vs_oracle(dev, golden):
     from oracle import render as orender
     m = build_ae_decoder("DiT2-L/2", image_size=64)
     sd = {k: v.clone() for k, v in m.state_dict().items()}
+    # random-init weights give a near-empty volume (white image, vacuous pixel error): a density bias of +3 fills
+    # ~80 % of the pixels of this view with partially transparent, coloured matter
+    sd["triplane_decoder.decoder.net.2.bias"][0] += 3.0
+    m.load_state_dict(sd)
     g = torch.Generator().manual_seed(32)
     lat = 0.96806 ** -1 * torch.randn(1, 12, 32, 32, generator=g)
     with torch.no_grad():
@@ -107,8 +111,12 @@ def test_dit2_L2_decode_and_pixels_vs_oracle(dev, golden):
     e_px_ref = _rel(px_refbf16["image_raw"], px_ref["image_raw"])
     _record(dit2_L2_planes_rel_l2=e_planes, dit2_L2_planes_rel_l2_reference_bf16_autocast=e_planes_ref,
             latent_to_pixels_rel_l2=e_px, latent_to_pixels_rel_l2_reference_bf16_autocast=e_px_ref)
-    print(f"planes: ours {e_planes:.3e} / reference-bf16 {e_planes_ref:.3e}; pixels: ours {e_px:.3e} / reference-bf16 {e_px_ref:.3e}")
-    assert e_planes < 2e-2, e_planes
+    occupied = float((px_ref["weights_samples"] > 0.05).float().mean())
+    _record(latent_to_pixels_occupied_fraction=occupied)
+    print(f"planes: ours {e_planes:.3e} / reference-bf16 {e_planes_ref:.3e}; pixels: ours {e_px:.3e} / "
+          f"reference-bf16 {e_px_ref:.3e}; occupied pixels {occupied:.2f}")
+    assert occupied > 0.1, "vacuous render: nothing in the volume"
+    assert e_planes < 3e-2, e_planes          # 24 bf16 DiT2 blocks + conv tail on random-init weights
     assert e_px < 3e-2, e_px
     assert e_planes < 1.5 * e_planes_ref + 1e-3 and e_px < 1.5 * e_px_ref + 1e-3
 

@@ -221,6 +221,17 @@ def test_overlay_lets_the_reference_script_utils_import():
         assert n.Triplane_fg_bg_plane.__module__ == "nsr.triplane"
         with pytest.raises(AttributeError):
             importlib.import_module("dit.dit_trilatent").no_such_name
+        # the reference's own factory, unmodified, now builds the mirrors (guided_diffusion/script_util.py:152-252)
+        d = g.model_and_diffusion_defaults()
+        d.update(dict(create_dit=True, dit_model_arch="DiT-B/2", context_dim=768, roll_out=True, denoise_in_channels=4,
+                      denoise_out_channels=4, diffusion_input_size=32, learn_sigma=False, mixed_prediction=False,
+                      timestep_respacing="10"))
+        model, diffusion = g.create_model_and_diffusion(**d)
+        assert type(model).__module__ == "ln3diff_b200.dit.dit_trilatent" and type(model).__name__ == "DiT_TriLatent"
+        assert type(diffusion).__module__ == "ln3diff_b200.guided_diffusion.respace" and diffusion.num_timesteps == 10
+        d.update(dict(i23d=True, dit_model_arch="DiT-PixArt-B/2", context_dim=1024))
+        model, _ = g.create_model_and_diffusion(**d)
+        assert type(model).__module__ == "ln3diff_b200.dit.dit_i23d"
     finally:
         overlay.uninstall()
         for k in list(sys.modules):

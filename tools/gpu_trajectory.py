@@ -26,7 +26,8 @@ c = torch.randn(1, 77, 768, generator=g)
 uc = torch.zeros(1, 77, 768)
 
 # ---- oracle loop (records the state at the marks)
-torch.set_num_threads(len(os.sched_getaffinity(0)))
+from ln3diff_b200.utils import host_cores
+torch.set_num_threads(host_cores())
 table = osmp.legacy_ddpm_sigmas(1000, append_zero=False, flip=True)
 sigmas = osmp.legacy_ddpm_sigmas(STEPS)
 ref_states = {}
