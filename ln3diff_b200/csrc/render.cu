@@ -269,11 +269,22 @@ __device__ __noinline__ void eval_batch(const RenderParams& p, const BlockSmem& 
         f[pl].z = ((v0.z * w.x + v1.z * w.y) + v2.z * w.z) + v3.z * w.w;
         f[pl].w = ((v0.w * w.x + v1.w * w.y) + v2.w * w.z) + v3.w * w.w;
       }
-      // sampled_features.mean(1)
-      ws.feat[sidx][c4 + 0] = ((f[0].x + f[1].x) + f[2].x) / 3.f;
-      ws.feat[sidx][c4 + 1] = ((f[0].y + f[1].y) + f[2].y) / 3.f;
-      ws.feat[sidx][c4 + 2] = ((f[0].z + f[1].z) + f[2].z) / 3.f;
-      ws.feat[sidx][c4 + 3] = ((f[0].w + f[1].w) + f[2].w) / 3.f;
+      // sampled_features.mean(1).  Exact path: IEEE division by 3 as torch's CPU mean (the oracle / goldens).
+      // TF32 path: sum * (1/3) as torch's CUDA mean kernel computes it (MeanOps multiplies by the fp32 factor
+      // 1/N) -- a last-ulp difference that the TF32 rounding of the MLP operand swallows; four IEEE divisions per
+      // lane here were ~10 % of the kernel's stall samples (profiles/r2_ncu_render_v3_tiles16.txt).
+      if constexpr (TF32) {
+        constexpr float kThird = 1.0f / 3.0f;
+        ws.feat[sidx][c4 + 0] = ((f[0].x + f[1].x) + f[2].x) * kThird;
+        ws.feat[sidx][c4 + 1] = ((f[0].y + f[1].y) + f[2].y) * kThird;
+        ws.feat[sidx][c4 + 2] = ((f[0].z + f[1].z) + f[2].z) * kThird;
+        ws.feat[sidx][c4 + 3] = ((f[0].w + f[1].w) + f[2].w) * kThird;
+      } else {
+        ws.feat[sidx][c4 + 0] = ((f[0].x + f[1].x) + f[2].x) / 3.f;
+        ws.feat[sidx][c4 + 1] = ((f[0].y + f[1].y) + f[2].y) / 3.f;
+        ws.feat[sidx][c4 + 2] = ((f[0].z + f[1].z) + f[2].z) / 3.f;
+        ws.feat[sidx][c4 + 3] = ((f[0].w + f[1].w) + f[2].w) / 3.f;
+      }
     }
   }
   __syncwarp();

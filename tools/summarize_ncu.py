@@ -58,5 +58,24 @@ def rep(src, dst):
                     out.write(f"  {m:72s} {r[i]:>16s} {units[i]}\n")
 
 
+def traffic(src, dst):
+    """dram read + write bytes of the (first) captured launch -> the JSON bench.py reads for `roofline.traffic`."""
+    import json
+    raw = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units, r = rows[0], rows[1], rows[2]
+
+    def val(name):
+        i = hdr.index(name)
+        v = float(r[i].replace(",", ""))
+        return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[units[i]]
+    rd, wr = val("dram__bytes_read.sum"), val("dram__bytes_write.sum")
+    i = hdr.index("gpu__time_duration.sum")
+    json.dump({"kernel": r[hdr.index("Kernel Name")], "dram_bytes_read": rd, "dram_bytes_write": wr,
+               "dram_bytes_per_launch": rd + wr, "gpu_time": f"{r[i]} {units[i]}",
+               "source": f"profiles/{dst.split('/')[-1]} <- ncu --set full --clock-control none capture {src.split('/')[-1]}"},
+              open(dst, "w"), indent=1)
+
+
 if __name__ == "__main__":
-    {"launches": launches, "rep": rep}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "rep": rep, "traffic": traffic}[sys.argv[1]](sys.argv[2], sys.argv[3])
