@@ -238,6 +238,14 @@ __device__ __noinline__ void eval_batch(const RenderParams& p, const BlockSmem& 
                                            float& cr, float& cg, float& cb) {
   inbox = (px >= p.bbox_min && px <= p.bbox_max) && (py >= p.bbox_min && py <= p.bbox_max) &&
           (pz >= p.bbox_min && pz <= p.bbox_max);
+  // The out-of-box filter (renderer.py:391-405) overwrites the network output of every sample outside the box, so
+  // a batch with no sample inside needs neither the gather nor the MLP: rays that miss the volume (their samples
+  // are spread over the group's global [min start, max end] range, all outside) cost only the bookkeeping.
+  if (!p.no_filter && !__any_sync(0xffffffffu, inbox)) {
+    sigma = -FLT_MAX / 3.f;
+    cr = cg = cb = 0.f;
+    return;
+  }
   // phase A: taps for this lane's sample
   {
     const float sx = p.coord_scale * px, sy = p.coord_scale * py, sz = p.coord_scale * pz;
@@ -385,9 +393,11 @@ __device__ __noinline__ void eval_batch(const RenderParams& p, const BlockSmem& 
 
 // Schedule: one CTA (16 warps = 16 rays) per SM walks work items; an item is a 4x4 PIXEL TILE of one view when the
 // rays of a view form an image (image_w > 0), else 16 consecutive rays.  Neighbouring pixels' rays pass through
-// neighbouring texels at every depth index, and the 16 warps of a tile stay in step (same trip counts, one
-// __syncthreads per item), so a texel line fetched by one warp is an L1 hit for its neighbours: the 64 KB of L1
-// left beside the shared-memory carve-out only helps rays that are co-resident in space AND time.
+// neighbouring texels at every depth index, and the 16 warps of a tile start together, so a texel line fetched by
+// one warp is usually an L1 hit for its neighbours (ncu: L1 hit rate 34 % -> 61.5 %, L2->L1 traffic -40 %): the
+// 64 KB of L1 left beside the shared-memory carve-out only helps rays that are co-resident in space AND time.
+// There is no barrier per item: rays that miss the volume skip the gather and the MLP (eval_batch) and their
+// warps simply move on to the next tile.
 template <bool TF32>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, 1)
 render_rays_kernel(const RenderParams p) {
@@ -402,7 +412,7 @@ render_rays_kernel(const RenderParams p) {
   const int tiles_x = p.image_w > 0 ? p.image_w / 4 : 0;
   const long long n_items = (total + kWarpsPerBlock - 1) / kWarpsPerBlock;   // tiles cover a view exactly (host check)
   const int items_per_view = p.M / kWarpsPerBlock;
-  for (long long item = blockIdx.x; item < n_items; item += gridDim.x, __syncthreads()) {
+  for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
     long long ray;
     if (tiles_x > 0) {
       const int v = static_cast<int>(item / items_per_view);
@@ -412,7 +422,7 @@ render_rays_kernel(const RenderParams p) {
     } else {
       ray = item * kWarpsPerBlock + warp;
     }
-    if (ray >= total) continue;   // linear schedule, last item only (the loop increment still syncs)
+    if (ray >= total) continue;   // linear schedule, last item only
     const int view = static_cast<int>(ray / p.M);
     const int grp = view / p.group_size;
     const int obj = p.view_obj ? p.view_obj[view] : view / p.views_per_obj;
