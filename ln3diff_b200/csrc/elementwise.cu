@@ -144,143 +144,283 @@ norm_modulate_kernel(const ln3_norm_modulate_args a) {
   }  // row loop
 }
 
-// 256-bit variant for D % 256 == 0 with 32-byte aligned rows (every DiT / DiT2 call): a lane owns NV8
-// chunks of 8 consecutive columns, so the fp32 row moves as LDG.256 / STG.256 (L1 no-allocate: each byte
-// is touched once) and the bf16 rows as 128-bit accesses -- half the memory instructions of the float4
-// version for the same bytes.  Same arithmetic, same order of operations per element.
+// ---- 256-bit kernels (D % 256 == 0, 32-byte aligned rows: every DiT / DiT2 call) -------------------------
+// A lane owns NV8 chunks of 8 consecutive columns: the fp32 row moves as 256-bit accesses and the bf16 rows as
+// 128-bit accesses.  nm_row_body is the arithmetic of one row, shared by the two kernels below; same operations in
+// the same order per element as the float4 kernel above.
+//   v      the row of x (registers)
+//   rown   this row's own residual row resid[row] (bf16, one uint4 per chunk), meaningful iff nm_needs_own_row()
+__device__ __forceinline__ bool nm_outside(const ln3_norm_modulate_args& a, int row) {
+  return a.resid_bcast != nullptr && (row < a.resid_row_begin || row >= a.resid_row_end);
+}
+__device__ __forceinline__ bool nm_needs_own_row(const ln3_norm_modulate_args& a, int row) {
+  return a.resid != nullptr && (!nm_outside(a, row) || a.resid_out_gate != nullptr);
+}
+
+template <int NV8>
+__device__ __forceinline__ void nm_row_body(const ln3_norm_modulate_args& a, int row, int lane, float (&v)[NV8][8],
+                                            const uint4 (&rown)[NV8]) {
+  float* x = const_cast<float*>(a.x) + static_cast<long long>(row) * a.ldx;
+  auto ld8 = [&](const float* p8, float* d8) {
+    const float4 p0 = __ldg(reinterpret_cast<const float4*>(p8));
+    const float4 p1 = __ldg(reinterpret_cast<const float4*>(p8 + 4));
+    d8[0] = p0.x, d8[1] = p0.y, d8[2] = p0.z, d8[3] = p0.w, d8[4] = p1.x, d8[5] = p1.y, d8[6] = p1.z, d8[7] = p1.w;
+  };
+  auto axpy8 = [&](float* acc, const float* g8, const uint4& rb) {
+    const uint32_t rw[4] = {rb.x, rb.y, rb.z, rb.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const __nv_bfloat162 r2 = *reinterpret_cast<const __nv_bfloat162*>(&rw[j]);
+      acc[2 * j] = fmaf(g8[2 * j], __low2float(r2), acc[2 * j]);
+      acc[2 * j + 1] = fmaf(g8[2 * j + 1], __high2float(r2), acc[2 * j + 1]);
+    }
+  };
+  if (a.resid != nullptr) {
+    const bool outside = nm_outside(a, row);
+    const bool own = !outside || a.resid_out_gate != nullptr;
+    // gate of the own row: resid_gate inside, resid_out_gate outside
+    const float* g_own = nullptr;
+    if (!outside) {
+      if (a.resid_gate) g_own = a.resid_gate + static_cast<long long>(row / a.resid_gate_rows) * a.resid_gate_ld;
+    } else if (a.resid_out_gate) {
+      g_own = a.resid_out_gate + static_cast<long long>(row / a.resid_out_gate_rows) * a.resid_out_gate_ld;
+    }
+    // outside rows: the per-group broadcast row, gated by resid_gate unless the own row took a gate of its own
+    const __nv_bfloat16* rb = nullptr;
+    const float* g_b = nullptr;
+    if (outside) {
+      rb = reinterpret_cast<const __nv_bfloat16*>(a.resid_bcast) + static_cast<long long>(row / a.resid_bcast_rows) * a.resid_bcast_ld;
+      if (a.resid_out_gate == nullptr && a.resid_gate)
+        g_b = a.resid_gate + static_cast<long long>(row / a.resid_gate_rows) * a.resid_gate_ld;
+    }
+#pragma unroll
+    for (int i = 0; i < NV8; ++i) {
+      const int c = (i * 32 + lane) * 8;
+      float g[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
+      if (own) {
+        if (g_own != nullptr) ld8(g_own + c, g);
+        axpy8(v[i], g, rown[i]);
+      }
+      if (rb != nullptr) {
+        float gb[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
+        if (g_b != nullptr) ld8(g_b + c, gb);
+        axpy8(v[i], gb, *reinterpret_cast<const uint4*>(rb + c));
+      }
+      stg256_f32(x + c, v[i]);
+    }
+    if (a.out == nullptr) return;
+  }
+  float mean = 0.f, rstd = 1.f;
+  if (a.norm == LN3_NORM_LAYER) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV8; ++i)  // same pairing as the float4 kernel: ((a+b)+(c+d)) per 4 columns
+      s += ((v[i][0] + v[i][1]) + (v[i][2] + v[i][3])) + ((v[i][4] + v[i][5]) + (v[i][6] + v[i][7]));
+    mean = warp_sum(s) / static_cast<float>(a.D);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV8; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float dlt = v[i][j] - mean;
+        q = fmaf(dlt, dlt, q);
+      }
+    rstd = rsqrtf(warp_sum(q) / static_cast<float>(a.D) + a.eps);
+  } else if (a.norm == LN3_NORM_RMS) {
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV8; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) q = fmaf(v[i][j], v[i][j], q);
+    rstd = rsqrtf(warp_sum(q) / static_cast<float>(a.D) + a.eps);
+  }
+  const float* sh = nullptr;
+  const float* sc = nullptr;
+  if (a.shift != nullptr) {
+    const long long g = row / a.mod_rows;
+    sh = a.shift + g * a.mod_ld;
+    sc = a.scale + g * a.mod_ld;
+  }
+  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(a.out) + static_cast<long long>(row) * a.ldo;
+#pragma unroll
+  for (int i = 0; i < NV8; ++i) {
+    const int c = (i * 32 + lane) * 8;
+    float y[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) y[j] = (v[i][j] - mean) * rstd;
+    if (a.weight != nullptr) {
+      float w[8];
+      ld8(a.weight + c, w);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) y[j] *= w[j];
+    }
+    if (sh != nullptr) {
+      float s1[8], s0[8];
+      ld8(sc + c, s1);
+      ld8(sh + c, s0);
+      if (a.scale_tab != nullptr) {
+        float t1[8], t0[8];
+        ld8(a.scale_tab + c, t1);
+        ld8(a.shift_tab + c, t0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s1[j] += t1[j], s0[j] += t0[j];
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) y[j] = fmaf(y[j], 1.f + s1[j], s0[j]);
+    }
+    if (a.act != LN3_ACT_NONE) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) y[j] = apply_act(y[j], a.act);
+    }
+    uint4 pk;
+    pk.x = pack_bf16x2(y[0], y[1]);
+    pk.y = pack_bf16x2(y[2], y[3]);
+    pk.z = pack_bf16x2(y[4], y[5]);
+    pk.w = pack_bf16x2(y[6], y[7]);
+    *reinterpret_cast<uint4*>(o + c) = pk;
+  }
+}
+
+// Warp per row straight from global memory.  (A software-pipelined variant -- next row's loads issued before the
+// current row's arithmetic, 2 CTAs/SM at 128 registers -- measured slower: 36.9 vs 32.8 us; so did the shared-memory
+// staged kernel below.  Occupancy at <= 80 registers beats explicit prefetch here.)
+template <int NV8>
+__device__ __forceinline__ void nm_load_row(const ln3_norm_modulate_args& a, int row, int lane, float (&v)[NV8][8],
+                                            uint4 (&rown)[NV8]) {
+  const float* x = a.x + static_cast<long long>(row) * a.ldx;
+#pragma unroll
+  for (int i = 0; i < NV8; ++i) ldg256_na(x + (i * 32 + lane) * 8, v[i]);
+  if (nm_needs_own_row(a, row)) {
+    const __nv_bfloat16* rr = reinterpret_cast<const __nv_bfloat16*>(a.resid) + static_cast<long long>(row) * a.resid_ld;
+#pragma unroll
+    for (int i = 0; i < NV8; ++i) rown[i] = *reinterpret_cast<const uint4*>(rr + (i * 32 + lane) * 8);
+  } else {
+#pragma unroll
+    for (int i = 0; i < NV8; ++i) rown[i] = make_uint4(0, 0, 0, 0);
+  }
+}
+
 template <int NV8>
 __global__ void __launch_bounds__(256, 3)
 norm_modulate_wide_kernel(const ln3_norm_modulate_args a) {
   pdl_launch_dependents();
   pdl_wait();
   const int lane = threadIdx.x & 31;
-  for (int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < a.rows;
-       row += gridDim.x * (blockDim.x >> 5)) {
-    float* x = const_cast<float*>(a.x) + static_cast<long long>(row) * a.ldx;
+  // A CTA owns a contiguous run of rows (not a grid-stride comb): consecutive token rows share their sample's
+  // shift / scale / gate vectors, which then stay in L1 instead of every SM cycling through all samples' vectors
+  // (LN + residual pass 36-38 -> 32.8 us at DiT-L/2 B'=16).
+  const int per_cta = (a.rows + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  const int row_begin = static_cast<int>(blockIdx.x) * per_cta;
+  const int row_end = min(a.rows, row_begin + per_cta);
+  for (int row = row_begin + (threadIdx.x >> 5); row < row_end; row += (blockDim.x >> 5)) {
     float v[NV8][8];
-#pragma unroll
-    for (int i = 0; i < NV8; ++i) ldg256_na(x + (i * 32 + lane) * 8, v[i]);
-    if (a.resid != nullptr) {
-      const __nv_bfloat16* rr = reinterpret_cast<const __nv_bfloat16*>(a.resid) + static_cast<long long>(row) * a.resid_ld;
-      const __nv_bfloat16* r2 = nullptr;   // outside rows with resid_out_gate: own resid row first, then the bcast row
-      const float* g2 = nullptr;
-      if (a.resid_bcast != nullptr && (row < a.resid_row_begin || row >= a.resid_row_end)) {
-        if (a.resid_out_gate != nullptr) {
-          r2 = rr;
-          g2 = a.resid_out_gate + static_cast<long long>(row / a.resid_out_gate_rows) * a.resid_out_gate_ld;
+    uint4 rown[NV8];
+    nm_load_row<NV8>(a, row, lane, v, rown);
+    nm_row_body<NV8>(a, row, lane, v, rown);
+  }
+}
+
+// Staged variant for the big residual-stream passes (the three per DiT block: 150 MB each at DiT-L/2 B'=16).
+// The warp-per-row kernel keeps at most one row per warp in flight and stops loading while it reduces and stores
+// (ncu: 4.2-4.9 TB/s = 0.64-0.75 of the measured copy bandwidth, dram ~40 % busy).  Here a producer thread streams
+// the fp32 rows (and their bf16 residual rows) into a 4-stage shared-memory ring with 1-D bulk copies
+// (cp.async.bulk, byte-counted mbarriers), 8 rows per stage, so ~144 KB per SM is always in flight while 8 consumer
+// warps (one row each) run the unchanged arithmetic out of shared memory and store straight to global.
+static constexpr int kNmStages = 4, kNmRowsPerStage = 8;
+template <int NV8>
+constexpr int nm_stage_bytes() { return kNmRowsPerStage * NV8 * 256 * (4 + 2); }
+template <int NV8>
+constexpr int nm_staged_smem() { return kNmStages * nm_stage_bytes<NV8>() + 128; }
+
+template <int NV8>
+__global__ void __launch_bounds__((kNmRowsPerStage + 1) * 32, 1)
+norm_modulate_staged_kernel(const ln3_norm_modulate_args a) {
+  extern __shared__ __align__(128) uint8_t nm_smem[];
+  constexpr int D = NV8 * 256;
+  constexpr int kXBytes = D * 4, kRBytes = D * 2;
+  uint64_t* full = reinterpret_cast<uint64_t*>(nm_smem + kNmStages * nm_stage_bytes<NV8>());
+  uint64_t* empty = full + kNmStages;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kNmStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], kNmRowsPerStage);
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
+  pdl_launch_dependents();
+  pdl_wait();
+  const int n_groups = (a.rows + kNmRowsPerStage - 1) / kNmRowsPerStage;
+  // contiguous run of row groups per CTA: the per-sample modulation vectors (shift / scale / gate rows, shared by
+  // 768 consecutive token rows) stay hot in the 28 KB of L1 left beside the ring
+  const int gpb = (n_groups + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  const int g_begin = static_cast<int>(blockIdx.x) * gpb;
+  const int g_end = min(n_groups, g_begin + gpb);
+  if (warp == kNmRowsPerStage) {
+    // ---- producer: one lane issues the bulk copies of a whole stage
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int g = g_begin; g < g_end; ++g) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        uint8_t* sx = nm_smem + stage * nm_stage_bytes<NV8>();
+        uint8_t* sr = sx + kNmRowsPerStage * kXBytes;
+        const int row0 = g * kNmRowsPerStage;
+        const int nrows = min(kNmRowsPerStage, a.rows - row0);
+        // contiguous rows (the usual case: x and resid are dense [rows, D] buffers) move as ONE bulk copy per
+        // operand and stage -- a bulk-copy instruction costs hundreds of issue cycles on the producer thread, and
+        // sixteen 2-4 KB copies per stage made the producer the bottleneck (2.4 TB/s)
+        int n_own = 0;
+        for (int r = 0; r < nrows; ++r) n_own += nm_needs_own_row(a, row0 + r) ? 1 : 0;
+        mbar_arrive_expect_tx(&full[stage], nrows * kXBytes + n_own * kRBytes);
+        if (a.ldx == D) {
+          bulk_load_1d(sx, a.x + static_cast<long long>(row0) * a.ldx, nrows * kXBytes, &full[stage]);
+        } else {
+          for (int r = 0; r < nrows; ++r)
+            bulk_load_1d(sx + r * kXBytes, a.x + static_cast<long long>(row0 + r) * a.ldx, kXBytes, &full[stage]);
         }
-        rr = reinterpret_cast<const __nv_bfloat16*>(a.resid_bcast) + static_cast<long long>(row / a.resid_bcast_rows) * a.resid_bcast_ld;
+        if (n_own == nrows && a.resid_ld == D) {
+          bulk_load_1d(sr, reinterpret_cast<const __nv_bfloat16*>(a.resid) + static_cast<long long>(row0) * a.resid_ld,
+                       nrows * kRBytes, &full[stage]);
+        } else if (n_own > 0) {
+          for (int r = 0; r < nrows; ++r)
+            if (nm_needs_own_row(a, row0 + r))
+              bulk_load_1d(sr + r * kRBytes,
+                           reinterpret_cast<const __nv_bfloat16*>(a.resid) + static_cast<long long>(row0 + r) * a.resid_ld,
+                           kRBytes, &full[stage]);
+        }
+        if (++stage == kNmStages) stage = 0, phase ^= 1;
       }
-      const float* gg = (a.resid_gate && r2 == nullptr)
-                            ? a.resid_gate + static_cast<long long>(row / a.resid_gate_rows) * a.resid_gate_ld : nullptr;
+    }
+    return;
+  }
+  // ---- consumers: warp w owns row w of every stage
+  int stage = 0;
+  uint32_t phase = 0;
+  for (int g = g_begin; g < g_end; ++g) {
+    const int row = g * kNmRowsPerStage + warp;
+    mbar_wait(&full[stage], phase);
+    float v[NV8][8];
+    uint4 rown[NV8];
+    const bool live = row < a.rows;
+    if (live) {
+      const uint8_t* sx = nm_smem + stage * nm_stage_bytes<NV8>() + warp * kXBytes;
+      const uint8_t* sr = nm_smem + stage * nm_stage_bytes<NV8>() + kNmRowsPerStage * kXBytes + warp * kRBytes;
+      const bool own = nm_needs_own_row(a, row);
 #pragma unroll
       for (int i = 0; i < NV8; ++i) {
-        const int c = (i * 32 + lane) * 8;
-        if (r2 != nullptr) {
-          const uint4 qb = *reinterpret_cast<const uint4*>(r2 + c);
-          const uint32_t qw[4] = {qb.x, qb.y, qb.z, qb.w};
-          const float4 h0 = __ldg(reinterpret_cast<const float4*>(g2 + c));
-          const float4 h1 = __ldg(reinterpret_cast<const float4*>(g2 + c + 4));
-          const float h[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const __nv_bfloat162 q2 = *reinterpret_cast<const __nv_bfloat162*>(&qw[j]);
-            v[i][2 * j] = fmaf(h[2 * j], __low2float(q2), v[i][2 * j]);
-            v[i][2 * j + 1] = fmaf(h[2 * j + 1], __high2float(q2), v[i][2 * j + 1]);
-          }
-        }
-        const uint4 rb = *reinterpret_cast<const uint4*>(rr + c);
-        const uint32_t rw[4] = {rb.x, rb.y, rb.z, rb.w};
-        float g[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
-        if (gg != nullptr) {
-          const float4 g0 = __ldg(reinterpret_cast<const float4*>(gg + c));
-          const float4 g1 = __ldg(reinterpret_cast<const float4*>(gg + c + 4));
-          g[0] = g0.x, g[1] = g0.y, g[2] = g0.z, g[3] = g0.w, g[4] = g1.x, g[5] = g1.y, g[6] = g1.z, g[7] = g1.w;
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const __nv_bfloat162 r2 = *reinterpret_cast<const __nv_bfloat162*>(&rw[j]);
-          v[i][2 * j] = fmaf(g[2 * j], __low2float(r2), v[i][2 * j]);
-          v[i][2 * j + 1] = fmaf(g[2 * j + 1], __high2float(r2), v[i][2 * j + 1]);
-        }
-        stg256_f32(x + c, v[i]);
+        const float4 lo = *reinterpret_cast<const float4*>(sx + (i * 32 + lane) * 32);
+        const float4 hi = *reinterpret_cast<const float4*>(sx + (i * 32 + lane) * 32 + 16);
+        v[i][0] = lo.x, v[i][1] = lo.y, v[i][2] = lo.z, v[i][3] = lo.w;
+        v[i][4] = hi.x, v[i][5] = hi.y, v[i][6] = hi.z, v[i][7] = hi.w;
+        rown[i] = own ? *reinterpret_cast<const uint4*>(sr + (i * 32 + lane) * 16) : make_uint4(0, 0, 0, 0);
       }
-      if (a.out == nullptr) continue;
     }
-    float mean = 0.f, rstd = 1.f;
-    if (a.norm == LN3_NORM_LAYER) {
-      float s = 0.f;
-#pragma unroll
-      for (int i = 0; i < NV8; ++i)  // same pairing as the float4 kernel: ((a+b)+(c+d)) per 4 columns
-        s += ((v[i][0] + v[i][1]) + (v[i][2] + v[i][3])) + ((v[i][4] + v[i][5]) + (v[i][6] + v[i][7]));
-      mean = warp_sum(s) / static_cast<float>(a.D);
-      float q = 0.f;
-#pragma unroll
-      for (int i = 0; i < NV8; ++i)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float dlt = v[i][j] - mean;
-          q = fmaf(dlt, dlt, q);
-        }
-      rstd = rsqrtf(warp_sum(q) / static_cast<float>(a.D) + a.eps);
-    } else if (a.norm == LN3_NORM_RMS) {
-      float q = 0.f;
-#pragma unroll
-      for (int i = 0; i < NV8; ++i)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) q = fmaf(v[i][j], v[i][j], q);
-      rstd = rsqrtf(warp_sum(q) / static_cast<float>(a.D) + a.eps);
-    }
-    const float* sh = nullptr;
-    const float* sc = nullptr;
-    if (a.shift != nullptr) {
-      const long long g = row / a.mod_rows;
-      sh = a.shift + g * a.mod_ld;
-      sc = a.scale + g * a.mod_ld;
-    }
-    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(a.out) + static_cast<long long>(row) * a.ldo;
-#pragma unroll
-    for (int i = 0; i < NV8; ++i) {
-      const int c = (i * 32 + lane) * 8;
-      float y[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) y[j] = (v[i][j] - mean) * rstd;
-      auto ld8 = [&](const float* p8, float* d8) {
-        const float4 p0 = __ldg(reinterpret_cast<const float4*>(p8));
-        const float4 p1 = __ldg(reinterpret_cast<const float4*>(p8 + 4));
-        d8[0] = p0.x, d8[1] = p0.y, d8[2] = p0.z, d8[3] = p0.w, d8[4] = p1.x, d8[5] = p1.y, d8[6] = p1.z, d8[7] = p1.w;
-      };
-      if (a.weight != nullptr) {
-        float w[8];
-        ld8(a.weight + c, w);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) y[j] *= w[j];
-      }
-      if (sh != nullptr) {
-        float s1[8], s0[8];
-        ld8(sc + c, s1);
-        ld8(sh + c, s0);
-        if (a.scale_tab != nullptr) {
-          float t1[8], t0[8];
-          ld8(a.scale_tab + c, t1);
-          ld8(a.shift_tab + c, t0);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) s1[j] += t1[j], s0[j] += t0[j];
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) y[j] = fmaf(y[j], 1.f + s1[j], s0[j]);
-      }
-      if (a.act != LN3_ACT_NONE) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) y[j] = apply_act(y[j], a.act);
-      }
-      uint4 pk;
-      pk.x = pack_bf16x2(y[0], y[1]);
-      pk.y = pack_bf16x2(y[2], y[3]);
-      pk.z = pack_bf16x2(y[4], y[5]);
-      pk.w = pack_bf16x2(y[6], y[7]);
-      *reinterpret_cast<uint4*>(o + c) = pk;
-    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[stage]);   // the row is in registers: the producer may refill the slot
+    if (live) nm_row_body<NV8>(a, row, lane, v, rown);
+    if (++stage == kNmStages) stage = 0, phase ^= 1;
   }
 }
 
@@ -319,6 +459,37 @@ int norm_modulate(const ln3_norm_modulate_args* a, cudaStream_t stream) {
   const bool wide = wide_enabled && a->D % 256 == 0 && a->D <= 1536 && a->ldx % 8 == 0 && a->ldo % 8 == 0 &&
                     (reinterpret_cast<uintptr_t>(a->x) & 31) == 0 && (a->out == nullptr || (reinterpret_cast<uintptr_t>(a->out) & 15) == 0) &&
                     (a->resid == nullptr || (a->resid_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(a->resid) & 15) == 0));
+  // opt-in (LN3_NORM_STAGED=1): shared-memory staged kernel for the big residual-stream passes.  Measured slower
+  // than the warp-per-row kernel (48 vs 36 us for LN + residual at DiT-L/2 B'=16): with the ring taking 196 KB the
+  // CTA has 8 consumer warps and 28 KB of L1, and the per-row arithmetic (two reductions, the modulation-vector
+  // loads) then bounds the pass, not the loads.
+  static const bool staged_enabled = getenv("LN3_NORM_STAGED") && atoi(getenv("LN3_NORM_STAGED")) != 0;
+  if (wide && staged_enabled && a->D <= 1024 && a->rows >= 2048 && (a->ldx * 4) % 16 == 0 &&
+      (a->resid == nullptr || (a->resid_ld * 2) % 16 == 0)) {
+    const int sms = device_sm_count();
+    const int n_groups = (a->rows + kNmRowsPerStage - 1) / kNmRowsPerStage;
+    const dim3 sgrid(n_groups < sms ? n_groups : sms), sblock((kNmRowsPerStage + 1) * 32);
+    static DeviceOnce once;
+    if (int rc = once.run([] {
+          cudaError_t e = cudaFuncSetAttribute(norm_modulate_staged_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, nm_staged_smem<1>());
+          if (e == cudaSuccess) e = cudaFuncSetAttribute(norm_modulate_staged_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, nm_staged_smem<2>());
+          if (e == cudaSuccess) e = cudaFuncSetAttribute(norm_modulate_staged_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, nm_staged_smem<3>());
+          if (e == cudaSuccess) e = cudaFuncSetAttribute(norm_modulate_staged_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, nm_staged_smem<4>());
+          return e == cudaSuccess ? LN3_OK : set_error(LN3_ECUDA, "norm_modulate: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        }))
+      return rc;
+    cudaError_t le = cudaSuccess;
+    switch (a->D / 256) {
+      case 1: le = launch_pdl(norm_modulate_staged_kernel<1>, sgrid, sblock, nm_staged_smem<1>(), stream, *a); break;
+      case 2: le = launch_pdl(norm_modulate_staged_kernel<2>, sgrid, sblock, nm_staged_smem<2>(), stream, *a); break;
+      case 3: le = launch_pdl(norm_modulate_staged_kernel<3>, sgrid, sblock, nm_staged_smem<3>(), stream, *a); break;
+      default: le = launch_pdl(norm_modulate_staged_kernel<4>, sgrid, sblock, nm_staged_smem<4>(), stream, *a); break;
+    }
+    cudaError_t e = le != cudaSuccess ? le : cudaGetLastError();
+    if (e != cudaSuccess) return set_error(LN3_ECUDA, "norm_modulate launch: %s", cudaGetErrorString(e));
+    count_launch();
+    return LN3_OK;
+  }
   if (wide) {
     cudaError_t le = cudaSuccess;
     const int wave3 = device_sm_count() * 3;  // 3 resident blocks per SM at <= 80 registers
