@@ -31,6 +31,8 @@
 
 namespace ln3 {
 
+int fmha3_launch(const ln3_fmha_args* a, int variant, cudaStream_t stream);  // attention3_tcgen05.cu
+
 static constexpr int kQT = 128;   // query rows per tile (2 tiles per CTA)
 static constexpr int kKT = 128;   // kv rows per block
 static constexpr int kHD = 64;    // head dim
@@ -666,6 +668,24 @@ int fmha_fwd(const ln3_fmha_args* a, cudaStream_t stream) {
   if ((reinterpret_cast<uintptr_t>(a->q) | reinterpret_cast<uintptr_t>(a->k) |
        reinterpret_cast<uintptr_t>(a->v) | reinterpret_cast<uintptr_t>(a->out)) & 15)
     return set_error(LN3_EINVAL, "fmha: pointers must be 16-byte aligned");
+  // LN3_FMHA_KERNEL: 3 (default) = three-warpgroup rota kernel (attention3_tcgen05.cu), 2 = the two-warpgroup
+  // kernel of this file.  LN3_FMHA_ROTA=1 switches the exponential-phase rota on (measured 2 % slower), LN3_FMHA_POLY=2 moves 2 of 8 exponentials to the FMA pipe.
+  static const int kernel3 = [] {
+    const char* kv = getenv("LN3_FMHA_KERNEL");
+    if (kv && atoi(kv) == 2) return -1;
+    const char* ro = getenv("LN3_FMHA_ROTA");
+    const char* po = getenv("LN3_FMHA_POLY");
+    return ((ro && atoi(ro) != 0) ? 0 : 1) | ((po && atoi(po) == 2) ? 2 : 0);   // bit 0 = rota OFF (default)
+  }();
+  if (kernel3 >= 0) {
+    if (a->k2 != nullptr || a->v2 != nullptr) {
+      if (!a->k2 || !a->v2 || a->Lkv2 <= 0) return set_error(LN3_EINVAL, "fmha: k2/v2/Lkv2 must be given together");
+      if ((a->k2_ld | a->v2_ld | a->k2_bs | a->v2_bs) % 8 ||
+          ((reinterpret_cast<uintptr_t>(a->k2) | reinterpret_cast<uintptr_t>(a->v2)) & 15))
+        return set_error(LN3_EINVAL, "fmha: k2/v2 alignment");
+    }
+    return fmha3_launch(a, kernel3, stream);
+  }
   // tuning knobs, read once: LN3_FMHA_POLY = exponentials per 8 on the FMA pipe (0, 2, 3, 4);
   // LN3_FMHA_PINGPONG = 1 enables the XU baton between the two softmax warpgroups (measured: no gain)
   static const int variant = [] {   // environment knobs: device-independent, read once (thread-safe static init)
