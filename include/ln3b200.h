@@ -341,6 +341,39 @@ int ln3_generate_rays(const float* cams, int V, int res, float* ray_o, float* ra
 int ln3_planes_to_channels_last(const float* planes, int n_obj, int C, int H, int W, float* out,
                                 void* stream);
 
+/* ------------------------------------------------------------------ mesh extraction: marching cubes
+ * Replaces the CPU `mcubes.marching_cubes(grid_out['sigma'] as (G,G,G) numpy, mesh_thres)` call of the mesh
+ * export (nsr/train_util_diffusion.py:221-223; PyMCubes is an un-vendored third-party package) that follows
+ * the G^3 point query (ln3_query_points).  grid fp32 [nx][ny][nz] (z fastest), exactly the array the reference
+ * hands to mcubes.  Output is an indexed mesh like PyMCubes':
+ *   vertices fp32 [n_vertices][3] = (i, j, k) index coordinates of the iso crossing on a lattice edge
+ *            (linear interpolation, `value <= iso` classifies a corner), times scale[] plus offset[] per axis
+ *            (scale 1 / offset 0 = mcubes; 2/(G-1)*0.45 and -0.45 fold the reference's :225-226 rescale in);
+ *            ordered by (owning lattice point's linear index, axis)
+ *   faces    int32 [n_faces][3] vertex indices, ordered by the cell's linear index; winding of the classic
+ *            case table (normal towards the `<= iso` side), case tables generated by tools/gen_mc_tables.py.
+ * Two calls because the sizes are data dependent: `_count` classifies and scans (totals[0] = n_vertices,
+ * totals[1] = n_faces, device ints the caller reads back), `_emit` writes at most max_vertices / max_faces
+ * entries.  workspace: ln3_marching_cubes_workspace_bytes(nx, ny, nz) bytes, 256-byte aligned, the SAME buffer
+ * (contents preserved) for both calls. */
+typedef struct ln3_marching_cubes_args {
+  const float* grid;
+  void* workspace;
+  size_t workspace_bytes;
+  int* totals;      /* device int[2] */
+  float* vertices;  /* emit only */
+  int* faces;       /* emit only */
+  int nx, ny, nz;
+  int max_vertices, max_faces;
+  float iso;
+  float scale[3];
+  float offset[3];
+} ln3_marching_cubes_args;
+
+size_t ln3_marching_cubes_workspace_bytes(int nx, int ny, int nz);
+int ln3_marching_cubes_count(const ln3_marching_cubes_args* args, void* stream);
+int ln3_marching_cubes_emit(const ln3_marching_cubes_args* args, void* stream);
+
 /* ------------------------------------------------------------------ frame sink
  * TrainLoopDiffusionWithRec.render_video_given_triplane's per-view host loop
  * (nsr/train_util_diffusion.py:292-376): `.cpu()` + numpy + matplotlib per view, replaced by one device

@@ -126,6 +126,15 @@ class PackFramesArgs(C.Structure):
     ]
 
 
+class MarchingCubesArgs(C.Structure):
+    _fields_ = [
+        ("grid", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t), ("totals", C.c_void_p),
+        ("vertices", C.c_void_p), ("faces", C.c_void_p),
+        ("nx", C.c_int), ("ny", C.c_int), ("nz", C.c_int), ("max_vertices", C.c_int), ("max_faces", C.c_int),
+        ("iso", C.c_float), ("scale", C.c_float * 3), ("offset", C.c_float * 3),
+    ]
+
+
 class ConvArgs(C.Structure):
     _fields_ = [
         ("x", C.c_void_p), ("w", C.c_void_p), ("bias", C.c_void_p), ("in_scale", C.c_void_p),
@@ -154,6 +163,7 @@ def lib() -> C.CDLL:
         L.ln3_add_launch_count.restype = None
         L.ln3_render_workspace_bytes.restype = C.c_size_t
         L.ln3_gemm_workspace_bytes.restype = C.c_size_t
+        L.ln3_marching_cubes_workspace_bytes.restype = C.c_size_t
         _lib = L
     return _lib
 

@@ -163,6 +163,15 @@ int ln3_planes_to_channels_last(const float* planes, int n_obj, int C, int H, in
   return planes_to_channels_last(planes, n_obj, C, H, W, out, static_cast<cudaStream_t>(stream));
 }
 
+size_t ln3_marching_cubes_workspace_bytes(int nx, int ny, int nz) { return marching_cubes_workspace_bytes(nx, ny, nz); }
+int ln3_marching_cubes_count(const ln3_marching_cubes_args* args, void* stream) {
+  if (!args) return set_error(LN3_EINVAL, "marching_cubes_count: null args");
+  return marching_cubes_count(args, static_cast<cudaStream_t>(stream));
+}
+int ln3_marching_cubes_emit(const ln3_marching_cubes_args* args, void* stream) {
+  if (!args) return set_error(LN3_EINVAL, "marching_cubes_emit: null args");
+  return marching_cubes_emit(args, static_cast<cudaStream_t>(stream));
+}
 int ln3_pack_frames(const ln3_pack_frames_args* args, void* stream) {
   if (!args) return set_error(LN3_EINVAL, "pack_frames: null args");
   return pack_frames(args, static_cast<cudaStream_t>(stream));

@@ -80,6 +80,9 @@ int planes_to_channels_last(const float* planes, int n_obj, int C, int H, int W,
                             cudaStream_t stream);
 
 int pack_frames(const ln3_pack_frames_args* a, cudaStream_t stream);
+size_t marching_cubes_workspace_bytes(int nx, int ny, int nz);
+int marching_cubes_count(const ln3_marching_cubes_args* a, cudaStream_t stream);
+int marching_cubes_emit(const ln3_marching_cubes_args* a, cudaStream_t stream);
 
 int conv_nhwc(const ln3_conv_args* a, cudaStream_t stream);
 int groupnorm_stats(const float* x, const float* gamma, const float* beta, int N, int HW, int C, int G,

@@ -564,3 +564,35 @@ def patch_embed_triplane(latent: torch.Tensor, weight: torch.Tensor, bias: torch
                                                    C.c_float(in_mul), _lib.ptr(tok), _lib.ptr(sb),
                                                    _lib.current_stream()), "ln3_patch_embed_triplane")
     return tok, sb
+
+
+def marching_cubes(volume: torch.Tensor, isovalue: float, *, scale=(1.0, 1.0, 1.0), offset=(0.0, 0.0, 0.0)):
+    """Device marching cubes (`mcubes.marching_cubes(volume, isovalue)`, nsr/train_util_diffusion.py:221-223).
+    volume (nx, ny, nz) fp32 CUDA, z fastest.  Returns (vertices fp32 (V, 3), faces int32 (F, 3)) on the device;
+    vertices are index coordinates times `scale` plus `offset` per axis.  One host sync (the mesh size is data
+    dependent: the counts are read back between the count and the emit pass)."""
+    _cuda(volume, "volume", torch.float32)
+    _req(volume.dim() == 3 and volume.is_contiguous(), "volume must be contiguous (nx, ny, nz)")
+    nx, ny, nz = (int(v) for v in volume.shape)
+    _req(min(nx, ny, nz) >= 2, "every volume dimension must be >= 2")
+    dev = volume.device
+    wbytes = int(_lib.lib().ln3_marching_cubes_workspace_bytes(nx, ny, nz))
+    ws = torch.empty(wbytes, dtype=torch.uint8, device=dev)
+    totals = torch.zeros(2, dtype=torch.int32, device=dev)
+    a = _lib.MarchingCubesArgs()
+    a.grid, a.workspace, a.workspace_bytes, a.totals = volume.data_ptr(), ws.data_ptr(), wbytes, totals.data_ptr()
+    a.nx, a.ny, a.nz, a.iso = nx, ny, nz, float(isovalue)
+    for q in range(3):
+        a.scale[q], a.offset[q] = float(scale[q]), float(offset[q])
+    _lib.check(_lib.lib().ln3_marching_cubes_count(C.byref(a), _lib.current_stream()), "ln3_marching_cubes_count")
+    nv, nf = (int(v) for v in totals.tolist())
+    vertices = torch.empty((nv, 3), dtype=torch.float32, device=dev)
+    faces = torch.empty((nf, 3), dtype=torch.int32, device=dev)
+    if nv == 0 and nf == 0:
+        return vertices, faces
+    # ctypes rejects NULL-size tensors' data_ptr() == 0 only when both are empty (handled above)
+    a.vertices = vertices.data_ptr() if nv else ws.data_ptr()
+    a.faces = faces.data_ptr() if nf else ws.data_ptr()
+    a.max_vertices, a.max_faces = nv, nf
+    _lib.check(_lib.lib().ln3_marching_cubes_emit(C.byref(a), _lib.current_stream()), "ln3_marching_cubes_emit")
+    return vertices, faces
