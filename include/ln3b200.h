@@ -52,7 +52,8 @@ void ln3_add_launch_count(unsigned long long n);
  *                      (the un-normalised cross-attention query input of TextCondDiTBlock).
  * Constraints: K % 64 == 0, N % 128 == 0, 16-byte aligned pointers and leading dimensions.
  */
-enum { LN3_ACT_NONE = 0, LN3_ACT_GELU_ERF = 1, LN3_ACT_GELU_TANH = 2, LN3_ACT_SILU = 3 };
+enum { LN3_ACT_NONE = 0, LN3_ACT_GELU_ERF = 1, LN3_ACT_GELU_TANH = 2, LN3_ACT_SILU = 3,
+       LN3_ACT_QUICK_GELU = 4 /* x * sigmoid(1.702 x): the CLIP towers of the conditioners */ };
 enum { LN3_OUT_BF16 = 0, LN3_OUT_F32 = 1, LN3_OUT_RESID_F32 = 2 };
 
 typedef struct ln3_gemm_args {
@@ -107,13 +108,16 @@ typedef struct ln3_fmha_args {
   long long q_ld, q_bs, k_ld, k_bs, v_ld, v_bs, o_ld, o_bs; /* elements */
   float scale;
   /* optional second K/V source appended after the first along the sequence (Lkv must then be a
-   * multiple of 128): the step-invariant DINO tokens the I23D blocks concatenate to the latent
+   * multiple of 128 for the two-warpgroup kernel; the default kernel takes any Lkv): the step-invariant DINO tokens the I23D blocks concatenate to the latent
    * tokens for self-attention (dit/dit_models_xformers.py:522-530) -- their K/V are cached per
    * prompt and never copied.  k2/v2 NULL -> unused. */
   const void* k2;
   const void* v2;
   int Lkv2;
   long long k2_ld, k2_bs, v2_ld, v2_bs;
+  /* causal != 0: key j is visible to query i only when j <= i (the CLIP text tower of FrozenCLIPEmbedder,
+   * sgm/modules/encoders/modules.py:347-408 -> transformers CLIPTextModel's causal mask); not with k2/v2. */
+  int causal;
 } ln3_fmha_args;
 
 int ln3_fmha_fwd(const ln3_fmha_args* args, void* stream);

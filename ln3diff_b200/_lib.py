@@ -13,7 +13,7 @@ _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "libln3b200.so"
 
 LN3_OK = 0
-ACT_NONE, ACT_GELU_ERF, ACT_GELU_TANH, ACT_SILU = 0, 1, 2, 3
+ACT_NONE, ACT_GELU_ERF, ACT_GELU_TANH, ACT_SILU, ACT_QUICK_GELU = 0, 1, 2, 3, 4
 OUT_BF16, OUT_F32, OUT_RESID_F32 = 0, 1, 2
 
 _lib = None
@@ -43,6 +43,7 @@ class FmhaArgs(C.Structure):
         ("scale", C.c_float),
         ("k2", C.c_void_p), ("v2", C.c_void_p), ("Lkv2", C.c_int),
         ("k2_ld", C.c_longlong), ("k2_bs", C.c_longlong), ("v2_ld", C.c_longlong), ("v2_bs", C.c_longlong),
+        ("causal", C.c_int),
     ]
 
 

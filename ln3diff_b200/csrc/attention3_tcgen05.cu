@@ -69,6 +69,7 @@ struct Params {
   float rcp_nq, rcp_H;
   float scale_log2;
   int full_items, n_split;  // tail schedule: see the file header
+  int causal;               // key j visible to query i only when j <= i
 };
 
 // 2^x on the FMA pipe (same polynomial as the two-warpgroup kernel; rel. error 8.8e-5 < bf16 rounding of P)
@@ -369,6 +370,12 @@ fmha3_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           for (int i = 0; i < kKB; ++i)
             if (i >= kv_valid) s[i] = 0xff800000u;  // -inf
         }
+        if (p.causal) {   // (first K/V source only; every row keeps key 0, so block 0 is never fully masked)
+          const int lim = q0 + t * kQT + row - j * kKB;   // columns i > lim are in the future of this row
+#pragma unroll
+          for (int i = 0; i < kKB; ++i)
+            if (i > lim) s[i] = 0xff800000u;
+        }
         const int c_end = kv_valid >= kKB ? kKB : (kv_valid + 15) & ~15;  // = 16 * PV k-steps
         // three independent 3-input max chains
         float mq[3];
@@ -528,6 +535,7 @@ int fmha3_launch(const ln3_fmha_args* a, int variant, cudaStream_t stream) {
   p.Lkv = a->Lkv;
   p.Lkv2 = two ? a->Lkv2 : 0;
   p.scale_log2 = a->scale * 1.4426950408889634f;
+  p.causal = a->causal ? 1 : 0;
   p.B = a->B;
   p.H = a->H;
   p.nq = (a->Lq + kNT * kQT - 1) / (kNT * kQT);

@@ -677,6 +677,9 @@ int fmha_fwd(const ln3_fmha_args* a, cudaStream_t stream) {
     const char* po = getenv("LN3_FMHA_POLY");
     return ((ro && atoi(ro) != 0) ? 0 : 1) | ((po && atoi(po) == 2) ? 2 : 0);   // bit 0 = rota OFF (default)
   }();
+  if (a->causal && (a->k2 != nullptr || a->v2 != nullptr))
+    return set_error(LN3_EINVAL, "fmha: causal attention takes a single K/V source");
+  if (a->causal && kernel3 < 0) return set_error(LN3_EUNSUPPORTED, "fmha: the two-warpgroup kernel has no causal mask");
   if (kernel3 >= 0) {
     if (a->k2 != nullptr || a->v2 != nullptr) {
       if (!a->k2 || !a->v2 || a->Lkv2 <= 0) return set_error(LN3_EINVAL, "fmha: k2/v2/Lkv2 must be given together");

@@ -107,6 +107,9 @@ for (int c = 0; c < BN; c += CW) {
     } else if (p.act == LN3_ACT_SILU) {
 #pragma unroll
       for (int i = 0; i < CW; ++i) f[i] = silu(f[i]);
+    } else if (p.act == LN3_ACT_QUICK_GELU) {
+#pragma unroll
+      for (int i = 0; i < CW; ++i) f[i] = quick_gelu(f[i]);
     }
   }
   const bool staged = (p.out_kind == LN3_OUT_RESID_F32) ? (p.epi_mode & 2) != 0 : (p.epi_mode & 1) != 0;
@@ -457,6 +460,9 @@ __device__ __forceinline__ void epilogue_cols(const GemmParams& p, uint32_t t_ro
     } else if constexpr (ACT == LN3_ACT_SILU) {
 #pragma unroll
       for (int i = 0; i < CW; ++i) f[i] = silu(f[i]);
+    } else if constexpr (ACT == LN3_ACT_QUICK_GELU) {
+#pragma unroll
+      for (int i = 0; i < CW; ++i) f[i] = quick_gelu(f[i]);
     }
     if (row_ok) {
       if constexpr (OUT == LN3_OUT_BF16) {
@@ -924,6 +930,7 @@ int gemm_bf16(const ln3_gemm_args* a, cudaStream_t stream) {
       case LN3_ACT_GELU_ERF: return launch_gemm2<LN3_ACT_GELU_ERF, LN3_OUT_BF16, false>(ta, tb, p, sms, a->workspace, a->workspace_bytes, stream);
       case LN3_ACT_GELU_TANH: return launch_gemm2<LN3_ACT_GELU_TANH, LN3_OUT_BF16, false>(ta, tb, p, sms, a->workspace, a->workspace_bytes, stream);
       case LN3_ACT_SILU: return launch_gemm2<LN3_ACT_SILU, LN3_OUT_BF16, false>(ta, tb, p, sms, a->workspace, a->workspace_bytes, stream);
+      case LN3_ACT_QUICK_GELU: return launch_gemm2<LN3_ACT_QUICK_GELU, LN3_OUT_BF16, false>(ta, tb, p, sms, a->workspace, a->workspace_bytes, stream);
       default: return set_error(LN3_EINVAL, "gemm: unknown activation %d", a->act);
     }
   }

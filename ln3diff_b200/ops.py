@@ -12,10 +12,10 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import (ACT_GELU_ERF, ACT_GELU_TANH, ACT_NONE, ACT_SILU, OUT_BF16, OUT_F32,
+from ._lib import (ACT_GELU_ERF, ACT_GELU_TANH, ACT_NONE, ACT_QUICK_GELU, ACT_SILU, OUT_BF16, OUT_F32,
                    OUT_RESID_F32)
 
-__all__ = ["gemm", "ACT_NONE", "ACT_GELU_ERF", "ACT_GELU_TANH", "ACT_SILU", "OUT_BF16", "OUT_F32",
+__all__ = ["gemm", "ACT_NONE", "ACT_GELU_ERF", "ACT_GELU_TANH", "ACT_SILU", "ACT_QUICK_GELU", "OUT_BF16", "OUT_F32",
            "OUT_RESID_F32"]
 
 
@@ -103,9 +103,10 @@ def _gemm_workspace(device: torch.device) -> torch.Tensor:
 
 def fmha(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, *,
          out: torch.Tensor | None = None, scale: float | None = None,
-         k2: torch.Tensor | None = None, v2: torch.Tensor | None = None) -> torch.Tensor:
+         k2: torch.Tensor | None = None, v2: torch.Tensor | None = None, causal: bool = False) -> torch.Tensor:
     """softmax(q k^T * scale) v per head.  q (B,Lq,H*64), k/v (B,Lkv,H*64) bf16 views with unit
-    inner stride (slices of a packed qkv buffer are fine); returns (B,Lq,H*64) bf16."""
+    inner stride (slices of a packed qkv buffer are fine); returns (B,Lq,H*64) bf16.
+    causal=True: key j is visible to query i only when j <= i (CLIP text tower)."""
     for name, t in (("q", q), ("k", k), ("v", v)):
         _cuda(t, name, torch.bfloat16)
         _req(t.dim() == 3 and t.stride(2) == 1, f"{name} must be (B,L,H*64) with unit inner stride")
@@ -125,6 +126,8 @@ def fmha(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, *,
     a.v_ld, a.v_bs = v.stride(1), v.stride(0)
     a.o_ld, a.o_bs = out.stride(1), out.stride(0)
     a.scale = float(scale if scale is not None else 64 ** -0.5)
+    a.causal = 1 if causal else 0
+    _req(not (causal and k2 is not None), "causal attention takes a single K/V source")
     if k2 is not None:
         for name, t in (("k2", k2), ("v2", v2)):
             _cuda(t, name, torch.bfloat16)

@@ -273,3 +273,34 @@ def test_sample_ode_default_runs_dopri5_on_cpu_model():
     traj = fn(x0, lambda x, t, **kw: -x * t[:, None])
     assert traj.shape == (50, 2, 3)
     assert torch.allclose(traj[-1], x0 * torch.exp(torch.tensor(-0.5)), atol=2e-3)
+
+
+def test_general_conditioner_routing_cpu():
+    """GeneralConditioner host logic (reference sgm/modules/encoders/modules.py:80-190) with stand-in embedders."""
+    import torch
+    from ln3diff_b200.sgm.modules.encoders.modules import AbstractEmbModel, GeneralConditioner
+
+    class Tok(AbstractEmbModel):
+        def __init__(self, d, pooled):
+            super().__init__()
+            self.d, self.pooled = d, pooled
+
+        def forward(self, x):
+            t = x[:, None, None].expand(-1, 5, self.d).float() + 1
+            return (t, t[:, 0]) if self.pooled else t
+
+    a, b = Tok(4, True), Tok(6, False)
+    a._emb_config = {"input_key": "caption", "ucg_rate": 0.1}
+    b._emb_config = {"input_key": "img", "ucg_rate": 0.0}
+    cond = GeneralConditioner([a, b])
+    batch = {"caption": torch.arange(3), "img": torch.arange(3) * 10}
+    c, uc = cond.get_unconditional_conditioning(batch, force_uc_zero_embeddings=["caption"])
+    assert c["crossattn"].shape == (3, 5, 10) and c["vector"].shape == (3, 4)      # crossattn concatenated on dim 2
+    assert torch.equal(c["crossattn"][..., :4], batch["caption"][:, None, None].expand(-1, 5, 4).float() + 1)
+    assert float(uc["crossattn"][..., :4].abs().max()) == 0 and torch.equal(uc["crossattn"][..., 4:], c["crossattn"][..., 4:])
+    assert float(uc["vector"].abs().max()) == 0 and a.ucg_rate == 0.1
+    import pytest
+    with pytest.raises(KeyError):
+        bad = Tok(4, False)
+        bad._emb_config = {}
+        GeneralConditioner([bad])
