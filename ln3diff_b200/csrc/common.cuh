@@ -416,6 +416,36 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
   const float w = (q * t) * (e * x);                            // x * 0.5 erfc(z), sign of x
   return fmaxf(x, 0.f) - fabsf(w);
 }
+// erf-GELU for the fc1 epilogue of the CTA-pair GEMM, two elements at a time on the packed fp32x2 FMA pipe and
+// WITHOUT the XU:  GELU(x) = x * Phi(x),  Phi(x) = sat(0.5 + x * Q(min(x^2, 16))),  Q an even polynomial of degree
+// 8 in u = x^2 fitted (x^2-weighted Chebyshev least squares on |x| <= 4) to (Phi(x) - 0.5) / x.  fma.sat clamps
+// Phi to [0, 1], which is also the right limit for |x| > 4 (x Q(16) = +-0.49997 |x| / 4).  7 issue slots per
+// element (FMUL2 + 8 FFMA2 + FMUL2 per pair, FMNMX + FFMA.SAT per element) against 12 FMA-pipe + 2 MUFU for
+// gelu_erf_fast -- the sampler is power-capped (profiles/r2_power_ops.json), so instructions are time.
+// Error (fp32 evaluation, |x| <= 8): |abs| <= 9e-6 for |x| < 4, relative <= 5e-4 where |GELU| > 0.01, and GELU is
+// flushed to 0 below x = -4 (true value > -1.3e-4): all below the bf16 rounding of the stored result (2^-9).
+__device__ __forceinline__ void gelu_erf_poly2(float& a, float& b) {
+  const uint64_t x = pk2(a, b);
+  uint64_t u = fma2(x, x, pk2(0.f, 0.f));
+  float u0, u1;
+  upk2(u, u0, u1);
+  u = pk2(fminf(u0, 16.f), fminf(u1, 16.f));
+  uint64_t q = pk2(6.4972029061e-11f, 6.4972029061e-11f);
+  q = fma2(q, u, pk2(-5.8924924216e-09f, -5.8924924216e-09f));
+  q = fma2(q, u, pk2(2.3887849765e-07f, 2.3887849765e-07f));
+  q = fma2(q, u, pk2(-5.7769494275e-06f, -5.7769494275e-06f));
+  q = fma2(q, u, pk2(9.4159107405e-05f, 9.4159107405e-05f));
+  q = fma2(q, u, pk2(-1.1085928497e-03f, -1.1085928497e-03f));
+  q = fma2(q, u, pk2(9.8028649727e-03f, 9.8028649727e-03f));
+  q = fma2(q, u, pk2(-6.6304471162e-02f, -6.6304471162e-02f));
+  q = fma2(q, u, pk2(3.9887112041e-01f, 3.9887112041e-01f));
+  float q0, q1, p0, p1;
+  upk2(q, q0, q1);
+  asm("fma.rn.sat.f32 %0, %1, %2, 0f3F000000;" : "=f"(p0) : "f"(a), "f"(q0));
+  asm("fma.rn.sat.f32 %0, %1, %2, 0f3F000000;" : "=f"(p1) : "f"(b), "f"(q1));
+  a *= p0;
+  b *= p1;
+}
 __device__ __forceinline__ float gelu_tanh(float x) {
   const float k0 = 0.7978845608028654f, k1 = 0.044715f;
   return 0.5f * x * (1.0f + tanhf(k0 * (x + k1 * x * x * x)));

@@ -384,6 +384,9 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
 // lanes x columns [c_begin, c_end) of one accumulator tile.  The tcgen05.ld of chunk c+1 is in flight
 // while chunk c is converted and stored; activation / output kind are template parameters (the
 // runtime switch compiled to an indirect branch + constant loads that stalled the warp ~15 %).
+// internal activation id (not in the ABI): erf-GELU by the packed polynomial of common.cuh
+static constexpr int kActGeluErfPoly = 100;
+
 template <int ACT, int OUT, bool HN>
 __device__ __forceinline__ void epilogue_cols(const GemmParams& p, uint32_t t_row, int m, int n_tile0,
                                               int c_begin, int c_end, const float* bias_s,
@@ -454,6 +457,9 @@ __device__ __forceinline__ void epilogue_cols(const GemmParams& p, uint32_t t_ro
     if constexpr (ACT == LN3_ACT_GELU_ERF) {
 #pragma unroll
       for (int i = 0; i < CW; ++i) f[i] = gelu_erf_fast(f[i]);
+    } else if constexpr (ACT == kActGeluErfPoly) {
+#pragma unroll
+      for (int i = 0; i < CW; i += 2) gelu_erf_poly2(f[i], f[i + 1]);
     } else if constexpr (ACT == LN3_ACT_GELU_TANH) {
 #pragma unroll
       for (int i = 0; i < CW; ++i) f[i] = gelu_tanh(f[i]);
@@ -927,7 +933,12 @@ int gemm_bf16(const ln3_gemm_args* a, cudaStream_t stream) {
     }
     switch (a->act) {
       case LN3_ACT_NONE: return launch_gemm2<LN3_ACT_NONE, LN3_OUT_BF16, false>(ta, tb, p, sms, a->workspace, a->workspace_bytes, stream);
-      case LN3_ACT_GELU_ERF: return launch_gemm2<LN3_ACT_GELU_ERF, LN3_OUT_BF16, false>(ta, tb, p, sms, a->workspace, a->workspace_bytes, stream);
+      case LN3_ACT_GELU_ERF: {
+        // LN3_GELU_EXACT=1: the A&S 7.1.26 form (|error| <= 1.5e-7, 2 MUFU per element) instead of the packed polynomial
+        static const bool exact = getenv("LN3_GELU_EXACT") && atoi(getenv("LN3_GELU_EXACT")) != 0;
+        if (exact) return launch_gemm2<LN3_ACT_GELU_ERF, LN3_OUT_BF16, false>(ta, tb, p, sms, a->workspace, a->workspace_bytes, stream);
+        return launch_gemm2<kActGeluErfPoly, LN3_OUT_BF16, false>(ta, tb, p, sms, a->workspace, a->workspace_bytes, stream);
+      }
       case LN3_ACT_GELU_TANH: return launch_gemm2<LN3_ACT_GELU_TANH, LN3_OUT_BF16, false>(ta, tb, p, sms, a->workspace, a->workspace_bytes, stream);
       case LN3_ACT_SILU: return launch_gemm2<LN3_ACT_SILU, LN3_OUT_BF16, false>(ta, tb, p, sms, a->workspace, a->workspace_bytes, stream);
       case LN3_ACT_QUICK_GELU: return launch_gemm2<LN3_ACT_QUICK_GELU, LN3_OUT_BF16, false>(ta, tb, p, sms, a->workspace, a->workspace_bytes, stream);
