@@ -560,6 +560,60 @@ def run_ours(args):
         except Exception as e:  # noqa
             grid = {"error": repr(e)}
 
+        # ---- mesh export tail: device marching cubes on a 192^3 density lattice
+        mc = None
+        try:
+            gx = torch.linspace(-1, 1, 192, device=dev)
+            dens = 10.0 * (0.7 - torch.sqrt(gx[:, None, None] ** 2 + gx[None, :, None] ** 2 + gx[None, None, :] ** 2)).contiguous()
+            for _ in range(2):
+                mv, mf = ops.marching_cubes(dens, 0.0)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                mv, mf = ops.marching_cubes(dens, 0.0)
+            e1.record()
+            torch.cuda.synchronize()
+            mms = e0.elapsed_time(e1) / 5
+            mc = {"value": 192 ** 3 / (mms / 1e3) / 1e6, "unit": "Mcells/s", "ms_per_192cubed_grid": mms,
+                  "vertices": int(mv.shape[0]), "faces": int(mf.shape[0]),
+                  "what": "ln3_marching_cubes_count + _emit incl. the size read-back (mcubes.marching_cubes replacement)"}
+        except Exception as e:  # noqa
+            mc = {"error": repr(e)}
+
+        # ---- conditioner towers: CLIP-L text (T23D), OpenCLIP ViT-L/14 + DINOv2 ViT-L/14-reg (I23D), random init
+        cond = None
+        try:
+            from ln3diff_b200.sgm.modules.encoders.modules import (FrozenCLIPEmbedder, FrozenDinov2ImageEmbedder,
+                                                                   FrozenOpenCLIPImageEmbedder)
+
+            def _time(fn, n=5):
+                for _ in range(2):
+                    fn()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(n):
+                    fn()
+                e1.record()
+                torch.cuda.synchronize()
+                return e0.elapsed_time(e1) / n
+            ids = torch.randint(3, 49000, (8, 77), generator=torch.Generator().manual_seed(9))
+            ids[:, 30:] = 49407
+            te = FrozenCLIPEmbedder(device=dev, always_return_pooled=True)
+            t_ms = _time(lambda: te(ids))
+            del te
+            img8 = torch.rand(8, 3, 224, 224, generator=torch.Generator().manual_seed(10)).to(dev) * 2 - 1
+            ce = FrozenOpenCLIPImageEmbedder(device=dev, output_tokens=True)
+            de = FrozenDinov2ImageEmbedder(device=dev)
+            i_ms = _time(lambda: (ce(img8), de(img8)))
+            del ce, de
+            cond = {"clip_text_prompts_per_s": 8 / t_ms * 1e3, "i23d_images_per_s": 8 / i_ms * 1e3,
+                    "ms_per_8_prompts": t_ms, "ms_per_8_images_clip_plus_dino": i_ms,
+                    "what": "frozen conditioner towers on the tcgen05 GEMM / FMHA kernels, 8 prompts or images per call"}
+        except Exception as e:  # noqa
+            cond = {"error": repr(e)}
+
         cpu = None
         if n_gpus == 1:
             try:
@@ -584,7 +638,8 @@ def run_ours(args):
                 "gpu_reference": gpu_ref,
                 "vs_gpu_reference": (value / gpu_ref["value"]) if gpu_ref and "value" in gpu_ref else None,
                 "config5_sharded_generation": c5,
-                "rendered_views": views, "vae_decode": vae, "i23d_flow": i23d, "point_queries": grid, "cpu_baseline": cpu}
+                "rendered_views": views, "vae_decode": vae, "i23d_flow": i23d, "point_queries": grid, "marching_cubes": mc, "conditioners": cond,
+                "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -372,6 +372,18 @@ __device__ __forceinline__ void ldg256_na(const void* p, float* v) {
                : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
                : "l"(p));
 }
+// L2 evict_last forms: the fp32 residual stream (50 MB at DiT-L/2 B'=16) is read and re-written by three passes per
+// block with 25-100 MB GEMM streams in between; marking its lines evict_last keeps them in the 126 MB L2.
+__device__ __forceinline__ void ldg256_na_el(const void* p, float* v) {
+  asm volatile("ld.global.L1::no_allocate.L2::evict_last.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void stg256_f32_el(void* p, const float* v) {
+  asm volatile("st.global.L2::evict_last.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]),
+               "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+               : "memory");
+}
 __device__ __forceinline__ void stg256_f32(void* p, const float* v) {
   asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]),
                "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])

@@ -157,6 +157,9 @@ __device__ __forceinline__ bool nm_needs_own_row(const ln3_norm_modulate_args& a
   return a.resid != nullptr && (!nm_outside(a, row) || a.resid_out_gate != nullptr);
 }
 
+// LN3_RESID_L2=1: residual-stream accesses carry the L2 evict_last priority (set once per process)
+__constant__ int c_nm_l2_hint;
+
 template <int NV8>
 __device__ __forceinline__ void nm_row_body(const ln3_norm_modulate_args& a, int row, int lane, float (&v)[NV8][8],
                                             const uint4 (&rown)[NV8]) {
@@ -206,7 +209,8 @@ __device__ __forceinline__ void nm_row_body(const ln3_norm_modulate_args& a, int
         if (g_b != nullptr) ld8(g_b + c, gb);
         axpy8(v[i], gb, *reinterpret_cast<const uint4*>(rb + c));
       }
-      stg256_f32(x + c, v[i]);
+      if (c_nm_l2_hint) stg256_f32_el(x + c, v[i]);
+      else stg256_f32(x + c, v[i]);
     }
     if (a.out == nullptr) return;
   }
@@ -289,7 +293,13 @@ __device__ __forceinline__ void nm_load_row(const ln3_norm_modulate_args& a, int
                                             uint4 (&rown)[NV8]) {
   const float* x = a.x + static_cast<long long>(row) * a.ldx;
 #pragma unroll
-  for (int i = 0; i < NV8; ++i) ldg256_na(x + (i * 32 + lane) * 8, v[i]);
+  if (c_nm_l2_hint) {
+#pragma unroll
+    for (int i = 0; i < NV8; ++i) ldg256_na_el(x + (i * 32 + lane) * 8, v[i]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < NV8; ++i) ldg256_na(x + (i * 32 + lane) * 8, v[i]);
+  }
   if (nm_needs_own_row(a, row)) {
     const __nv_bfloat16* rr = reinterpret_cast<const __nv_bfloat16*>(a.resid) + static_cast<long long>(row) * a.resid_ld;
 #pragma unroll
@@ -463,6 +473,15 @@ int norm_modulate(const ln3_norm_modulate_args* a, cudaStream_t stream) {
   // than the warp-per-row kernel (48 vs 36 us for LN + residual at DiT-L/2 B'=16): with the ring taking 196 KB the
   // CTA has 8 consumer warps and 28 KB of L1, and the per-row arithmetic (two reductions, the modulation-vector
   // loads) then bounds the pass, not the loads.
+  {  // LN3_RESID_L2=1: evict_last hints on the residual stream (uploaded once per device)
+    static DeviceOnce l2_once;
+    if (int rc = l2_once.run([] {
+          const int v = (getenv("LN3_RESID_L2") && atoi(getenv("LN3_RESID_L2")) != 0) ? 1 : 0;
+          cudaError_t e = cudaMemcpyToSymbol(c_nm_l2_hint, &v, sizeof(v));
+          return e == cudaSuccess ? LN3_OK : set_error(LN3_ECUDA, "norm_modulate: constant upload: %s", cudaGetErrorString(e));
+        }))
+      return rc;
+  }
   static const bool staged_enabled = getenv("LN3_NORM_STAGED") && atoi(getenv("LN3_NORM_STAGED")) != 0;
   if (wide && staged_enabled && a->D <= 1024 && a->rows >= 2048 && (a->ldx * 4) % 16 == 0 &&
       (a->resid == nullptr || (a->resid_ld * 2) % 16 == 0)) {
