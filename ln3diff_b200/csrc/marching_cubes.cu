@@ -34,10 +34,27 @@ __constant__ uint8_t c_edge_owner[12][4];
 
 struct McDims {
   int nx, ny, nz;
-  long long n;       // lattice points
-  long long sy, sx;  // strides of j and i (sz = 1)
+  int n;       // lattice points (< 2^28: all index arithmetic is 32-bit)
+  int sy, sx;  // strides of j and i (sz = 1)
   float iso;
 };
+
+struct McIjk { int i, j, k; };
+// (i, j, k) of linear index p: two 32-bit divisions, once per thread; the thread's further points advance k with carry
+__device__ __forceinline__ McIjk mc_ijk(const McDims& d, int p) {
+  McIjk c;
+  const int t = p / d.nz;
+  c.k = p - t * d.nz;
+  c.i = t / d.ny;
+  c.j = t - c.i * d.ny;
+  return c;
+}
+__device__ __forceinline__ void mc_next(const McDims& d, McIjk& c) {
+  if (++c.k == d.nz) {
+    c.k = 0;
+    if (++c.j == d.ny) c.j = 0, ++c.i;
+  }
+}
 
 struct McPoint {
   uint32_t mask;  // bit a: owned edge along axis a (0 = x / i, 1 = y / j, 2 = z / k) is crossed
@@ -45,15 +62,11 @@ struct McPoint {
   float f0, f1[3];
 };
 
-__device__ __forceinline__ McPoint classify(const float* __restrict__ g, const McDims& d, long long p) {
+__device__ __forceinline__ McPoint classify(const float* __restrict__ g, const McDims& d, int p, const McIjk& c3) {
   McPoint r;
   r.mask = 0;
   r.cube = 0;
-  const int k = static_cast<int>(p % d.nz);
-  const long long t = p / d.nz;
-  const int j = static_cast<int>(t % d.ny);
-  const int i = static_cast<int>(t / d.ny);
-  const bool hx = i + 1 < d.nx, hy = j + 1 < d.ny, hz = k + 1 < d.nz;
+  const bool hx = c3.i + 1 < d.nx, hy = c3.j + 1 < d.ny, hz = c3.k + 1 < d.nz;
   r.f0 = __ldg(g + p);
   const bool in0 = r.f0 <= d.iso;
   r.f1[0] = hx ? __ldg(g + p + d.sx) : r.f0;
@@ -99,16 +112,18 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* smem8, int& tota
 
 __global__ void __launch_bounds__(kMcThreads) mc_count_kernel(const float* __restrict__ g, McDims d, int2* __restrict__ block_counts) {
   __shared__ int sm[2][kMcThreads / 32];
-  const long long base = static_cast<long long>(blockIdx.x) * kMcBlockPts + threadIdx.x * kMcPerThread;
+  const int base = blockIdx.x * kMcBlockPts + threadIdx.x * kMcPerThread;
   int nv = 0, nt = 0;
+  McIjk c3 = mc_ijk(d, base < d.n ? base : 0);
 #pragma unroll
   for (int u = 0; u < kMcPerThread; ++u) {
-    const long long p = base + u;
+    const int p = base + u;
     if (p < d.n) {
-      const McPoint r = classify(g, d, p);
+      const McPoint r = classify(g, d, p, c3);
       nv += __popc(r.mask);
       nt += c_num_tris[r.cube];
     }
+    mc_next(d, c3);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -164,29 +179,29 @@ __global__ void __launch_bounds__(kMcThreads) mc_vertices_kernel(const float* __
                                                                  uint32_t* __restrict__ vert_index, float* __restrict__ vertices,
                                                                  int max_vertices, McAffine aff) {
   __shared__ int sm[kMcThreads / 32];
-  const long long base = static_cast<long long>(blockIdx.x) * kMcBlockPts + threadIdx.x * kMcPerThread;
+  const int base = blockIdx.x * kMcBlockPts + threadIdx.x * kMcPerThread;
   McPoint r[kMcPerThread];
   int nv = 0;
+  const McIjk c0 = mc_ijk(d, base < d.n ? base : 0);
+  McIjk c3 = c0;
 #pragma unroll
   for (int u = 0; u < kMcPerThread; ++u) {
-    const long long p = base + u;
-    if (p < d.n) r[u] = classify(g, d, p);
+    const int p = base + u;
+    if (p < d.n) r[u] = classify(g, d, p, c3);
     else { r[u].mask = 0; r[u].cube = 0; }
     nv += __popc(r[u].mask);
+    mc_next(d, c3);
   }
+  c3 = c0;
   int total;
   int first = block_offsets[blockIdx.x].x + block_exclusive_scan(nv, sm, total);
 #pragma unroll
-  for (int u = 0; u < kMcPerThread; ++u) {
-    const long long p = base + u;
+  for (int u = 0; u < kMcPerThread; ++u, mc_next(d, c3)) {
+    const int p = base + u;
     if (p >= d.n) break;
     vert_index[p] = (static_cast<uint32_t>(first) << 3) | r[u].mask;
     if (r[u].mask) {
-      const int k = static_cast<int>(p % d.nz);
-      const long long t = p / d.nz;
-      const int j = static_cast<int>(t % d.ny);
-      const int i = static_cast<int>(t / d.ny);
-      const float c[3] = {static_cast<float>(i), static_cast<float>(j), static_cast<float>(k)};
+      const float c[3] = {static_cast<float>(c3.i), static_cast<float>(c3.j), static_cast<float>(c3.k)};
 #pragma unroll
       for (int a = 0; a < 3; ++a) {
         if (r[u].mask >> a & 1) {
@@ -207,14 +222,16 @@ __global__ void __launch_bounds__(kMcThreads) mc_faces_kernel(const float* __res
                                                               const uint32_t* __restrict__ vert_index, int* __restrict__ faces,
                                                               int max_faces) {
   __shared__ int sm[kMcThreads / 32];
-  const long long base = static_cast<long long>(blockIdx.x) * kMcBlockPts + threadIdx.x * kMcPerThread;
+  const int base = blockIdx.x * kMcBlockPts + threadIdx.x * kMcPerThread;
   uint32_t cube[kMcPerThread];
   int nt = 0;
+  McIjk c3 = mc_ijk(d, base < d.n ? base : 0);
 #pragma unroll
   for (int u = 0; u < kMcPerThread; ++u) {
-    const long long p = base + u;
-    cube[u] = p < d.n ? classify(g, d, p).cube : 0u;
+    const int p = base + u;
+    cube[u] = p < d.n ? classify(g, d, p, c3).cube : 0u;
     nt += c_num_tris[cube[u]];
+    mc_next(d, c3);
   }
   int total;
   int first = block_offsets[blockIdx.x].y + block_exclusive_scan(nt, sm, total);
@@ -223,14 +240,14 @@ __global__ void __launch_bounds__(kMcThreads) mc_faces_kernel(const float* __res
   for (int u = 0; u < kMcPerThread; ++u) {
     const int n = c_num_tris[cube[u]];
     if (n == 0) continue;
-    const long long p = base + u;
+    const int p = base + u;
     for (int r = 0; r < n; ++r, ++first) {
       if (first >= max_faces) continue;
       int idx[3];
 #pragma unroll
       for (int q = 0; q < 3; ++q) {
         const int e = c_tri_table[cube[u]][3 * r + q];
-        const long long owner = p + c_edge_owner[e][0] * d.sx + c_edge_owner[e][1] * d.sy + c_edge_owner[e][2];
+        const int owner = p + c_edge_owner[e][0] * d.sx + c_edge_owner[e][1] * d.sy + c_edge_owner[e][2];
         const uint32_t w = __ldg(vert_index + owner);
         const int axis = c_edge_owner[e][3];
         idx[q] = static_cast<int>(w >> 3) + __popc(w & 7u & ((1u << axis) - 1u));
@@ -271,10 +288,11 @@ int mc_check(const ln3_marching_cubes_args* a, McDims& d, McLayout& l) {
   if (!a->grid || !a->workspace || !a->totals) return set_error(LN3_EINVAL, "marching_cubes: null grid / workspace / totals");
   if (a->nx < 2 || a->ny < 2 || a->nz < 2) return set_error(LN3_EINVAL, "marching_cubes: every dimension must be >= 2");
   d.nx = a->nx; d.ny = a->ny; d.nz = a->nz;
-  d.n = static_cast<long long>(a->nx) * a->ny * a->nz;
-  if (d.n >= (1ll << 28)) return set_error(LN3_EUNSUPPORTED, "marching_cubes: more than 2^28 lattice points");
+  const long long n64 = static_cast<long long>(a->nx) * a->ny * a->nz;
+  if (n64 >= (1ll << 28)) return set_error(LN3_EUNSUPPORTED, "marching_cubes: more than 2^28 lattice points");
+  d.n = static_cast<int>(n64);
   d.sy = a->nz;
-  d.sx = static_cast<long long>(a->ny) * a->nz;
+  d.sx = a->ny * a->nz;
   d.iso = a->iso;
   l = mc_layout(d.n);
   if (a->workspace_bytes < l.total) return set_error(LN3_EINVAL, "marching_cubes: workspace too small (%zu < %zu)", a->workspace_bytes, l.total);
