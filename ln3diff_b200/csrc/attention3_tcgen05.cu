@@ -105,8 +105,8 @@ fmha3_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   uint64_t* v_full = k_empty + kStages;
   uint64_t* v_empty = v_full + kStages;
   uint64_t* s_full = v_empty + kStages;        // [kNT]
-  uint64_t* s_empty = s_full + kNT;            // [kNT] 128 arrivals: S_t is in registers
-  uint64_t* p_full = s_empty + kNT;            // [kNT] 128 arrivals
+  uint64_t* s_empty = s_full + kNT;            // [kNT] 4 arrivals (one per warp): S_t is in registers
+  uint64_t* p_full = s_empty + kNT;            // [kNT] 4 arrivals
   uint64_t* o_full = p_full + kNT;             // [kNT]
   // [kNT][2] 4 arrivals (one per warp): exponential phase n of warpgroup t finished -> exp_done[2 t + (n & 1)].
   // Two barriers per warpgroup because a warpgroup may finish its NEXT phase before its successor in the rota has
@@ -164,8 +164,8 @@ fmha3_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     }
     for (int i = 0; i < kNT; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&s_empty[i], kQT);
-      mbar_init(&p_full[i], kQT);
+      mbar_init(&s_empty[i], 4);   // one arrival per softmax warp (elected lane after __syncwarp)
+      mbar_init(&p_full[i], 4);
       mbar_init(&o_full[i], 1);
       mbar_init(&exp_done[2 * i], 4);
       mbar_init(&exp_done[2 * i + 1], 4);
@@ -364,7 +364,10 @@ fmha3_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         tmem_ld_wait();
         if (row == 0) LN3_TR3(t, g, 2);  // S in registers
         tc_fence_before();
-        mbar_arrive(&s_empty[t]);  // the tensor core may overwrite S_t with the next block now
+        // one arrival per warp: 128 per-thread arrivals are 128 serialised barrier updates on the MIO queue the
+        // exponentials of the other warpgroups are competing for
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(&s_empty[t]);  // the tensor core may overwrite S_t with the next block now
         if (kv_valid < kKB) {
 #pragma unroll
           for (int i = 0; i < kKB; ++i)
@@ -454,7 +457,8 @@ fmha3_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         }
         fence_proxy_async_smem();  // P (generic-proxy stores) -> visible to the tensor core
         tc_fence_before();
-        mbar_arrive(&p_full[t]);
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(&p_full[t]);
         if (row == 0) LN3_TR3(t, g, 7);  // P handed to the tensor core
       }
       if (row == 0) LN3_TR3(t, g - 1, 8);   // epilogue: start waiting for the last P V

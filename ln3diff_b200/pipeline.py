@@ -144,6 +144,37 @@ def generate_t23d(model, decoder, randn, c, uc, cameras, num_steps: int = 250, s
     return latents, decode_and_render(decoder, latents, cameras, resolution)
 
 
+@torch.no_grad()
+def condition_prompt(conditioner, cond_key: str, prompt, num_samples: int, device=None, dtype=torch.float32):
+    """The conditioner call of DiffusionEngineLSGM.eval_cldm (nsr/lsgm/sgm_DiffusionEngine.py:443-477): ONE prompt
+    (a caption string / token-id row for T23D, an image (1,3,H,W) for I23D) -> (c, uc) with the unconditional half
+    forced to zero embeddings, every tensor repeated to `num_samples` rows (`repeat_interleave`, :473-477)."""
+    ucg_keys = [cond_key]
+    batch_c = {cond_key: prompt}
+    c, uc = conditioner.get_unconditional_conditioning(
+        batch_c, force_uc_zero_embeddings=ucg_keys if len(conditioner.embedders) > 0 else [])
+    for k in c:
+        if isinstance(c[k], torch.Tensor):
+            assert c[k].shape[0] == 1, "eval_cldm conditions on one prompt at a time"
+            c[k], uc[k] = (y[k].repeat_interleave(num_samples, 0).to(dtype) for y in (c, uc))
+            if device is not None:
+                c[k], uc[k] = c[k].to(device), uc[k].to(device)
+    return c, uc
+
+
+@torch.no_grad()
+def text_to_3d(conditioner, model, decoder, prompt, cameras, num_samples: int = 1, num_steps: int = 250,
+               scale: float = 6.5, resolution: int = 128, seed: int = 41):
+    """eval_cldm for one caption end to end (:410-523): conditioner -> `th.manual_seed(41)` CPU noise draw (:457-466,
+    395-398) -> Euler-EDM + CFG sampling -> decode -> render.  Returns (latents, render dict)."""
+    dev = next(model.parameters()).device
+    c, uc = condition_prompt(conditioner, "caption", prompt, num_samples, device=dev)
+    g = torch.Generator().manual_seed(seed)
+    C = model.in_channels if not model.roll_out else 3 * model.in_channels
+    randn = torch.randn(num_samples, C, 32, 32, generator=g).to(dev)
+    return generate_t23d(model, decoder, randn, c, uc, cameras, num_steps, scale, resolution)
+
+
 # ---------------------------------------------------------------------------------------------- multi-GPU
 def shard_range(n_total: int, world: int, rank: int) -> tuple[int, int, int]:
     """Contiguous block of ceil(P/G) prompts per rank: returns (lo, hi, per) with
