@@ -97,3 +97,22 @@ def test_extract_mesh_through_the_decoder_mirror(dev, tmp_path):
     assert np.array_equal(m["vertex_colors"], (rgb.clamp(0, 1) * 255).to(torch.uint8).cpu().numpy())
     p = pmesh.export_obj(str(tmp_path / "m.obj"), m["vertices"], m["faces"], m["vertex_colors"])
     assert sum(1 for ln in open(p) if ln.startswith("f ")) == m["faces"].shape[0]
+
+
+def test_patch_embed_triplane_unit(dev):
+    """V1 PatchEmbedTriplane (reference vit/vit_triplane.py:58-108) on its own: grouped 2x2 stride-2 conv + the
+    `(b, E, 3, h, w) -> (b, 3 h w, E)` channel-interleave, against the oracle's F.conv2d(groups=3) restatement."""
+    from ln3diff_b200 import ops
+    from oracle import decoder as odec
+    g = torch.Generator().manual_seed(11)
+    for (B, Cz, S, E) in [(2, 4, 32, 384), (1, 4, 32, 1024), (3, 4, 16, 128)]:
+        lat = torch.randn(B, 3 * Cz, S, S, generator=g)
+        w = torch.randn(3 * E, Cz, 2, 2, generator=g) * 0.2
+        b = torch.randn(3 * E, generator=g) * 0.1
+        sd = {"superresolution.ldm_upsample.proj.weight": w, "superresolution.ldm_upsample.proj.bias": b}
+        ref = odec.patch_embed_triplane(sd, lat * 0.5)
+        tok, sb = ops.patch_embed_triplane(lat.to(dev).contiguous(), w.to(dev).contiguous(), b.to(dev), in_mul=0.5)
+        assert tok.shape == ref.shape == (B, 3 * (S // 2) ** 2, E)
+        assert float((tok.cpu() - ref).abs().max()) < 1e-5
+        silu = torch.nn.functional.silu(ref)
+        assert float(((sb.float().cpu() - silu).norm() / silu.norm())) < 4e-3     # bf16 rounding of the GEMM operand
