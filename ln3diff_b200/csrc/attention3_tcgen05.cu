@@ -84,7 +84,7 @@ __device__ __forceinline__ float exp2_poly(float x) {
   return __uint_as_float(__float_as_uint(q) + (__float_as_uint(t) << 23));
 }
 
-template <int kPolyPer8, bool ROTA>
+template <int kPolyPer8, bool ROTA, bool CHAIN = false>
 __global__ void __launch_bounds__(kThreads, 1)
 fmha3_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                  const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_k2,
@@ -436,8 +436,43 @@ fmha3_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                          : "memory");
           }
         };
-        if (kv_valid >= kKB) exp_store(std::true_type{});
-        else exp_store(std::false_type{});
+        // CHAIN: full blocks run a software pipeline with an artificial dependency chain instead.  ptxas schedules the
+        // straight-line loop above as runs of up to 17 back-to-back MUFUs; an in-order warp then sits on the XU pipe's
+        // 8-cycle issue interval with nothing else to issue, and the FMA-pipe work of the same elements is issued later
+        // with the XU idle (MUFU time and issue time add up instead of overlapping).  Here MUFU(i+1) reads
+        // x(i+1) = s(i+1) * scale + t(i) with t(i) = rs(i) * 0 + (-m), and rs(i) has just added e(i - LAG): the order
+        // MUFU, FADD, FFMA, FFMA, [F2FP, STS] per element is forced by data dependencies (one extra FFMA per element;
+        // tools/microbench/exploop.cu).  e(i) overwrites s(i) in place.
+        auto exp_store_chain = [&]() {
+          constexpr int LAG = 4;
+          const float nm = -m_ref;
+          float tt = nm;
+#pragma unroll
+          for (int i = 0; i < kKB + LAG; ++i) {
+            if (i < kKB) s[i] = __float_as_uint(fast_exp2(fmaf(__uint_as_float(s[i]), p.scale_log2, tt)));
+            if (i >= LAG) {
+              const int jj = i - LAG;
+              rs += __uint_as_float(s[jj]);
+              tt = fmaf(rs, 0.0f, nm);
+              if ((jj & 7) == 7) {
+                const int c = jj - 7;
+                const uint32_t addr = p_row + (c >> 6) * kQBytes + ((((c & 63) >> 3) ^ swz) << 4);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr),
+                             "r"(pack_bf16x2(__uint_as_float(s[c]), __uint_as_float(s[c + 1]))),
+                             "r"(pack_bf16x2(__uint_as_float(s[c + 2]), __uint_as_float(s[c + 3]))),
+                             "r"(pack_bf16x2(__uint_as_float(s[c + 4]), __uint_as_float(s[c + 5]))),
+                             "r"(pack_bf16x2(__uint_as_float(s[c + 6]), __uint_as_float(s[c + 7])))
+                             : "memory");
+              }
+            }
+          }
+        };
+        if (kv_valid >= kKB) {
+          if constexpr (CHAIN) exp_store_chain();
+          else exp_store(std::true_type{});
+        } else {
+          exp_store(std::false_type{});
+        }
         rota_done();
         if (row == 0) LN3_TR3(t, g, 6);  // exponentials done
         l_run += rs;
@@ -505,7 +540,7 @@ fmha3_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 }  // namespace fmha3
 
 // Launcher; arguments were validated by fmha_fwd (attention_tcgen05.cu).  variant: bit 0 = rota off,
-// bits 1.. = exponentials per 8 on the FMA pipe (0 or 2).
+// bit 1 = 2 of 8 exponentials on the FMA pipe, bit 2 = dependency-chained exponential loop (no polynomial).
 int fmha3_launch(const ln3_fmha_args* a, int variant, cudaStream_t stream) {
   using namespace fmha3;
   static DeviceOnce once;   // the shared-memory opt-in is per device
@@ -516,6 +551,7 @@ int fmha3_launch(const ln3_fmha_args* a, int variant, cudaStream_t stream) {
         };
         set(fmha3_fwd_kernel<0, true>); set(fmha3_fwd_kernel<0, false>);
         set(fmha3_fwd_kernel<2, true>); set(fmha3_fwd_kernel<2, false>);
+        set(fmha3_fwd_kernel<0, true, true>); set(fmha3_fwd_kernel<0, false, true>);
         return e == cudaSuccess ? LN3_OK : set_error(LN3_ECUDA, "fmha3: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       }))
     return rc;
@@ -562,10 +598,10 @@ int fmha3_launch(const ln3_fmha_args* a, int variant, cudaStream_t stream) {
   }
   cudaError_t le = cudaSuccess;
   switch (variant) {
-    case 0: le = launch_pdl(fmha3_fwd_kernel<0, true>, dim3(grid), dim3(kThreads), kSmem, stream, tq, tk, tv, tk2, tv2, to, p); break;
-    case 1: le = launch_pdl(fmha3_fwd_kernel<0, false>, dim3(grid), dim3(kThreads), kSmem, stream, tq, tk, tv, tk2, tv2, to, p); break;
-    case 2: le = launch_pdl(fmha3_fwd_kernel<2, true>, dim3(grid), dim3(kThreads), kSmem, stream, tq, tk, tv, tk2, tv2, to, p); break;
-    case 3: le = launch_pdl(fmha3_fwd_kernel<2, false>, dim3(grid), dim3(kThreads), kSmem, stream, tq, tk, tv, tk2, tv2, to, p); break;
+#define LN3_F3(V, P, R, C) case V: le = launch_pdl(fmha3_fwd_kernel<P, R, C>, dim3(grid), dim3(kThreads), kSmem, stream, tq, tk, tv, tk2, tv2, to, p); break;
+    LN3_F3(0, 0, true, false) LN3_F3(1, 0, false, false) LN3_F3(2, 2, true, false) LN3_F3(3, 2, false, false)
+    LN3_F3(4, 0, true, true) LN3_F3(5, 0, false, true)
+#undef LN3_F3
     default: return set_error(LN3_EINVAL, "fmha3: bad variant");
   }
   cudaError_t e = le != cudaSuccess ? le : cudaGetLastError();

@@ -675,6 +675,9 @@ int fmha_fwd(const ln3_fmha_args* a, cudaStream_t stream) {
     if (kv && atoi(kv) == 2) return -1;
     const char* ro = getenv("LN3_FMHA_ROTA");
     const char* po = getenv("LN3_FMHA_POLY");
+    const char* ch = getenv("LN3_FMHA_CHAIN");
+    const int chain = (ch && atoi(ch) != 0) ? 4 : 0;   // LN3_FMHA_CHAIN=1: dependency-chained exponential loop
+    if (chain) return ((ro && atoi(ro) != 0) ? 0 : 1) | chain;
     return ((ro && atoi(ro) != 0) ? 0 : 1) | ((po && atoi(po) == 2) ? 2 : 0);   // bit 0 = rota OFF (default)
   }();
   if (a->causal && (a->k2 != nullptr || a->v2 != nullptr))

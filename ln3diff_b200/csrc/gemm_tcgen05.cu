@@ -231,7 +231,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
   const int lane = threadIdx.x & 31;
 
   const int tiles_m = (p.M + BM - 1) / BM;
-  const int tiles_n = p.N / BN;
+  const int tiles_n = (p.N + BN - 1) / BN;
   const int num_tiles = tiles_m * tiles_n;
   const int num_kb = p.K / BK;
 
@@ -298,7 +298,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tm_base + acc * BN;
+        const uint32_t d_tmem = tm_base + acc * 256;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
@@ -340,7 +340,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const int m_base = tm * BM + quarter * 32;
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * 256;
       epilogue_tile<BN, HN>(p, stage, t_row, m_base, tn, lane);
       tc_fence_before();
       __syncwarp();
@@ -390,7 +390,9 @@ static constexpr int kActGeluErfPoly = 100;
 template <int ACT, int OUT, bool HN>
 __device__ __forceinline__ void epilogue_cols(const GemmParams& p, uint32_t t_row, int m, int n_tile0,
                                               int c_begin, int c_end, const float* bias_s,
-                                              const float* part_row = nullptr, int nparts = 0) {
+                                              const float* part_row = nullptr, int nparts = 0, int c_lim = 1 << 30) {
+  // c_lim (bf16 output only): tile columns >= c_lim are not stored -- the 176-wide tiles end their slices and the
+  // last tile of a row inside a 32-column chunk (multiples of 8)
   constexpr int CW = HN ? 64 : 32;
   // Plain epilogues software-pipeline the TMEM loads (chunk c+1 in flight while c is stored).  The
   // activation epilogues run with 16 warps and a 96-register budget instead: no prefetch registers,
@@ -473,7 +475,7 @@ __device__ __forceinline__ void epilogue_cols(const GemmParams& p, uint32_t t_ro
     if (row_ok) {
       if constexpr (OUT == LN3_OUT_BF16) {
         __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + m * p.ldo + n0;
-        if (p.wide_ok) {
+        if (p.wide_ok && c + CW <= c_lim) {
 #pragma unroll
           for (int i = 0; i < CW; i += 16) {
             uint32_t q[8];
@@ -484,6 +486,7 @@ __device__ __forceinline__ void epilogue_cols(const GemmParams& p, uint32_t t_ro
         } else {
 #pragma unroll
           for (int i = 0; i < CW; i += 8) {
+            if (c + i + 8 > c_lim) break;
             uint4 q;
             q.x = pack_bf16x2(f[i], f[i + 1]);
             q.y = pack_bf16x2(f[i + 2], f[i + 3]);
@@ -562,13 +565,19 @@ constexpr int gemm2_threads() { return 64 + 32 * EW; }
 template <int ACT>
 constexpr int gemm2_epi_warps() { return ACT == LN3_ACT_NONE ? 8 : 16; }
 
-template <int ACT, int OUT, bool HN>
+// BN = 256, or 176 (plain bf16 epilogue only): with T tiles on P pairs the cost is ceil(T / P) * BN, and for the
+// N = 1024 GEMMs of the DiT 6 column tiles of 176 (5 x 176 + 144) beat 4 of 256 -- 288 tiles = 3.89 rounds of 0.69
+// instead of 192 tiles = 2.59 -> 3 rounds (M = 12288), 144 tiles = 1.95 -> 2 rounds of 0.69 instead of 96 = 1.3 -> 2
+// rounds (M = 6144).  The W box is BN / 2 rows per CTA; TMEM stages stay 256 columns apart; columns past N in the
+// last tile are zero-filled by TMA and never stored.
+template <int ACT, int OUT, bool HN, int BN = 256>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gemm2_threads<gemm2_epi_warps<ACT>()>(), 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const GemmParams p) {
-  constexpr int BN = 256;
+  static_assert(BN == 256 || (BN == 176 && ACT == LN3_ACT_NONE && OUT == LN3_OUT_BF16 && !HN), "176-wide tiles: plain bf16 epilogue");
   constexpr int EW = gemm2_epi_warps<ACT>();
-  constexpr int kABytes = BM * BK * 2, kBBytes = 128 * BK * 2;
+  constexpr int kABytes = BM * BK * 2, kBBytes = 128 * BK * 2;   // smem strides (the W box uses BN / 2 of its 128 rows)
+  constexpr int kStageTx = (BM * BK + (BN / 2) * BK) * 2;        // bytes one CTA's two TMA loads deliver per stage
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -607,7 +616,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc_2sm(tmem_slot, 2 * BN);
+    tmem_alloc_2sm(tmem_slot, 512);
     tmem_relinquish_2sm();
   }
   tc_fence_before();
@@ -669,11 +678,11 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         int tm, tn;
         tile_coords(it.tile, tm, tn);
         const int row_a = tm * 2 * BM + static_cast<int>(rank) * BM;
-        const int row_b = tn * BN + static_cast<int>(rank) * 128;
+        const int row_b = tn * BN + static_cast<int>(rank) * (BN / 2);
         for (int kb = it.kb0; kb < it.kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           const uint32_t full_leader = mapa_u32(&full_bar[stage], 0);
-          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * kStageBytes2);  // bytes of both CTAs
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * kStageTx);  // bytes of both CTAs
           tma_load_2d_2sm(smem_a + stage * kABytes, &tmap_a, full_leader, kb * BK, row_a);
           tma_load_2d_2sm(smem_b + stage * kBBytes, &tmap_b, full_leader, kb * BK, row_b);
           if (++stage == kStages2) {
@@ -687,7 +696,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     // Warp-uniform control flow + elect_one_sync() around the tcgen05 instructions only: with an
     // `if (lane == 0)` region ptxas wraps every UTCHMMA in an ELECT / R2UR.BROADCAST waterfall.
     if (leader) {
-      constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN, 0, 0);
+      constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN, 0, 0);   // UMMA 256 x BN x 16 over the pair
       const uint32_t tm_base = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint64_t a_desc0 = make_smem_desc_sw128(smem_u32(smem_a), 0, 1024);
       const uint64_t b_desc0 = make_smem_desc_sw128(smem_u32(smem_b), 0, 1024);
@@ -731,7 +740,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   } else {
     const int quarter = warp & 3;
     const int slice = (warp - 2) >> 2;  // which slice of the tile's columns
-    constexpr int kSliceCols = BN / (EW / 4);
+    constexpr int kSliceCols = BN / (EW / 4);   // 88 for the 176-wide tiles: the chunk loop's last 32-column load runs 8 past
     int acc = 0;
     uint32_t acc_phase = 0;
     int t_dp = pair;
@@ -742,8 +751,10 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       tile_coords(it.tile, tm, tn);
       // stage the tile's 256 bias values (one per epilogue thread) while the mainloop is still running;
       // two buffers + one barrier per tile: nobody can be two tiles ahead of the slowest warp
-      if (p.bias != nullptr && threadIdx.x < 64 + BN)
-        bias_s[acc * BN + (threadIdx.x - 64)] = __ldg(p.bias + tn * BN + (threadIdx.x - 64));
+      if (p.bias != nullptr && threadIdx.x < 64 + BN) {
+        const int bc = tn * BN + (threadIdx.x - 64);
+        bias_s[acc * 256 + (threadIdx.x - 64)] = bc < p.N ? __ldg(p.bias + bc) : 0.f;
+      }
       named_bar_sync(1, 32 * EW);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
@@ -782,8 +793,16 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           }
           __syncwarp();
         }
-        epilogue_cols<ACT, OUT, HN>(p, t_row, m, tn * BN, slice * kSliceCols, (slice + 1) * kSliceCols, bias_s + acc * BN,
-                                    my_part + 2 * 128 * 256, it.mode == 2 ? it.nparts : 0);
+        if constexpr (BN == 256) {
+          epilogue_cols<ACT, OUT, HN>(p, t_row, m, tn * BN, slice * kSliceCols, (slice + 1) * kSliceCols, bias_s + acc * 256,
+                                      my_part + 2 * 128 * 256, it.mode == 2 ? it.nparts : 0);
+        } else {
+          // 176 columns as [0, 96) | [96, 176): both slices start on a 16-column boundary (256-bit stores stay
+          // aligned); the second one ends inside its last 32-column chunk, and the last tile of a row at N
+          const int c_lo = slice * 96, c_hi = slice == 0 ? 96 : BN;
+          epilogue_cols<ACT, OUT, HN>(p, t_row, m, tn * BN, c_lo, c_hi, bias_s + acc * 256, nullptr, 0,
+                                      min(c_hi, p.N - tn * BN));
+        }
         if (it.mode == 2) {
           // second tick per warp; whoever brings a slot's counter to 2 * EW resets it for the next launch
           __syncwarp();
@@ -807,24 +826,24 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   tc_fence_before();
   cluster_sync_all();  // no CTA exits (or frees TMEM) while its peer can still signal it
   tc_fence_after();
-  if (warp == 1) tmem_dealloc_2sm(tmem_base, 2 * BN);
+  if (warp == 1) tmem_dealloc_2sm(tmem_base, 512);
 }
 
 size_t gemm_workspace_bytes() {
   return 1024 + static_cast<size_t>(device_sm_count() / 2) * 2 * 128 * 256 * sizeof(float);
 }
 
-template <int ACT, int OUT, bool HN>
+template <int ACT, int OUT, bool HN, int BN = 256>
 static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams p, int num_sms,
                         void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   static DeviceOnce once;
   if (int rc = once.run([] {
-        cudaError_t e = cudaFuncSetAttribute(gemm2_bf16_kernel<ACT, OUT, HN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(gemm2_bf16_kernel<ACT, OUT, HN, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              kSmemBytes2);
         return e == cudaSuccess ? LN3_OK : set_error(LN3_ECUDA, "gemm2: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       }))
     return rc;
-  const int tiles = ((p.M + 2 * BM - 1) / (2 * BM)) * (p.N / 256);
+  const int tiles = ((p.M + 2 * BM - 1) / (2 * BM)) * ((p.N + BN - 1) / BN);
   const int num_kb = p.K / BK;
   const int all_pairs = num_sms / 2;
   int pairs = tiles < all_pairs ? tiles : all_pairs;
@@ -838,7 +857,7 @@ static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams
   p.sk_tiles = 0;
   p.sk_flags = nullptr;
   p.sk_partials = nullptr;
-  if (!sk_off && workspace != nullptr && workspace_bytes >= gemm_workspace_bytes() &&
+  if (BN == 256 && !sk_off && workspace != nullptr && workspace_bytes >= gemm_workspace_bytes() &&
       (reinterpret_cast<uintptr_t>(workspace) & 255) == 0 && num_kb >= 4) {
     int sk = 0;
     if (tiles >= all_pairs) {
@@ -854,7 +873,7 @@ static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams
       pairs = all_pairs;
     }
   }
-  cudaError_t e = launch_pdl(gemm2_bf16_kernel<ACT, OUT, HN>, dim3(2 * pairs), dim3(gemm2_threads<gemm2_epi_warps<ACT>()>()),
+  cudaError_t e = launch_pdl(gemm2_bf16_kernel<ACT, OUT, HN, BN>, dim3(2 * pairs), dim3(gemm2_threads<gemm2_epi_warps<ACT>()>()),
                              kSmemBytes2, stream, ta, tb, p);
   if (e != cudaSuccess) return set_error(LN3_ECUDA, "gemm2 launch: %s", cudaGetErrorString(e));
   count_launch();
@@ -882,10 +901,20 @@ int gemm_bf16(const ln3_gemm_args* a, cudaStream_t stream) {
     if (!ok) use_pair = false;
   }
 
+  // 176-wide column tiles for the plain bf16 pair GEMM when they need fewer tile-rounds (cost = rounds x width)
+  bool narrow = false;
+  if (use_pair && a->out_kind == LN3_OUT_BF16 && a->act == LN3_ACT_NONE && a->head_norm_w == nullptr) {
+    static const int bn_env = getenv("LN3_GEMM_BN") ? atoi(getenv("LN3_GEMM_BN")) : 0;   // 256 / 176 force, 0 = cost model
+    const int pairs = device_sm_count() / 2;
+    const long long tm = (a->M + 2 * BM - 1) / (2 * BM);
+    const long long t256 = tm * (a->N / 256), t176 = tm * ((a->N + 175) / 176);
+    const long long c256 = ((t256 + pairs - 1) / pairs) * 256, c176 = ((t176 + pairs - 1) / pairs) * 176;
+    narrow = bn_env == 176 || (bn_env == 0 && t256 > 1 && c176 * 100 < c256 * 95);
+  }
   CUtensorMap ta, tb;
   int rc = make_tmap_2d_bf16(&ta, a->A, a->M, a->K, a->lda, BM, BK);
   if (rc) return rc;
-  rc = make_tmap_2d_bf16(&tb, a->W, a->N, a->K, a->ldw, use_pair ? 128 : bn, BK);
+  rc = make_tmap_2d_bf16(&tb, a->W, a->N, a->K, a->ldw, use_pair ? (narrow ? 88 : 128) : bn, BK);
   if (rc) return rc;
 
   GemmParams p;
@@ -931,6 +960,7 @@ int gemm_bf16(const ln3_gemm_args* a, cudaStream_t stream) {
       if (a->act != LN3_ACT_NONE) return set_error(LN3_EUNSUPPORTED, "gemm: fp32 output with activation");
       return launch_gemm2<LN3_ACT_NONE, LN3_OUT_F32, false>(ta, tb, p, sms, a->workspace, a->workspace_bytes, stream);
     }
+    if (narrow) return launch_gemm2<LN3_ACT_NONE, LN3_OUT_BF16, false, 176>(ta, tb, p, sms, a->workspace, a->workspace_bytes, stream);
     switch (a->act) {
       case LN3_ACT_NONE: return launch_gemm2<LN3_ACT_NONE, LN3_OUT_BF16, false>(ta, tb, p, sms, a->workspace, a->workspace_bytes, stream);
       case LN3_ACT_GELU_ERF: {

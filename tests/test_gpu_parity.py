@@ -41,6 +41,25 @@ def test_gemm_bf16(dev, M, N, K):
     assert _rel(out32, ref) < 1e-5                     # fp32 accumulate in TMEM
 
 
+@pytest.mark.parametrize("M,N,K", [(12288, 1024, 4096), (6144, 1024, 1024), (616, 768, 768), (2000, 1024, 64),
+                                   (12288, 1024, 1024), (300, 512, 128)])
+def test_gemm_bf16_narrow_tile_shapes(dev, M, N, K):
+    """Shapes for which the host cost model picks the 176-column tiles of the CTA-pair GEMM (6 column tiles per 1024
+    columns, the last one 144 wide; ragged M): compared element-wise -- a column-addressing slip would not show in a norm."""
+    from ln3diff_b200 import ops
+    g = torch.Generator().manual_seed(M + 3 * N + K)
+    a = (torch.randn(M, K, generator=g) * 0.5).bfloat16()
+    w = (torch.randn(N, K, generator=g) * 0.05).bfloat16()
+    b = torch.randn(N, generator=g)
+    ref = a.float() @ w.float().t() + b
+    out = ops.gemm(a.to(dev), w.to(dev), b.to(dev)).float().cpu()
+    assert _rel(out, ref) < 4e-3
+    err = (out - ref).abs() / (ref.abs() + 1.0)
+    assert float(err.max()) < 2e-2, (float(err.max()), torch.nonzero(err > 2e-2)[:5])
+    nob = ops.gemm(a.to(dev), w.to(dev)).float().cpu()           # no bias
+    assert _rel(nob, ref - b) < 4e-3
+
+
 def test_gemm_epilogues(dev):
     from ln3diff_b200 import ops
     g = torch.Generator().manual_seed(5)

@@ -37,7 +37,7 @@ x32 = torch.randn(M, D, device=dev)
 xb = x32.bfloat16()
 
 
-def gemm_case(name, N, K, act=ops.ACT_NONE):
+def gemm_case(name, N, K, act=ops.ACT_NONE, M=M):
     a = (torch.randn(M, K, device=dev) * 0.5).bfloat16()
     w = (torch.randn(N, K, device=dev) * 0.03).bfloat16()
     b = torch.randn(N, device=dev)
@@ -51,6 +51,7 @@ gemm_case("gemm_fc1_gelu_4096x1024", 4096, 1024, ops.ACT_GELU_ERF)
 gemm_case("gemm_fc1_noact_4096x1024", 4096, 1024)
 gemm_case("gemm_fc2_1024x4096", 1024, 4096)
 gemm_case("gemm_proj_1024x1024", 1024, 1024)
+gemm_case("gemm_q_cond_1024x1024_m6144", 1024, 1024, M=6144)
 
 B, H, L = 16, 16, 768
 qkv = (torch.randn(B, L, 3 * H * 64, device=dev) * 0.5).bfloat16()

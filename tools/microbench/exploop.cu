@@ -46,10 +46,10 @@ __device__ __forceinline__ void exp2_poly2(uint64_t x2, float& e0, float& e1) {
 }
 
 template <int POLY, int MODE>
-__global__ void __launch_bounds__(320, 1) k(const float* in, float* out, int iters, long long* cyc, float scale) {
+__global__ void __launch_bounds__(384, 1) k(const float* in, float* out, int iters, long long* cyc, float scale) {
   extern __shared__ uint8_t smem[];
   const int row = threadIdx.x & 127;
-  const uint32_t p_row = (uint32_t)__cvta_generic_to_shared(smem) + (threadIdx.x >> 7) * 32768 + row * 128;
+  const uint32_t p_row = (uint32_t)__cvta_generic_to_shared(smem) + ((threadIdx.x >> 7) & 1) * 32768 + row * 128;
   const int swz = row & 7;
   uint32_t s[128];
 #pragma unroll
@@ -101,6 +101,33 @@ __global__ void __launch_bounds__(320, 1) k(const float* in, float* out, int ite
       upk2(rs2, r0, r1);
       rs = r0 + r1;
     }
+    if (MODE == 2 || MODE == 3) {
+      // Software pipeline with an artificial dependency chain so that ptxas cannot batch the MUFUs of an in-order
+      // warp: MUFU(i+1) reads x(i+1) = s*scale + t(i), t(i) = rs(i)*0 + (-m) depends on the running sum after
+      // step i, which added e(i - LAG).  Issue order per step is then forced: MUFU, FADD, FFMA(t), FFMA(x), [F2FP, STS].
+      constexpr int LAG = MODE == 2 ? 4 : 6;
+      const float nm = -m_ref;
+      float e[128];
+      float t = nm;
+#pragma unroll
+      for (int i = 0; i < 128 + LAG; ++i) {
+        if (i < 128) {
+          const float x = fmaf(__uint_as_float(s[i]), scale, t);
+          e[i] = fast_exp2(x);
+        }
+        if (i >= LAG) {
+          const int j = i - LAG;
+          rs += e[j];
+          t = fmaf(rs, 0.0f, nm);
+          if ((j & 7) == 7) {
+            const int c = j - 7;
+            const uint32_t addr = p_row + (c >> 6) * 16384 + ((((c & 63) >> 3) ^ swz) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pack_bf16x2(e[c], e[c + 1])),
+                         "r"(pack_bf16x2(e[c + 2], e[c + 3])), "r"(pack_bf16x2(e[c + 4], e[c + 5])), "r"(pack_bf16x2(e[c + 6], e[c + 7])) : "memory");
+          }
+        }
+      }
+    }
     l_run += rs;
     m_ref += 1e-6f * rs;   // loop-carried dependence so iterations cannot be merged
 #pragma unroll
@@ -133,8 +160,10 @@ int main() {
   cudaMemset(in, 0, 4096 * 4);
   cudaMalloc(&out, 148 * 1024 * 4);
   cudaMalloc(&cyc, 148 * 8);
-  for (int warps : {4, 8}) {
+  for (int warps : {4, 8, 12}) {
     run<0, 0>(warps, in, out, cyc);
+    run<0, 2>(warps, in, out, cyc);
+    run<0, 3>(warps, in, out, cyc);
     run<0, 1>(warps, in, out, cyc);
     run<2, 1>(warps, in, out, cyc);
     run<4, 1>(warps, in, out, cyc);
