@@ -231,7 +231,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
   const int lane = threadIdx.x & 31;
 
   const int tiles_m = (p.M + BM - 1) / BM;
-  const int tiles_n = (p.N + BN - 1) / BN;
+  const int tiles_n = p.N / BN;
   const int num_tiles = tiles_m * tiles_n;
   const int num_kb = p.K / BK;
 
@@ -298,7 +298,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tm_base + acc * 256;
+        const uint32_t d_tmem = tm_base + acc * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
@@ -340,7 +340,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const int m_base = tm * BM + quarter * 32;
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * 256;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
       epilogue_tile<BN, HN>(p, stage, t_row, m_base, tn, lane);
       tc_fence_before();
       __syncwarp();
@@ -391,8 +391,8 @@ template <int ACT, int OUT, bool HN>
 __device__ __forceinline__ void epilogue_cols(const GemmParams& p, uint32_t t_row, int m, int n_tile0,
                                               int c_begin, int c_end, const float* bias_s,
                                               const float* part_row = nullptr, int nparts = 0, int c_lim = 1 << 30) {
-  // c_lim (bf16 output only): tile columns >= c_lim are not stored -- the 176-wide tiles end their slices and the
-  // last tile of a row inside a 32-column chunk (multiples of 8)
+  // c_lim (bf16 output only): tile columns >= c_lim are not stored -- the last 192-wide tile of a row ends at N,
+  // possibly inside a 32-column chunk (multiples of 8)
   constexpr int CW = HN ? 64 : 32;
   // Plain epilogues software-pipeline the TMEM loads (chunk c+1 in flight while c is stored).  The
   // activation epilogues run with 16 warps and a 96-register budget instead: no prefetch registers,
@@ -565,16 +565,18 @@ constexpr int gemm2_threads() { return 64 + 32 * EW; }
 template <int ACT>
 constexpr int gemm2_epi_warps() { return ACT == LN3_ACT_NONE ? 8 : 16; }
 
-// BN = 256, or 176 (plain bf16 epilogue only): with T tiles on P pairs the cost is ceil(T / P) * BN, and for the
-// N = 1024 GEMMs of the DiT 6 column tiles of 176 (5 x 176 + 144) beat 4 of 256 -- 288 tiles = 3.89 rounds of 0.69
-// instead of 192 tiles = 2.59 -> 3 rounds (M = 12288), 144 tiles = 1.95 -> 2 rounds of 0.69 instead of 96 = 1.3 -> 2
-// rounds (M = 6144).  The W box is BN / 2 rows per CTA; TMEM stages stay 256 columns apart; columns past N in the
-// last tile are zero-filled by TMA and never stored.
+// BN = 256, or 192 / 176 (plain bf16 epilogue only): with T tiles on P pairs the cost is ceil(T / P) * BN.  For the
+// N = 1024 GEMMs at M = 6144 (cond-only q / out of the DiT, proj / fc2 of the VAE decoder) 6 column tiles of 176
+// (5 x 176 + 144) give 144 tiles = 1.95 -> 2 rounds of 0.69 instead of 96 tiles = 1.3 -> 2 rounds of 1.0: 20.3 -> 17.0 us.
+// (At M = 12288 the model predicts 8 % -- 288 tiles = 3.89 rounds -- but the two extra passes over A cost more: fc2
+// 85.5 -> 96.2 us, so the host only switches for a predicted gain >= 20 %.)
+// The W box is BN / 2 rows per CTA; TMEM stages stay 256 columns apart; columns past N in the last tile of a row
+// are zero-filled by TMA and never stored.
 template <int ACT, int OUT, bool HN, int BN = 256>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gemm2_threads<gemm2_epi_warps<ACT>()>(), 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const GemmParams p) {
-  static_assert(BN == 256 || (BN == 176 && ACT == LN3_ACT_NONE && OUT == LN3_OUT_BF16 && !HN), "176-wide tiles: plain bf16 epilogue");
+  static_assert(BN == 256 || ((BN == 192 || BN == 176) && ACT == LN3_ACT_NONE && OUT == LN3_OUT_BF16 && !HN), "narrow tiles: plain bf16 epilogue");
   constexpr int EW = gemm2_epi_warps<ACT>();
   constexpr int kABytes = BM * BK * 2, kBBytes = 128 * BK * 2;   // smem strides (the W box uses BN / 2 of its 128 rows)
   constexpr int kStageTx = (BM * BK + (BN / 2) * BK) * 2;        // bytes one CTA's two TMA loads deliver per stage
@@ -598,7 +600,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
 
   const int tiles_m = (p.M + 2 * BM - 1) / (2 * BM);
-  const int tiles_n = p.N / BN;
+  const int tiles_n = (p.N + BN - 1) / BN;
   const int num_tiles = tiles_m * tiles_n;
   const int num_kb = p.K / BK;
 
@@ -710,7 +712,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       while (next_item(t_dp, u, it)) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tm_base + acc * BN;
+        const uint32_t d_tmem = tm_base + acc * 256;
         for (int kb = it.kb0; kb < it.kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
@@ -740,7 +742,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   } else {
     const int quarter = warp & 3;
     const int slice = (warp - 2) >> 2;  // which slice of the tile's columns
-    constexpr int kSliceCols = BN / (EW / 4);   // 88 for the 176-wide tiles: the chunk loop's last 32-column load runs 8 past
+    constexpr int kSliceCols = BN / (EW / 4);
     int acc = 0;
     uint32_t acc_phase = 0;
     int t_dp = pair;
@@ -759,7 +761,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const int m = tm * 2 * BM + static_cast<int>(rank) * BM + quarter * 32 + lane;
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * 256;
       // this thread's row inside a partial-sum slot: [pair][rank][256 / 8 column groups][128 rows][8]
       float* my_part = p.sk_partials + (static_cast<long long>(pair) * 2 + rank) * (128 * 256) + (quarter * 32 + lane) * 8;
       if (it.mode == 1) {
@@ -797,8 +799,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           epilogue_cols<ACT, OUT, HN>(p, t_row, m, tn * BN, slice * kSliceCols, (slice + 1) * kSliceCols, bias_s + acc * 256,
                                       my_part + 2 * 128 * 256, it.mode == 2 ? it.nparts : 0);
         } else {
-          // 176 columns as [0, 96) | [96, 176): both slices start on a 16-column boundary (256-bit stores stay
-          // aligned); the second one ends inside its last 32-column chunk, and the last tile of a row at N
+          // BN columns as [0, 96) | [96, BN): both slices start on a 16-column boundary (aligned 256-bit stores); the
+          // 176-wide tile ends inside its last 32-column chunk, the last tile of a row at N (multiples of 8 columns)
           const int c_lo = slice * 96, c_hi = slice == 0 ? 96 : BN;
           epilogue_cols<ACT, OUT, HN>(p, t_row, m, tn * BN, c_lo, c_hi, bias_s + acc * 256, nullptr, 0,
                                       min(c_hi, p.N - tn * BN));
@@ -901,20 +903,27 @@ int gemm_bf16(const ln3_gemm_args* a, cudaStream_t stream) {
     if (!ok) use_pair = false;
   }
 
-  // 176-wide column tiles for the plain bf16 pair GEMM when they need fewer tile-rounds (cost = rounds x width)
-  bool narrow = false;
+  // narrower column tiles (192 or 176) for the plain bf16 pair GEMM when they need fewer tile-rounds: cost = rounds x width
+  int narrow = 0;
   if (use_pair && a->out_kind == LN3_OUT_BF16 && a->act == LN3_ACT_NONE && a->head_norm_w == nullptr) {
-    static const int bn_env = getenv("LN3_GEMM_BN") ? atoi(getenv("LN3_GEMM_BN")) : 0;   // 256 / 176 force, 0 = cost model
+    static const int bn_env = getenv("LN3_GEMM_BN") ? atoi(getenv("LN3_GEMM_BN")) : 0;   // 256 / 192 / 176 force, 0 = cost model
     const int pairs = device_sm_count() / 2;
     const long long tm = (a->M + 2 * BM - 1) / (2 * BM);
-    const long long t256 = tm * (a->N / 256), t176 = tm * ((a->N + 175) / 176);
-    const long long c256 = ((t256 + pairs - 1) / pairs) * 256, c176 = ((t176 + pairs - 1) / pairs) * 176;
-    narrow = bn_env == 176 || (bn_env == 0 && t256 > 1 && c176 * 100 < c256 * 95);
+    auto cost = [&](int w) { const long long t = tm * ((a->N + w - 1) / w); return ((t + pairs - 1) / pairs) * w; };
+    if (bn_env == 192 || bn_env == 176) {
+      narrow = bn_env;
+    } else if (bn_env == 0 && tm * (a->N / 256) > 1) {
+      const long long c256 = cost(256), c192 = cost(192), c176 = cost(176);
+      const long long best = c192 <= c176 ? c192 : c176;
+      // only when the model predicts >= 20 %: narrower tiles re-read the A operand once per column tile, and at
+      // M = 12288, K = 4096 (fc2: 6 instead of 4 passes over 100 MB) the predicted 8 % became 12 % slower
+      if (best * 100 < c256 * 80) narrow = c192 <= c176 ? 192 : 176;
+    }
   }
   CUtensorMap ta, tb;
   int rc = make_tmap_2d_bf16(&ta, a->A, a->M, a->K, a->lda, BM, BK);
   if (rc) return rc;
-  rc = make_tmap_2d_bf16(&tb, a->W, a->N, a->K, a->ldw, use_pair ? (narrow ? 88 : 128) : bn, BK);
+  rc = make_tmap_2d_bf16(&tb, a->W, a->N, a->K, a->ldw, use_pair ? (narrow ? narrow / 2 : 128) : bn, BK);
   if (rc) return rc;
 
   GemmParams p;
@@ -960,7 +969,8 @@ int gemm_bf16(const ln3_gemm_args* a, cudaStream_t stream) {
       if (a->act != LN3_ACT_NONE) return set_error(LN3_EUNSUPPORTED, "gemm: fp32 output with activation");
       return launch_gemm2<LN3_ACT_NONE, LN3_OUT_F32, false>(ta, tb, p, sms, a->workspace, a->workspace_bytes, stream);
     }
-    if (narrow) return launch_gemm2<LN3_ACT_NONE, LN3_OUT_BF16, false, 176>(ta, tb, p, sms, a->workspace, a->workspace_bytes, stream);
+    if (narrow == 192) return launch_gemm2<LN3_ACT_NONE, LN3_OUT_BF16, false, 192>(ta, tb, p, sms, a->workspace, a->workspace_bytes, stream);
+    if (narrow == 176) return launch_gemm2<LN3_ACT_NONE, LN3_OUT_BF16, false, 176>(ta, tb, p, sms, a->workspace, a->workspace_bytes, stream);
     switch (a->act) {
       case LN3_ACT_NONE: return launch_gemm2<LN3_ACT_NONE, LN3_OUT_BF16, false>(ta, tb, p, sms, a->workspace, a->workspace_bytes, stream);
       case LN3_ACT_GELU_ERF: {

@@ -44,8 +44,9 @@ def test_gemm_bf16(dev, M, N, K):
 @pytest.mark.parametrize("M,N,K", [(12288, 1024, 4096), (6144, 1024, 1024), (616, 768, 768), (2000, 1024, 64),
                                    (12288, 1024, 1024), (300, 512, 128)])
 def test_gemm_bf16_narrow_tile_shapes(dev, M, N, K):
-    """Shapes for which the host cost model picks the 176-column tiles of the CTA-pair GEMM (6 column tiles per 1024
-    columns, the last one 144 wide; ragged M): compared element-wise -- a column-addressing slip would not show in a norm."""
+    """Shapes around the host cost model's choice between 256- and 192-column tiles of the CTA-pair GEMM (6 column tiles
+    per 1024 columns, the last one 64 wide; ragged M): compared element-wise -- a column-addressing slip would not show
+    in a norm."""
     from ln3diff_b200 import ops
     g = torch.Generator().manual_seed(M + 3 * N + K)
     a = (torch.randn(M, K, generator=g) * 0.5).bfloat16()
