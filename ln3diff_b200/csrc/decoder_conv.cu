@@ -17,6 +17,8 @@
 //   patch_embed_triplane  grouped 2x2/s2 conv + the reference's channel interleave -> tokens
 // The decode is < 1 % of the pipeline's FLOPs (20 GFLOP / latent vs 307 TFLOP of sampling), so these
 // kernels favour exact fp32 parity with the reference over tensor-core throughput.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "ln3_internal.h"
 
@@ -208,7 +210,12 @@ int conv_nhwc(const ln3_conv_args* a, cudaStream_t stream) {
     return set_error(LN3_EINVAL, "conv: in_scale / in_shift must be given together");
   if (!a->x || !a->w || !a->out) return set_error(LN3_EINVAL, "conv: null pointer");
   const int tiles = ((a->H + kCT - 1) / kCT) * ((a->W + kCT - 1) / kCT);
-  const int cot = (a->Cout >= 64) ? 64 : 32;
+  // 64 output channels per CTA, or 32 when the 64-channel grid would leave the GPU under two CTAs per SM (the 16 x 16
+  // and 32 x 32 levels of the VAE decoder: 192 CTAs; the kernel is bound by the latency of its staging loads --
+  // ncu long_scoreboard 8.5 cycles per issue, 16 % warps active -- so more, smaller CTAs hide more of it)
+  static const bool cot_auto = !(getenv("LN3_CONV_COT64") && atoi(getenv("LN3_CONV_COT64")) != 0);
+  int cot = (a->Cout >= 64) ? 64 : 32;
+  if (cot == 64 && cot_auto && static_cast<long long>(tiles) * ((a->Cout + 63) / 64) * a->N < 2 * device_sm_count()) cot = 32;
   dim3 grid(tiles, (a->Cout + cot - 1) / cot, a->N);
   if (a->ksize == 3 && a->precision == LN3_MLP_TF32) {
     if (cot == 64) conv3x3_tf32_kernel<64><<<grid, 256, 0, stream>>>(*a);

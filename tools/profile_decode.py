@@ -13,4 +13,10 @@ lat = torch.randn(8, 12, 32, 32, device="cuda")
 for _ in range(n):
     out = dec.decode_to_channels_last(lat, in_mul=0.96806)
 torch.cuda.synchronize()
-print("done", tuple(out.shape))
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(n):
+    out = dec.decode_to_channels_last(lat, in_mul=0.96806)
+e1.record()
+torch.cuda.synchronize()
+print("done", tuple(out.shape), f"{e0.elapsed_time(e1) / n:.3f} ms per 8-latent decode, checksum {float(out.double().abs().mean()):.6f}")
