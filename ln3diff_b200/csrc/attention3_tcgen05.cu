@@ -84,7 +84,7 @@ __device__ __forceinline__ float exp2_poly(float x) {
   return __uint_as_float(__float_as_uint(q) + (__float_as_uint(t) << 23));
 }
 
-template <int kPolyPer8, bool ROTA, bool CHAIN = false>
+template <int kPolyPer8, bool ROTA, bool CHAIN = false, bool LAZYMAX = false>
 __global__ void __launch_bounds__(kThreads, 1)
 fmha3_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                  const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_k2,
@@ -380,31 +380,37 @@ fmha3_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             if (i > lim) s[i] = 0xff800000u;
         }
         const int c_end = kv_valid >= kKB ? kKB : (kv_valid + 15) & ~15;  // = 16 * PV k-steps
-        // three independent 3-input max chains
-        float mq[3];
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-          const int b0 = 32 * a;
-          mq[a] = fmax3(__uint_as_float(s[b0]), __uint_as_float(s[b0 + 1]), __uint_as_float(s[b0 + 2]));
-        }
-#pragma unroll
-        for (int i = 3; i < 31; i += 2) {
-#pragma unroll
-          for (int a = 0; a < 3; ++a)
-            mq[a] = fmax3(mq[a], __uint_as_float(s[32 * a + i]), __uint_as_float(s[32 * a + i + 1]));
-        }
-        const float mx = fmax3(fmax3(mq[0], mq[1], mq[2]), __uint_as_float(s[31]),
-                               fmaxf(__uint_as_float(s[63]), __uint_as_float(s[95])));
-        const float m_cand = mx * p.scale_log2;
+        // LAZYMAX: only the first block of an item pays a separate max pass.  Later blocks exponentiate against the
+        // running reference straight away and track their own maximum INSIDE the exponential loop (FMNMX on the ALU pipe,
+        // in the issue slots the XU-bound loop leaves free); if the block then turns out to exceed the reference by more
+        // than the lazy-rescale threshold -- rare: the threshold is 2^8 -- the block is redone against the new maximum.
         float alpha = 1.f;
         bool need = false;
-        if (j == 0) {
-          m_ref = m_cand;
-        } else if (m_cand > m_ref + kRescaleThreshold) {
-          need = true;
-          alpha = fast_exp2(m_ref - m_cand);
-          m_ref = m_cand;
-          l_run *= alpha;
+        if (!LAZYMAX || j == 0) {
+          // three independent 3-input max chains
+          float mq[3];
+#pragma unroll
+          for (int a = 0; a < 3; ++a) {
+            const int b0 = 32 * a;
+            mq[a] = fmax3(__uint_as_float(s[b0]), __uint_as_float(s[b0 + 1]), __uint_as_float(s[b0 + 2]));
+          }
+#pragma unroll
+          for (int i = 3; i < 31; i += 2) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+              mq[a] = fmax3(mq[a], __uint_as_float(s[32 * a + i]), __uint_as_float(s[32 * a + i + 1]));
+          }
+          const float mx = fmax3(fmax3(mq[0], mq[1], mq[2]), __uint_as_float(s[31]),
+                                 fmaxf(__uint_as_float(s[63]), __uint_as_float(s[95])));
+          const float m_cand = mx * p.scale_log2;
+          if (j == 0) {
+            m_ref = m_cand;
+          } else if (m_cand > m_ref + kRescaleThreshold) {
+            need = true;
+            alpha = fast_exp2(m_ref - m_cand);
+            m_ref = m_cand;
+            l_run *= alpha;
+          }
         }
         if (row == 0) LN3_TR3(t, g, 3);  // max done
         if (j == 0 && g > 0) {  // previous item's O tile left this buffer?  (long done; one barrier per item)
@@ -417,6 +423,7 @@ fmha3_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         rota_wait();
         if (row == 0) LN3_TR3(t, g, 5);  // permit
         float rs = 0.f;
+        float mb[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // LAZYMAX: running maxima of this block's scores
         auto exp_store = [&](auto full_tag) {
           constexpr bool FULL = decltype(full_tag)::value;
 #pragma unroll
@@ -427,6 +434,7 @@ fmha3_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             for (int i = 0; i < 8; ++i) {
               const float x = fmaf(__uint_as_float(s[c + i]), p.scale_log2, -m_ref);
               e[i] = (i < kPolyPer8) ? exp2_poly(x) : fast_exp2(x);
+              if constexpr (LAZYMAX) mb[i & 3] = fmaxf(mb[i & 3], __uint_as_float(s[c + i]));
             }
             rs += ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));
             const uint32_t addr = p_row + (c >> 6) * kQBytes + ((((c & 63) >> 3) ^ swz) << 4);
@@ -468,10 +476,27 @@ fmha3_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           }
         };
         if (kv_valid >= kKB) {
-          if constexpr (CHAIN) exp_store_chain();
+          if constexpr (CHAIN && !LAZYMAX) exp_store_chain();
           else exp_store(std::true_type{});
         } else {
           exp_store(std::false_type{});
+        }
+        if constexpr (LAZYMAX) {
+          if (j > 0) {
+            const float m_cand = fmaxf(fmaxf(mb[0], mb[1]), fmaxf(mb[2], mb[3])) * p.scale_log2;
+            need = m_cand > m_ref + kRescaleThreshold;
+            if (__any_sync(0xffffffffu, need)) {
+              // redo the block against the new reference (rows without `need` recompute the same values)
+              if (need) {
+                alpha = fast_exp2(m_ref - m_cand);
+                m_ref = m_cand;
+                l_run *= alpha;
+              }
+              rs = 0.f;
+              if (kv_valid >= kKB) exp_store(std::true_type{});
+              else exp_store(std::false_type{});
+            }
+          }
         }
         rota_done();
         if (row == 0) LN3_TR3(t, g, 6);  // exponentials done
@@ -540,7 +565,8 @@ fmha3_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 }  // namespace fmha3
 
 // Launcher; arguments were validated by fmha_fwd (attention_tcgen05.cu).  variant: bit 0 = rota off,
-// bit 1 = 2 of 8 exponentials on the FMA pipe, bit 2 = dependency-chained exponential loop (no polynomial).
+// bit 1 = 2 of 8 exponentials on the FMA pipe, bit 2 = dependency-chained exponential loop (no polynomial),
+// 9 = lazy block maximum (no rota, no polynomial).
 int fmha3_launch(const ln3_fmha_args* a, int variant, cudaStream_t stream) {
   using namespace fmha3;
   static DeviceOnce once;   // the shared-memory opt-in is per device
@@ -552,6 +578,7 @@ int fmha3_launch(const ln3_fmha_args* a, int variant, cudaStream_t stream) {
         set(fmha3_fwd_kernel<0, true>); set(fmha3_fwd_kernel<0, false>);
         set(fmha3_fwd_kernel<2, true>); set(fmha3_fwd_kernel<2, false>);
         set(fmha3_fwd_kernel<0, true, true>); set(fmha3_fwd_kernel<0, false, true>);
+        set(fmha3_fwd_kernel<0, false, false, true>);
         return e == cudaSuccess ? LN3_OK : set_error(LN3_ECUDA, "fmha3: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       }))
     return rc;
@@ -602,6 +629,7 @@ int fmha3_launch(const ln3_fmha_args* a, int variant, cudaStream_t stream) {
     LN3_F3(0, 0, true, false) LN3_F3(1, 0, false, false) LN3_F3(2, 2, true, false) LN3_F3(3, 2, false, false)
     LN3_F3(4, 0, true, true) LN3_F3(5, 0, false, true)
 #undef LN3_F3
+    case 9: le = launch_pdl(fmha3_fwd_kernel<0, false, false, true>, dim3(grid), dim3(kThreads), kSmem, stream, tq, tk, tv, tk2, tv2, to, p); break;
     default: return set_error(LN3_EINVAL, "fmha3: bad variant");
   }
   cudaError_t e = le != cudaSuccess ? le : cudaGetLastError();

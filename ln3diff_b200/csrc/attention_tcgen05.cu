@@ -675,7 +675,12 @@ int fmha_fwd(const ln3_fmha_args* a, cudaStream_t stream) {
     if (kv && atoi(kv) == 2) return -1;
     const char* ro = getenv("LN3_FMHA_ROTA");
     const char* po = getenv("LN3_FMHA_POLY");
+    const char* lz = getenv("LN3_FMHA_LAZYMAX");
     const char* ch = getenv("LN3_FMHA_CHAIN");
+    const bool plain = !(ro && atoi(ro) != 0) && !(po && atoi(po) == 2) && !(ch && atoi(ch) != 0);
+    // default: block maximum tracked inside the exponential loop (82.3 -> 80.3 us); LN3_FMHA_LAZYMAX=0 or any of the
+    // other knobs selects the separate max pass
+    if (plain && !(lz && atoi(lz) == 0)) return 9;
     const int chain = (ch && atoi(ch) != 0) ? 4 : 0;   // LN3_FMHA_CHAIN=1: dependency-chained exponential loop
     if (chain) return ((ro && atoi(ro) != 0) ? 0 : 1) | chain;
     return ((ro && atoi(ro) != 0) ? 0 : 1) | ((po && atoi(po) == 2) ? 2 : 0);   // bit 0 = rota OFF (default)
