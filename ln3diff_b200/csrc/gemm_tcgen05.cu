@@ -399,7 +399,8 @@ __device__ __forceinline__ void epilogue_cols(const GemmParams& p, uint32_t t_ro
   // Plain epilogues software-pipeline the TMEM loads (chunk c+1 in flight while c is stored).  The
   // activation epilogues run with 16 warps and a 96-register budget instead: no prefetch registers,
   // the other three warps of the scheduler cover the tcgen05.ld latency.
-  constexpr bool PREFETCH = ACT == LN3_ACT_NONE;
+  // (the head-norm epilogue holds a whole 64-column head per thread: with prefetch registers on top it spilled 1.5 KB)
+  constexpr bool PREFETCH = ACT == LN3_ACT_NONE && !HN;
   const bool row_ok = m < p.M;
   uint32_t v[CW], vn[PREFETCH ? CW : 1];
   if constexpr (PREFETCH) {
