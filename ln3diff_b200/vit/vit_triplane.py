@@ -131,17 +131,18 @@ class RodinSR_256_fusionv6_ConvQuant_liteSR_dinoInit3DAttn_SD_B_3L_C_withrollout
         x = P["pos"].expand(B, T, D).clone()   # the residual stream is updated in place: never alias the weights
         x2 = x.view(M, D)
         dev = latent.device
-        mod = torch.empty(M, 6 * D, device=dev, dtype=torch.float32)
+        # two modulation buffers, alternating per block: the deferred MLP residual of block i-1 is applied by block i's
+        # first pass with block i-1's per-token gate, which then still sits in the other buffer (no copy)
+        mods = (torch.empty(M, 6 * D, device=dev, dtype=torch.float32), torch.empty(M, 6 * D, device=dev, dtype=torch.float32))
         a = torch.empty(M, D, device=dev, dtype=torch.bfloat16)
         qkv = torch.empty(M, 3 * D, device=dev, dtype=torch.bfloat16)
         att = torch.empty(M, D, device=dev, dtype=torch.bfloat16)
         hbuf = torch.empty(M, int(vd.mlp_ratio) * D, device=dev, dtype=torch.bfloat16)
         val = torch.empty(M, D, device=dev, dtype=torch.bfloat16)
-        gate_prev = torch.empty(M, D, device=dev, dtype=torch.float32)   # gate_mlp of the previous block
+        mod = mods[0]
         for i, W in enumerate(P["blocks"]):
-            # deferred residual of the previous block's MLP uses that block's per-token gate
-            if i > 0:
-                gate_prev.copy_(mod[:, 5 * D:6 * D])
+            gate_prev = mod[:, 5 * D:6 * D]      # gate_mlp of the previous block (its buffer is not rewritten until block i+1)
+            mod = mods[i & 1]
             ops.gemm(sc2, W["ada_w"], W["ada_b"], out_kind=ops.OUT_F32, out=mod)   # per-token adaLN (B*768, 6D)
             sl = lambda j: mod[:, j * D:(j + 1) * D]
             ops.norm_modulate(x2, norm=NORM_LAYER, shift=sl(0), scale=sl(1), mod_rows=1, out=a,
