@@ -377,6 +377,10 @@ def test_decoder_conv_ops(dev):
     q, k, v = (torch.randn(3, 256, 128, generator=g) for _ in range(3))
     ref = torch.softmax(q @ k.transpose(1, 2) * 128 ** -0.5, -1) @ v
     assert _rel(ops.attn_single_head(q.to(dev), k.to(dev), v.to(dev)), ref) < 1e-5
+    for (n_, L_, C_) in [(2, 200, 64), (1, 37, 32), (2, 5, 128)]:      # ragged key blocks / query groups
+        q, k, v = (torch.randn(n_, L_, C_, generator=g) for _ in range(3))
+        ref = torch.softmax(q @ k.transpose(1, 2) * C_ ** -0.5, -1) @ v
+        assert _rel(ops.attn_single_head(q.to(dev), k.to(dev), v.to(dev)), ref) < 1e-5
 
 
 def test_vae_decoder_matches_reference_golden(dev, golden):
