@@ -84,6 +84,27 @@ __device__ __forceinline__ float exp2_poly(float x) {
   return __uint_as_float(__float_as_uint(q) + (__float_as_uint(t) << 23));
 }
 
+// two exponentials on the FMA pipe with packed fp32x2 arithmetic (see exp2_poly): half the issue slots of two scalar
+// polynomial exponentials
+__device__ __forceinline__ void exp2_poly2(uint64_t x2, float& e0, float& e1) {
+  float x0, x1;
+  upk2(x2, x0, x1);
+  x2 = pk2(fmaxf(x0, -126.f), fmaxf(x1, -126.f));
+  const uint64_t magic = pk2(12582912.f, 12582912.f), nmagic = pk2(-12582912.f, -12582912.f);
+  uint64_t t2;
+  asm("add.rm.ftz.f32x2 %0, %1, %2;" : "=l"(t2) : "l"(x2), "l"(magic));
+  const uint64_t f2 = fma2(add2(t2, nmagic), pk2(-1.f, -1.f), x2);
+  uint64_t q2 = fma2(f2, pk2(0.077119089663028717041015625f, 0.077119089663028717041015625f),
+                     pk2(0.227564394474029541015625f, 0.227564394474029541015625f));
+  q2 = fma2(f2, q2, pk2(0.695146143436431884765625f, 0.695146143436431884765625f));
+  q2 = fma2(f2, q2, pk2(1.f, 1.f));
+  float q0, q1, t0, t1;
+  upk2(q2, q0, q1);
+  upk2(t2, t0, t1);
+  e0 = __uint_as_float(__float_as_uint(q0) + (__float_as_uint(t0) << 23));
+  e1 = __uint_as_float(__float_as_uint(q1) + (__float_as_uint(t1) << 23));
+}
+
 template <int kPolyPer8, bool ROTA, bool CHAIN = false, bool LAZYMAX = false>
 __global__ void __launch_bounds__(kThreads, 1)
 fmha3_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
@@ -430,11 +451,31 @@ fmha3_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           for (int c = 0; c < kKB; c += 8) {
             if (!FULL && c >= c_end) break;
             float e[8];
+            if constexpr (LAZYMAX && kPolyPer8 == 2) {
+              // packed variant: the scale / subtract of all 8 elements and the two polynomial exponentials run on the
+              // fp32x2 FMA pipe (tools/microbench/exploop.cu: 3 370 -> 2 775 cycles per 128 exponentials at 3 warps per scheduler)
+              const uint64_t sc2 = pk2(p.scale_log2, p.scale_log2), nm2 = pk2(-m_ref, -m_ref);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float x = fmaf(__uint_as_float(s[c + i]), p.scale_log2, -m_ref);
-              e[i] = (i < kPolyPer8) ? exp2_poly(x) : fast_exp2(x);
-              if constexpr (LAZYMAX) mb[i & 3] = fmaxf(mb[i & 3], __uint_as_float(s[c + i]));
+              for (int i = 0; i < 8; i += 2) {
+                const uint64_t x2 = fma2(pk2(__uint_as_float(s[c + i]), __uint_as_float(s[c + i + 1])), sc2, nm2);
+                if (i < 2) {
+                  exp2_poly2(x2, e[i], e[i + 1]);
+                } else {
+                  float x0, x1;
+                  upk2(x2, x0, x1);
+                  e[i] = fast_exp2(x0);
+                  e[i + 1] = fast_exp2(x1);
+                }
+                mb[i & 3] = fmaxf(mb[i & 3], __uint_as_float(s[c + i]));
+                mb[(i + 1) & 3] = fmaxf(mb[(i + 1) & 3], __uint_as_float(s[c + i + 1]));
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float x = fmaf(__uint_as_float(s[c + i]), p.scale_log2, -m_ref);
+                e[i] = (i < kPolyPer8) ? exp2_poly(x) : fast_exp2(x);
+                if constexpr (LAZYMAX) mb[i & 3] = fmaxf(mb[i & 3], __uint_as_float(s[c + i]));
+              }
             }
             rs += ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));
             const uint32_t addr = p_row + (c >> 6) * kQBytes + ((((c & 63) >> 3) ^ swz) << 4);
@@ -578,7 +619,7 @@ int fmha3_launch(const ln3_fmha_args* a, int variant, cudaStream_t stream) {
         set(fmha3_fwd_kernel<0, true>); set(fmha3_fwd_kernel<0, false>);
         set(fmha3_fwd_kernel<2, true>); set(fmha3_fwd_kernel<2, false>);
         set(fmha3_fwd_kernel<0, true, true>); set(fmha3_fwd_kernel<0, false, true>);
-        set(fmha3_fwd_kernel<0, false, false, true>);
+        set(fmha3_fwd_kernel<0, false, false, true>); set(fmha3_fwd_kernel<2, false, false, true>);
         return e == cudaSuccess ? LN3_OK : set_error(LN3_ECUDA, "fmha3: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       }))
     return rc;
@@ -629,6 +670,7 @@ int fmha3_launch(const ln3_fmha_args* a, int variant, cudaStream_t stream) {
     LN3_F3(0, 0, true, false) LN3_F3(1, 0, false, false) LN3_F3(2, 2, true, false) LN3_F3(3, 2, false, false)
     LN3_F3(4, 0, true, true) LN3_F3(5, 0, false, true)
 #undef LN3_F3
+    case 10: le = launch_pdl(fmha3_fwd_kernel<2, false, false, true>, dim3(grid), dim3(kThreads), kSmem, stream, tq, tk, tv, tk2, tv2, to, p); break;
     case 9: le = launch_pdl(fmha3_fwd_kernel<0, false, false, true>, dim3(grid), dim3(kThreads), kSmem, stream, tq, tk, tv, tk2, tv2, to, p); break;
     default: return set_error(LN3_EINVAL, "fmha3: bad variant");
   }

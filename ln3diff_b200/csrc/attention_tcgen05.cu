@@ -681,6 +681,7 @@ int fmha_fwd(const ln3_fmha_args* a, cudaStream_t stream) {
     // default: block maximum tracked inside the exponential loop (82.3 -> 80.3 us); LN3_FMHA_LAZYMAX=0 or any of the
     // other knobs selects the separate max pass
     if (plain && !(lz && atoi(lz) == 0)) return 9;
+    if (lz && atoi(lz) == 2) return 10;   // LN3_FMHA_LAZYMAX=2: lazy maximum + packed 2-of-8 polynomial exponentials
     const int chain = (ch && atoi(ch) != 0) ? 4 : 0;   // LN3_FMHA_CHAIN=1: dependency-chained exponential loop
     if (chain) return ((ro && atoi(ro) != 0) ? 0 : 1) | chain;
     return ((ro && atoi(ro) != 0) ? 0 : 1) | ((po && atoi(po) == 2) ? 2 : 0);   // bit 0 = rota OFF (default)
