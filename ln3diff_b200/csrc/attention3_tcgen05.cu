@@ -38,6 +38,12 @@ namespace ln3 {
 
 namespace fmha3 {
 
+// every mbarrier wait of this kernel: try_wait with a suspend-time hint (Params::wait_ns; 0 = plain polling)
+__device__ __forceinline__ void wait3(uint64_t* bar, uint32_t parity, int ns) {
+  if (ns > 0) mbar_wait_hint(bar, parity, static_cast<uint32_t>(ns));
+  else mbar_wait(bar, parity);
+}
+
 static constexpr int kQT = 128;    // query rows per tile
 static constexpr int kNT = 3;      // query tiles (= softmax warpgroups) per CTA
 static constexpr int kKB = 96;     // kv rows per block
@@ -70,6 +76,7 @@ struct Params {
   float scale_log2;
   int full_items, n_split;  // tail schedule: see the file header
   int causal;               // key j visible to query i only when j <= i
+  int wait_ns;              // suspend-time hint of the mbarrier waits (LN3_FMHA_WAITHINT, default 2000; 0 = plain polling)
 };
 
 // 2^x on the FMA pipe (same polynomial as the two-warpgroup kernel; rel. error 8.8e-5 < bf16 rounding of P)
@@ -212,7 +219,7 @@ fmha3_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         int q0, head, batch;
         const int mask = sched(it, q0, head, batch);
         if (mask == 0) continue;
-        mbar_wait(q_empty, (n_items & 1) ^ 1);
+        wait3(q_empty, (n_items & 1) ^ 1, p.wait_ns);
         ++n_items;
         mbar_arrive_expect_tx(q_full, __popc(mask) * kQBytes);
         for (int t = 0; t < kNT; ++t)
@@ -221,10 +228,10 @@ fmha3_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           const CUtensorMap* mk = j < nkv1 ? &tmap_k : &tmap_k2;
           const CUtensorMap* mv = j < nkv1 ? &tmap_v : &tmap_v2;
           const int r0 = (j < nkv1 ? j : j - nkv1) * kKB;
-          mbar_wait(&k_empty[st], ph ^ 1);
+          wait3(&k_empty[st], ph ^ 1, p.wait_ns);
           mbar_arrive_expect_tx(&k_full[st], kKVBytes);
           tma_load_3d(sK + st * kKVBytes, mk, &k_full[st], head * kHD, r0, batch);
-          mbar_wait(&v_empty[st], ph ^ 1);
+          wait3(&v_empty[st], ph ^ 1, p.wait_ns);
           mbar_arrive_expect_tx(&v_full[st], kKVBytes);
           tma_load_3d(sV + st * kKVBytes, mv, &v_full[st], head * kHD, r0, batch);
           if (++st == kStages) st = 0, ph ^= 1;
@@ -277,10 +284,10 @@ fmha3_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 
     // S_t of the block under `cq` (or, when the item does not include this tile, only the ring releases)
     auto qk_step = [&]() {
-      if (cq.j == 0) mbar_wait(q_full, cq.items & 1);
-      mbar_wait(&k_full[cq.st], cq.ph);
+      if (cq.j == 0) wait3(q_full, cq.items & 1, p.wait_ns);
+      wait3(&k_full[cq.st], cq.ph, p.wait_ns);
       if (cq.mask >> t & 1) {
-        if (n_qk > 0) mbar_wait(&s_empty[t], (n_qk - 1) & 1);  // the previous S_t is in registers
+        if (n_qk > 0) wait3(&s_empty[t], (n_qk - 1) & 1, p.wait_ns);  // the previous S_t is in registers
         ++n_qk;
         tc_fence_after();
         const uint64_t kd = dK + static_cast<uint32_t>(cq.st) * kKVD;
@@ -303,12 +310,12 @@ fmha3_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       cur_next(cq);
     };
     auto pv_step = [&]() {
-      mbar_wait(&v_full[cp.st], cp.ph);
+      wait3(&v_full[cp.st], cp.ph, p.wait_ns);
       if (cp.mask >> t & 1) {
         const int kv_valid = (cp.j < nkv1) ? p.Lkv - cp.j * kKB : p.Lkv2 - (cp.j - nkv1) * kKB;
         const int ksteps = kv_valid >= kKB ? kKB / 16 : (kv_valid + 15) >> 4;  // P beyond is never written
         const uint64_t vd = dV + static_cast<uint32_t>(cp.st) * kKVD;
-        mbar_wait(&p_full[t], n_pv & 1);  // P_t in smem, O_t rescaled if needed
+        wait3(&p_full[t], n_pv & 1, p.wait_ns);  // P_t in smem, O_t rescaled if needed
         ++n_pv;
         LN3_TR3(3, seq, 3 + 2 * t);
         tc_fence_after();
@@ -352,7 +359,7 @@ fmha3_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     auto rota_wait = [&]() {
       if (!ROTA) return;
       const int n = t == 2 ? G : G - 1;   // the predecessor's phase count that must have finished
-      if (n >= 0) mbar_wait(&exp_done[2 * pred + (n & 1)], (n >> 1) & 1);
+      if (n >= 0) wait3(&exp_done[2 * pred + (n & 1)], (n >> 1) & 1, p.wait_ns);
     };
     auto rota_done = [&]() {
       if (!ROTA) return;
@@ -375,7 +382,7 @@ fmha3_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       for (int j = 0; j < nkv; ++j, ++g, ++G) {
         const int kv_valid = (j < nkv1) ? p.Lkv - j * kKB : p.Lkv2 - (j - nkv1) * kKB;  // >= 1
         if (row == 0) LN3_TR3(t, g, 0);  // start waiting for S
-        mbar_wait(&s_full[t], g & 1);
+        wait3(&s_full[t], g & 1, p.wait_ns);
         if (row == 0) LN3_TR3(t, g, 1);  // S ready
         tc_fence_after();
         uint32_t s[kKB];
@@ -439,7 +446,7 @@ fmha3_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           named_bar_sync(3 + t, kQT);
         }
         // P_t (smem) is read by P_t V of the previous block until o_full fires
-        if (g > 0) mbar_wait(&o_full[t], (g - 1) & 1);
+        if (g > 0) wait3(&o_full[t], (g - 1) & 1, p.wait_ns);
         if (row == 0) LN3_TR3(t, g, 4);  // O of previous block complete
         rota_wait();
         if (row == 0) LN3_TR3(t, g, 5);  // permit
@@ -563,7 +570,7 @@ fmha3_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         if (row == 0) LN3_TR3(t, g, 7);  // P handed to the tensor core
       }
       if (row == 0) LN3_TR3(t, g - 1, 8);   // epilogue: start waiting for the last P V
-      mbar_wait(&o_full[t], (g - 1) & 1);
+      wait3(&o_full[t], (g - 1) & 1, p.wait_ns);
       if (row == 0) LN3_TR3(t, g - 1, 9);   // O complete
       tc_fence_after();
       const float inv = 1.f / l_run;
@@ -644,6 +651,8 @@ int fmha3_launch(const ln3_fmha_args* a, int variant, cudaStream_t stream) {
   p.Lkv2 = two ? a->Lkv2 : 0;
   p.scale_log2 = a->scale * 1.4426950408889634f;
   p.causal = a->causal ? 1 : 0;
+  static const int wait_ns = getenv("LN3_FMHA_WAITHINT") ? atoi(getenv("LN3_FMHA_WAITHINT")) : 2000;
+  p.wait_ns = wait_ns;
   p.B = a->B;
   p.H = a->H;
   p.nq = (a->Lq + kNT * kQT - 1) / (kNT * kQT);

@@ -73,6 +73,32 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// try_wait with an explicit suspend-time hint (ns): the thread may sleep in hardware until the phase completes or the
+// time limit passes, instead of returning after the (short, implementation-defined) default slice -- a waiting warp
+// then stops feeding try_wait / branch pairs into the issue slots and the MIO queue of the math warps it shares a
+// scheduler with.
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait_hint(bar, parity, ns)) {
+    if (++spins == (1u << 22)) {
+      printf("ln3: mbarrier timeout block=(%d,%d,%d) thread=%d parity=%u\n", blockIdx.x, blockIdx.y, blockIdx.z,
+             threadIdx.x, parity);
+      __trap();
+    }
+  }
+}
+
 // ------------------------------------------------------------------ TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
