@@ -304,3 +304,33 @@ def test_general_conditioner_routing_cpu():
         bad = Tok(4, False)
         bad._emb_config = {}
         GeneralConditioner([bad])
+
+
+def test_conditioner_embedders_build_from_reference_layouts_and_refuse_cpu():
+    """The three embedders accept state dicts in the key layout the reference objects hold (`transformer.*`,
+    `model.visual.*`, dinov2 hub names under `model.`); there is no CPU fallback behind them."""
+    import pytest
+    import torch
+    from ln3diff_b200.sgm.modules.encoders.modules import (FrozenCLIPEmbedder, FrozenDinov2ImageEmbedder,
+                                                           FrozenOpenCLIPImageEmbedder)
+    from oracle import conditioners as oc
+    _, sd = oc.clip_text(depth=2)
+    te = FrozenCLIPEmbedder(device="cpu", always_return_pooled=True, state_dict=sd)
+    assert len(te.tower.layers) == 2 and te.tower.causal and te.token_embedding.shape == (49408, 768)
+    assert te.tower.layers[0].qkv_w.shape == (3 * 768, 768) and te.tower.layers[0].qkv_w.dtype == torch.bfloat16
+    _, sdv = oc.clip_vision(depth=1, width=256, mlp=1024, embed=128)
+    ce = FrozenOpenCLIPImageEmbedder(device="cpu", output_tokens=True, state_dict=sdv)
+    assert ce._conv_w.shape == (256, 640) and ce._embed_dim == 128 and ce.positional_embedding.shape == (257, 256)
+    _, sdd = oc.dinov2_reg(depth=1, width=256)
+    de = FrozenDinov2ImageEmbedder(device="cpu", state_dict=sdd)
+    assert de.register_tokens.shape == (1, 4, 256) and de.tower.layers[0].ls1.shape == (1, 256)
+    assert de.interpolate_pos_encoding(16).shape == (1, 257, 256)
+    assert de.interpolate_pos_encoding(8).shape == (1, 65, 256)           # bicubic down-interpolation of the table
+    if not torch.cuda.is_available():
+        with pytest.raises(ValueError, match="CUDA"):
+            te(torch.zeros(1, 77, dtype=torch.long))
+        with pytest.raises(ValueError, match="CUDA"):
+            de(torch.zeros(1, 3, 224, 224))
+        from ln3diff_b200 import mesh
+        with pytest.raises(ValueError, match="CUDA"):
+            mesh.marching_cubes(torch.zeros(4, 4, 4), 0.0)
