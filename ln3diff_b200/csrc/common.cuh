@@ -460,7 +460,7 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
 // Phi to [0, 1], which is also the right limit for |x| > 4 (x Q(16) = +-0.49997 |x| / 4).  7 issue slots per
 // element (FMUL2 + 8 FFMA2 + FMUL2 per pair, FMNMX + FFMA.SAT per element) against 12 FMA-pipe + 2 MUFU for
 // gelu_erf_fast -- the sampler is power-capped (profiles/r2_power_ops.json), so instructions are time.
-// Error (fp32 evaluation, |x| <= 8): |abs| <= 9e-6 for |x| < 4, relative <= 5e-4 where |GELU| > 0.01, and GELU is
+// Error (fp32 evaluation, |x| <= 8): |abs| <= 1.1e-5 for |x| < 4, relative <= 5e-4 where |GELU| > 0.01, and GELU is
 // flushed to 0 below x = -4 (true value > -1.3e-4): all below the bf16 rounding of the stored result (2^-9).
 __device__ __forceinline__ void gelu_erf_poly2(float& a, float& b) {
   const uint64_t x = pk2(a, b);

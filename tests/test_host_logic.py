@@ -334,3 +334,32 @@ def test_conditioner_embedders_build_from_reference_layouts_and_refuse_cpu():
         from ln3diff_b200 import mesh
         with pytest.raises(ValueError, match="CUDA"):
             mesh.marching_cubes(torch.zeros(4, 4, 4), 0.0)
+
+
+def test_gelu_polynomial_error_bounds_cpu():
+    """The packed-polynomial erf-GELU of the fc1 epilogue (csrc/common.cuh: gelu_erf_poly2), restated in float32 numpy
+    with the coefficients parsed from the source: the documented error bounds hold."""
+    import math
+    import os
+    import re
+    import numpy as np
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "ln3diff_b200", "csrc", "common.cuh")).read()
+    body = src[src.index("void gelu_erf_poly2("):]
+    body = body[:body.index("asm(\"fma.rn.sat.f32")]
+    coef = [float(c) for c in re.findall(r"pk2\((-?\d\.\d+e[+-]\d+)f,", body)]     # Horner order: highest degree first
+    assert len(coef) == 9
+    x = np.linspace(-8, 8, 200001).astype(np.float32)
+    u = np.minimum(x * x, np.float32(16.0)).astype(np.float32)
+    q = np.full_like(x, np.float32(coef[0]))
+    for c in coef[1:]:
+        q = (q * u + np.float32(c)).astype(np.float32)
+    phi = np.clip((x * q + np.float32(0.5)).astype(np.float32), 0.0, 1.0).astype(np.float32)
+    g = (x * phi).astype(np.float32)
+    ref = np.array([0.5 * v * (1.0 + math.erf(v / math.sqrt(2.0))) for v in x.astype(np.float64)])
+    err = np.abs(g - ref)
+    inside = np.abs(x) < 3.99
+    assert err[inside].max() < 1.2e-5
+    assert err.max() < 1.4e-4                                   # the flush to 0 just below x = -4
+    big = np.abs(ref) > 1e-2
+    assert (err[big] / np.abs(ref[big])).max() < 6e-4
+    assert np.all(g[x > 4.01] == x[x > 4.01]) and np.all(g[x < -4.01] == 0)
