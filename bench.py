@@ -600,12 +600,12 @@ def run_ours(args):
                 return e0.elapsed_time(e1) / n
             ids = torch.randint(3, 49000, (8, 77), generator=torch.Generator().manual_seed(9))
             ids[:, 30:] = 49407
-            te = FrozenCLIPEmbedder(device=dev, always_return_pooled=True)
+            te = FrozenCLIPEmbedder(device=dev, always_return_pooled=True, random_init=True)
             t_ms = _time(lambda: te(ids))
             del te
             img8 = torch.rand(8, 3, 224, 224, generator=torch.Generator().manual_seed(10)).to(dev) * 2 - 1
-            ce = FrozenOpenCLIPImageEmbedder(device=dev, output_tokens=True)
-            de = FrozenDinov2ImageEmbedder(device=dev)
+            ce = FrozenOpenCLIPImageEmbedder(device=dev, output_tokens=True, random_init=True)
+            de = FrozenDinov2ImageEmbedder(device=dev, random_init=True)
             i_ms = _time(lambda: (ce(img8), de(img8)))
             del ce, de
             cond = {"clip_text_prompts_per_s": 8 / t_ms * 1e3, "i23d_images_per_s": 8 / i_ms * 1e3,

@@ -7,9 +7,10 @@ and `FrozenDinov2ImageEmbedder` (:735-868, I23D) -- same class names, constructo
 Weights.  The reference constructors download pretrained weights (`CLIPTextModel.from_pretrained`,
 `open_clip.create_model_and_transforms`, `torch.hub.load`).  There is no network here: every embedder takes
 `state_dict=` with the keys the reference object would hold (`transformer.text_model.*` / `model.visual.*` /
-`model.*` of the dinov2 hub module; bare sub-module keys are accepted too) and builds random-init tensors of the
-right shapes when none is given (`pretrained=False`).  `pretrained=True` tries the reference's loader and raises
-if it cannot run.  CUDA only -- no CPU fallback.
+`model.*` of the dinov2 hub module; bare sub-module keys are accepted too).  Without one the constructor does what
+the reference does -- it calls the reference's own loader (`from_pretrained` / `open_clip` / `torch.hub`) -- and
+RAISES when that cannot run (no network, package absent): random weights are never substituted silently;
+`random_init=True` asks for them explicitly (benchmarks, tests).  CUDA only -- no CPU fallback.
 
 Third-party arithmetic restated here (file:line = reference call site):
   * transformers CLIPTextModel (:367): token + position embedding, causal pre-LN blocks with QuickGELU, final
@@ -208,6 +209,15 @@ def _pack_patch_weight(w: torch.Tensor, device) -> torch.Tensor:
     return out
 
 
+def _load_pretrained(what: str, loader):
+    """Run the reference's weight loader; a failure is an error, never a silent random initialisation."""
+    try:
+        return loader()
+    except Exception as e:  # noqa: BLE001 -- network / missing package / missing assets
+        raise RuntimeError(f"{what}: the reference's pretrained loader failed ({type(e).__name__}: {e}); pass "
+                           f"state_dict= (keys as the reference object holds them) or random_init=True") from e
+
+
 def _randn(*shape, std=0.02, g=None):
     return torch.randn(*shape, generator=g) * std
 
@@ -219,7 +229,7 @@ class FrozenCLIPEmbedder(AbstractEmbModel):
 
     def __init__(self, version="openai/clip-vit-large-patch14", device="cuda", max_length=77, freeze=True,
                  layer="last", layer_idx=None, always_return_pooled=False, *, state_dict: dict | None = None,
-                 pretrained: bool = False, tokenizer=None, vocab_size=49408, width=768, heads=12, depth=12,
+                 random_init: bool = False, tokenizer=None, vocab_size=49408, width=768, heads=12, depth=12,
                  mlp_dim=3072, eos_token_id=2, seed=0):
         super().__init__()
         assert layer in self.LAYERS
@@ -233,10 +243,11 @@ class FrozenCLIPEmbedder(AbstractEmbModel):
             assert layer_idx is not None
             assert 0 <= abs(layer_idx) <= 12
         self.tokenizer = tokenizer
-        if pretrained:
-            from transformers import CLIPTextModel, CLIPTokenizer   # the reference's own loader (:366-367)
-            self.tokenizer = CLIPTokenizer.from_pretrained(version)
-            state_dict = CLIPTextModel.from_pretrained(version).state_dict()
+        if state_dict is None and not random_init:
+            def _load():
+                from transformers import CLIPTextModel, CLIPTokenizer   # the reference's own loader (:366-367)
+                return CLIPTokenizer.from_pretrained(version), CLIPTextModel.from_pretrained(version).state_dict()
+            self.tokenizer, state_dict = _load_pretrained("FrozenCLIPEmbedder", _load)
         if state_dict is None:
             g = torch.Generator().manual_seed(seed)
             sd = {"text_model.embeddings.token_embedding.weight": _randn(vocab_size, width, g=g),
@@ -358,15 +369,17 @@ class FrozenOpenCLIPImageEmbedder(_ImageEmbedderBase):
 
     def __init__(self, arch="ViT-L-14", version="openai", device="cuda", max_length=77, freeze=True, antialias=True,
                  ucg_rate=0.0, unsqueeze_dim=False, repeat_to_max_len=False, num_image_crops=0, output_tokens=False,
-                 init_device=None, *, state_dict: dict | None = None, pretrained: bool = False, width=1024, heads=16,
+                 init_device=None, *, state_dict: dict | None = None, random_init: bool = False, width=1024, heads=16,
                  depth=24, mlp_dim=4096, embed_dim=768, patch=14, image_size=224, seed=0):
         super().__init__()
         self._init_common(device, max_length, antialias, ucg_rate, unsqueeze_dim, repeat_to_max_len, num_image_crops,
                           output_tokens)
-        if pretrained:
-            import open_clip   # the reference's own loader (:600-604); not in this image
-            model, _, _ = open_clip.create_model_and_transforms(arch, device=torch.device("cpu"), pretrained=version)
-            state_dict = {"model." + k: v for k, v in model.state_dict().items()}
+        if state_dict is None and not random_init:
+            def _load():
+                import open_clip   # the reference's own loader (:600-604); not in this image
+                model, _, _ = open_clip.create_model_and_transforms(arch, device=torch.device("cpu"), pretrained=version)
+                return {"model." + k: v for k, v in model.state_dict().items()}
+            state_dict = _load_pretrained("FrozenOpenCLIPImageEmbedder", _load)
         if state_dict is None:
             g = torch.Generator().manual_seed(seed)
             n = (image_size // patch) ** 2 + 1
@@ -475,7 +488,7 @@ class FrozenDinov2ImageEmbedder(_ImageEmbedderBase):
 
     def __init__(self, arch="vitl", version="dinov2", device="cuda", max_length=77, freeze=True, antialias=True,
                  ucg_rate=0.0, unsqueeze_dim=False, repeat_to_max_len=False, num_image_crops=0, output_tokens=False,
-                 output_cls=False, init_device=None, *, state_dict: dict | None = None, pretrained: bool = False,
+                 output_cls=False, init_device=None, *, state_dict: dict | None = None, random_init: bool = False,
                  width=1024, depth=24, mlp_dim=4096, patch=14, num_register_tokens=4, pos_grid=37,
                  interpolate_antialias=True, interpolate_offset=0.0, seed=0):
         super().__init__()
@@ -483,9 +496,11 @@ class FrozenDinov2ImageEmbedder(_ImageEmbedderBase):
                           output_tokens)
         self.output_cls = output_cls
         self.interpolate_antialias, self.interpolate_offset = interpolate_antialias, interpolate_offset
-        if pretrained:
-            model = torch.hub.load(f"facebookresearch/{version}", f"{version}_{arch}14_reg", pretrained=True)  # :760-765
-            state_dict = {"model." + k: v for k, v in model.state_dict().items()}
+        if state_dict is None and not random_init:
+            def _load():
+                model = torch.hub.load(f"facebookresearch/{version}", f"{version}_{arch}14_reg", pretrained=True)  # :760-765
+                return {"model." + k: v for k, v in model.state_dict().items()}
+            state_dict = _load_pretrained("FrozenDinov2ImageEmbedder", _load)
         if state_dict is None:
             g = torch.Generator().manual_seed(seed)
             sd = {"cls_token": _randn(1, 1, width, g=g), "register_tokens": _randn(1, num_register_tokens, width, g=g),

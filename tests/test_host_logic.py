@@ -363,3 +363,15 @@ def test_gelu_polynomial_error_bounds_cpu():
     big = np.abs(ref) > 1e-2
     assert (err[big] / np.abs(ref[big])).max() < 6e-4
     assert np.all(g[x > 4.01] == x[x > 4.01]) and np.all(g[x < -4.01] == 0)
+
+
+def test_conditioner_never_substitutes_random_weights_silently():
+    """Without state_dict= the embedders call the reference's loaders; offline those fail, and that is an error."""
+    import pytest
+    from ln3diff_b200.sgm.modules.encoders.modules import FrozenDinov2ImageEmbedder, FrozenOpenCLIPImageEmbedder
+    with pytest.raises(RuntimeError, match="pretrained loader failed"):
+        FrozenOpenCLIPImageEmbedder(device="cpu")          # open_clip is not installed
+    with pytest.raises(RuntimeError, match="pretrained loader failed"):
+        FrozenDinov2ImageEmbedder(device="cpu")            # torch.hub needs the network
+    m = FrozenDinov2ImageEmbedder(device="cpu", random_init=True, depth=1, width=128)
+    assert len(m.tower.layers) == 1
